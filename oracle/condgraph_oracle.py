@@ -237,8 +237,10 @@ def dbscan_location_mask(act_fg, feature, eps, thr, use_sklearn=True):
 
 
 def target_node_indices(act_maps, features, eps, thr, use_sklearn=True, sampling="dbscan", plabel_th=0.9):
-    """loss.py:464-518.  Returns (lv, rows, plabels) or (None, None, None)."""
+    """loss.py:464-518.  Returns (lv, rows, plabels, per-level masks); the first three are None
+    when no level has a positive location."""
     neg, pos = [], []
+    masks = []
     for l, (act, feat) in enumerate(zip(act_maps, features)):
         k = act.shape[1]
         flat_act = act.permute(0, 2, 3, 1).reshape(-1, k)
@@ -248,6 +250,7 @@ def target_node_indices(act_maps, features, eps, thr, use_sklearn=True, sampling
             conf = (flat_act[:, 1:] > plabel_th).sum(-1).bool()      # loss.py:479-481
         else:
             raise KeyError("unknown target labels!")
+        masks.append(conf)
         if bool(conf.any()):
             p = torch.nonzero(conf).reshape(-1)
             n_ = torch.nonzero(~conf).reshape(-1)
@@ -259,12 +262,12 @@ def target_node_indices(act_maps, features, eps, thr, use_sklearn=True, sampling
             pos.append((l, p, plab))
             neg.append((l, sel, torch.zeros_like(sel)))
     if not pos:
-        return None, None, None
+        return None, None, None, masks
     seq = neg + pos
     lv = torch.cat([torch.full_like(idx, l) for l, idx, _ in seq])
     rows = torch.cat([idx for _, idx, _ in seq])
     labs = torch.cat([lb for _, _, lb in seq])
-    return lv, rows, labs
+    return lv, rows, labs, masks
 
 
 # --------------------------------------------------------------------------------------
@@ -667,15 +670,21 @@ class OracleCondGraph(nn.Module):
             return self.post(feats, acts), (node_loss, 0), loss, acts
         if self.training and mode == "target" and forward_target:
             acts = [self.act_of(self.dynamic_conv(f, self.conded_weight())) for f in feats]
-            lv, rows, plab = target_node_indices(acts, feats, mh.DBSCAN_EPS, mh.DBSCAN_THR, self.use_sklearn,
-                                                 mh.TARGET_SAMPLING_CFG, self.cfg.SOLVER.MIDDLE_HEAD.PLABEL_TH[0])
+            lv, rows, plab, masks = target_node_indices(
+                acts, feats, mh.DBSCAN_EPS, mh.DBSCAN_THR, self.use_sklearn,
+                mh.TARGET_SAMPLING_CFG, self.cfg.SOLVER.MIDDLE_HEAD.PLABEL_TH[0])
             self.last.update(node_level=lv, node_rows=rows, node_labels=plab)
+            if mh.TARGET_SAMPLING_CFG == "dbscan":
+                self.last["dbscan_masks"] = masks
             out = self.post(feats, acts)
             if lv is not None and (mh.TRANSFER_CFG[0] is not None or mh.GCN_SELF_TRAINING):
                 nodes = gather_nodes(feats, lv, rows)
                 node_loss, tg_proto = self.forward_gcns(nodes, plab)
                 node_loss = mh.GCN_LOSS_WEIGHT_TG * node_loss
-                tl = self.transfer_loss(tg_proto, nodes, plab)
+                # with GLOBAL_GCN=False the reference has overwritten the sampled rows IN PLACE with the
+                # GCN outputs (condgraph.py:413) before it reaches get_transfer_loss (:526)
+                tl_nodes = nodes if mh.GLOBAL_GCN else self.last["nodes_out"]
+                tl = self.transfer_loss(tg_proto, tl_nodes, plab)
                 if tl is not None and bool(tl):
                     tl = mh.CON_LOSS_WEIGHT * tl
                 if mh.GCN_SELF_TRAINING:
