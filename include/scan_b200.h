@@ -1,0 +1,210 @@
+/*
+ * scan_b200 C ABI -- the drop-in boundary of the B200-native condgraph middle head.
+ *
+ * Conventions (they mirror the native-op convention of the reference's
+ * fcos_core/csrc, e.g. csrc/cuda/SigmoidFocalLoss_cuda.cu:103-188 and csrc/SigmoidFocalLoss.h:10-41,
+ * minus the at::Tensor types):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns and pre-allocates every buffer (torch on the Python side) and passes the CUDA
+ *     stream the work must be enqueued on (`stream` is a cudaStream_t cast to void*; NULL = legacy stream);
+ *   - the callee never allocates device memory, never synchronises and never touches another stream;
+ *   - return value: 0 on success, a negative SCAN_E* code otherwise (`scan_strerror`); the Python shim
+ *     turns it into RuntimeError, like AT_ERROR / AT_ASSERTM in the reference;
+ *   - dynamic counts (number of sampled nodes, DBSCAN points, ...) are produced in device-side int32
+ *     records and read by the caller when it needs them;
+ *   - "rows" layout: the pixels of all FPN levels of all images as one [R, C] row-major fp32 matrix in
+ *     the reference's own flattening order -- level first, then image, then y, then x
+ *     (`features[l].permute(0,2,3,1).reshape(-1,C)` of loss.py:440 concatenated over levels as in
+ *     loss.py:289-294, condgraph.py:348-351).  Row g of level l, image n, pixel (y,x):
+ *         g = row_off[l] + (n*H_l + y)*W_l + x,   row_off[l] = N * sum_{j<l} H_j*W_j.
+ *   - every entry point is safe to call twice on the same saved tensors (the reference back-propagates
+ *     the source graph twice, engine/trainer.py:299,343): inputs are never modified.
+ *
+ * All file:line citations are relative to /root/reference/fcos_core/.
+ */
+#ifndef SCAN_B200_H_
+#define SCAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAN_ABI_VERSION 1
+#define SCAN_MAX_LEVELS 8
+#define SCAN_MAX_CLASSES 16 /* K = used_num_classes <= 16 (one tcgen05 N=16 tile) */
+
+enum {
+  SCAN_OK = 0,
+  SCAN_EINVAL = -1,   /* bad argument (shape, alignment, K > SCAN_MAX_CLASSES ...) */
+  SCAN_ECUDA = -2,    /* a CUDA runtime / driver call failed; see scan_last_cuda_error() */
+  SCAN_ENOTSUP = -3,  /* configuration not supported by this build */
+  SCAN_ECAPACITY = -4 /* caller-provided workspace too small */
+};
+
+int scan_abi_version(void);
+const char* scan_strerror(int code);
+const char* scan_last_cuda_error(void);
+/* bytes of dynamic shared memory / SM count etc. are queried lazily; this forces it (returns 0 / SCAN_ECUDA) */
+int scan_init(int device);
+
+/* ---- geometry ------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_levels;                     /* <= SCAN_MAX_LEVELS */
+  int32_t n_images;                     /* N */
+  int32_t h[SCAN_MAX_LEVELS];           /* H_l */
+  int32_t w[SCAN_MAX_LEVELS];           /* W_l */
+  int32_t stride[SCAN_MAX_LEVELS];      /* FPN stride of the level (MODEL.FCOS.FPN_STRIDES) */
+} scan_levels_t;
+
+/* ---- layout: NCHW <-> rows (replaces features[l].permute(0,2,3,1).reshape(-1,C), loss.py:440) -- */
+/* nchw_host: host array of n_levels device pointers, level l is [N, C, H_l, W_l] fp32 contiguous. */
+int scan_pack_rows(const scan_levels_t* lv, const void* const* nchw_host, int32_t channels,
+                   float* rows, void* stream);
+/* rows [R, C] -> nchw (overwrite when accumulate == 0, += otherwise): the backward of scan_pack_rows */
+int scan_unpack_rows(const scan_levels_t* lv, const float* rows, int32_t channels,
+                     void* const* nchw_host, int32_t accumulate, void* stream);
+
+/* ---- K1a: FCOS ground-truth assignment (loss.py:262-343, PrototypeComputation.prepare_targets +
+ *      compute_targets_for_locations; locations of condgraph.py:631-655 are computed from the index) --
+ * boxes      [N, g_max, 4] fp32 xyxy, box_labels [N, g_max] int64, box_count [N] int32 (1..g_max)
+ * labels_out [R] int64, rows layout.  Bit-exact with the reference (fp32, no FMA contraction). */
+int scan_fcos_assign(const scan_levels_t* lv, const float* boxes, const int64_t* box_labels,
+                     const int32_t* box_count, int32_t g_max, int64_t* labels_out, void* stream);
+
+/* ---- K1b: node sampling (loss.py:430-458 source branch; loss.py:497-516 target branch) ---------
+ * mode 0 (source): positive <=> labels[g] > 0, node label = labels[g]; per level all negatives when
+ *                  n_pos > n_neg, else the floor(linspace(0, n_neg-2, n_pos)) rows of the negative list;
+ *                  with_bg == 0 drops the negatives (PROTO_WITH_BG False).
+ * mode 1 (target): positive <=> pos_mask[g] != 0, node label = plabel[g]; levels without a positive
+ *                  contribute nothing; n_pos negatives by floor(linspace(0, n_neg-2, n_pos)) (negative
+ *                  indices wrap like Python indexing; n_neg == 0 sets meta.error = 1: the reference
+ *                  raises IndexError there).
+ * Node order: [neg(level 0..), pos(level 0..)].  Outputs: node_rows int32 [cap], node_labels int64 [cap],
+ * meta (device): see scan_sample_meta_t.  workspace: scan_sample_workspace_bytes(R). */
+typedef struct {
+  int32_t n_nodes;                      /* M */
+  int32_t n_neg_nodes;                  /* nodes [0, n_neg_nodes) are negatives */
+  int32_t error;                        /* 0 ok, 1 = no negative row left at a level with positives, 2 = cap too small */
+  int32_t reserved;
+  int32_t n_pos[SCAN_MAX_LEVELS];
+  int32_t n_neg[SCAN_MAX_LEVELS];
+  int32_t n_neg_sel[SCAN_MAX_LEVELS];
+  int32_t neg_off[SCAN_MAX_LEVELS];     /* first node index of the level's negatives */
+  int32_t pos_off[SCAN_MAX_LEVELS];     /* first node index of the level's positives */
+} scan_sample_meta_t;
+
+int64_t scan_sample_workspace_bytes(int64_t n_rows);
+int scan_sample_nodes(const scan_levels_t* lv, int32_t mode, int32_t with_bg, const int64_t* labels,
+                      const uint8_t* pos_mask, const int64_t* plabel, int32_t* node_rows,
+                      int64_t* node_labels, int32_t cap, scan_sample_meta_t* meta, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* ---- K1c: gather / scatter of node rows ------------------------------------------------------ */
+/* out[i, :] = rows[node_rows[i], :], i < n_nodes (C % 4 == 0) */
+int scan_gather_rows(const float* rows, const int32_t* node_rows, int32_t n_nodes, int32_t channels,
+                     float* out, void* stream);
+/* d_rows[node_rows[i], :] += d_nodes[i, :] (repeated indices allowed) */
+int scan_scatter_add_rows(const float* d_nodes, const int32_t* node_rows, int32_t n_nodes,
+                          int32_t channels, float* d_rows, void* stream);
+
+/* ---- K4b: conditional 1x1 convolution + activation + focal loss (condgraph.py:619-629 dynamic_conv,
+ *      :338-370 get_act_loss; layers/sigmoid_focal_loss_wbg.py:7-64 FocalLoss, :148-177 BCEFocalLoss) --
+ * rows [R, 256] fp32, weight [K, 256], bias [K] or NULL (COND_WITH_BIAS).
+ * act_mode 0: softmax over K (softmaxFL / no loss), 1: sigmoid (sigmoidFL).
+ * act_nchw_host: host array of n_levels device pointers, level l is [N, K, H_l, W_l]: the activation maps
+ *                in the reference's own layout.
+ * labels [R] int64 or NULL; when given, loss_partials[i] (fp64, i < scan_condconv_num_partials()) receives
+ * per-CTA partial sums of the UN-normalised focal loss (caller divides by R for softmaxFL and by 2R for
+ * sigmoidFL and multiplies by ACT_LOSS_WEIGHT); flags[0] is set when a p_t < 1e-15 was clamped.
+ * Arithmetic: tcgen05.mma kind::tf32 with fp32 accumulation in TMEM (impl 0) or fp32 FFMA (impl 1,
+ * verification kernel); tolerance of impl 0 against the fp32 reference: rtol 1e-3. */
+int32_t scan_condconv_num_partials(void);
+int scan_condconv_fwd(const scan_levels_t* lv, const float* rows, const float* weight, const float* bias,
+                      int32_t num_classes, int32_t act_mode, void* const* act_nchw_host,
+                      const int64_t* labels, double* loss_partials, int32_t* flags, int32_t impl,
+                      void* stream);
+/* Backward.  d_act_nchw_host: upstream gradient w.r.t. the activation maps (NULL entries = zero),
+ * loss_scale: ACT_LOSS_WEIGHT / normaliser (0 when there is no act loss); d_loss: device scalar
+ * d(total)/d(act_loss) or NULL (= 1), read on the device so that backward needs no host sync.
+ * Outputs: d_rows [R,256] (overwritten), d_weight [K,256] and d_bias [K] (overwritten; d_bias may be NULL).
+ * workspace: scan_condconv_bwd_workspace_bytes(). */
+int64_t scan_condconv_bwd_workspace_bytes(int32_t num_classes);
+int scan_condconv_bwd(const scan_levels_t* lv, const float* rows, const float* weight,
+                      int32_t num_classes, int32_t act_mode, const void* const* act_nchw_host,
+                      const void* const* d_act_nchw_host, const int64_t* labels, float loss_scale,
+                      const float* d_loss, float* d_rows, float* d_weight, float* d_bias, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* ---- K3a: graph aggregation, global variant (layers/transformer.py:5-90 dot_attention inside
+ *      MultiHeadAttention, called at condgraph.py:390-393) ----------------------------------------
+ * q,k,v [M,256] are the three linear projections.  The reference's .view(4,-1,64) makes 4 independent
+ * chunks of M sub-tokens of 64 dims: chunk b owns sub-token rows [b*M,(b+1)*M) of the
+ * row-major [4M,64] reinterpretation.  ctx [M,256] (same reinterpretation), lse [4M] (log-sum-exp of the
+ * scaled scores, saved for backward).  scale = 0.25.  dropout_p > 0 applies a counter-based Bernoulli
+ * mask keyed by (seed, chunk, i, j) to the probabilities (train-mode nn.Dropout of transformer.py:31). */
+int scan_attn_fwd(const float* q, const float* k, const float* v, int32_t m, float scale,
+                  float dropout_p, uint64_t seed, float* ctx, float* lse, void* stream);
+int scan_attn_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* lse,
+                  const float* d_ctx, int32_t m, float scale, float dropout_p, uint64_t seed,
+                  float* dq, float* dk, float* dv, float* delta_ws, void* stream);
+
+/* ---- K3b: per-class prototype sums + paradigm EMA (condgraph.py:395-398 class means;
+ *      :558-617 update_prototype / _nx1 / _nx1_rnn) -------------------------------
+ * scan_class_sums: sums[c, :] = sum of nodes with label c + label_shift... , sums[K*C + c] = count
+ *   nodes [M, C], labels [M] int64 (class c <=> labels == c + label_shift), out: packed [K, C+1] fp32
+ *   (row c = sum over nodes, last column = count) -- the buffer the multi-GPU all-reduce operates on. */
+int scan_class_sums(const float* nodes, const int64_t* labels, int32_t m, int32_t channels,
+                    int32_t num_classes, int32_t label_shift, float* packed_sums, void* stream);
+/* scan_proto_update: batch[c] = sums[c]/count[c] (0 where count == 0), exist = (sum_j batch[c][j] != 0),
+ *   then EMA into prototype [K, C, P] (P == 1: [K, C]) slot `slot` with momentum = cosine(old, batch)
+ *   (cosine_on) or `momentum`; shift != 0 first moves slots 1..P-1 down by one for ALL classes
+ *   (counter == PROTO_ITER case of update_prototype_nx1_rnn).  proto_batch_out [K, C] receives batch. */
+int scan_proto_update(const float* packed_sums, int32_t num_classes, int32_t channels, int32_t proto_iter,
+                      int32_t slot, int32_t shift, int32_t cosine_on, float momentum, float* prototype,
+                      float* proto_batch_out, void* stream);
+
+/* ---- K2: DBSCAN target-node sampling (loss.py:397-423 DBSCAN_batch_cpu; sklearn.cluster.DBSCAN
+ *      eps=DBSCAN_EPS, min_samples=5, euclidean, brute) ------------------------------------------------
+ * One level per call.  act_nchw [N, K, H, W] (channel 0 = background), rows_level = first row of the
+ * level in `rows` [R,256].  Steps (all on device, no host sync):
+ *   select   entries (n, cls>=1, y, x) with act > thr in flat order ((n*CLS+cls-1)*H+y)*W+x;
+ *   points   p_i = fl32(rows[g_i, :] * act_i)                                  (n_points x 256, workspace);
+ *   neighbours  d2 = |p_i|^2 + |p_j|^2 - 2 p_i.p_j evaluated in fp32 tiles, pairs within a band around
+ *            eps^2 re-evaluated in fp64 exactly as sklearn does (float64 accumulation of fp32 inputs);
+ *   core = #neighbours(incl. self) >= min_samples; union-find over core-core edges; cluster id = rank of
+ *   the component's smallest index; border point -> smallest cluster id among its core neighbours; else -1.
+ *   location mask: entry value = 1 for noise, 0 for cluster 0, id otherwise (loss.py:417-418); a location
+ *   is positive iff any of its class entries is non-zero (loss.py:420-421); clustering is skipped (every
+ *   selected entry positive) iff all selected points are exactly zero (loss.py:415).
+ * Outputs: pos_mask [N*H*W] uint8, plabel [N*H*W] int64 = argmax_{c>=1} act + 1 (loss.py:500),
+ *          point_labels int32 [cap] (sklearn labels, for tests), info (device int32[8]):
+ *          [0] n_points, [1] n_clusters, [2] n_noise, [3] skipped, [4] error (1 = cap exceeded), [5] n_recheck.
+ * workspace: scan_dbscan_workspace_bytes(cap). */
+int64_t scan_dbscan_workspace_bytes(int64_t cap_points);
+int scan_dbscan_level(const float* rows_level, const float* act_nchw, int32_t n_images, int32_t num_classes,
+                      int32_t h, int32_t w, float thr, double eps, int32_t min_samples, int32_t cap_points,
+                      uint8_t* pos_mask, int64_t* plabel, int32_t* point_labels, int32_t* info,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+/* Stand-alone clustering of an explicit point set [n, dim] fp32 (dim % 4 == 0): labels int32 [n]. */
+int scan_dbscan_points(const float* points, int32_t n, int32_t dim, double eps, int32_t min_samples,
+                       int32_t* labels, int32_t* info, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* ---- K5: sigmoid focal loss (csrc/cuda/SigmoidFocalLoss_cuda.cu:21-101, the `_C.sigmoid_focalloss_*`
+ *      pair wrapped by layers/sigmoid_focal_loss.py:9-37) and TEST.MODE ensembling (fcos.py:162-169) -- */
+int scan_sigmoid_focal_fwd(const float* logits, const int32_t* targets, int64_t n_rows, int32_t num_classes,
+                           float gamma, float alpha, float* losses, void* stream);
+int scan_sigmoid_focal_bwd(const float* logits, const int32_t* targets, const float* d_losses,
+                           int64_t n_rows, int32_t num_classes, float gamma, float alpha, float* d_logits,
+                           void* stream);
+/* mode 0 'common': out = sigmoid(cls); 1 'light': out = act[:,1:]; 2 'precision': 0.5*sigmoid(cls)+0.5*act[:,1:]
+ * cls [N, K-1, H, W] (may be NULL for light), act [N, K, H, W], out [N, K-1, H, W]; hw = H*W */
+int scan_ensemble(const float* cls_logits, const float* act, int32_t n_images, int32_t num_classes,
+                  int64_t hw, int32_t mode, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAN_B200_H_ */

@@ -1,0 +1,97 @@
+"""ctypes binding of the C-ABI library `libscan_b200.so` (include/scan_b200.h).
+
+The library is the product: there is NO fallback.  If it is missing or fails to load, importing an op
+raises; if a call returns a negative code, `check()` raises RuntimeError (the reference turns AT_ERROR /
+AT_ASSERTM into RuntimeError the same way, csrc/SigmoidFocalLoss.h:20-23).
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscan_b200.so")
+
+SCAN_MAX_LEVELS = 8
+SCAN_MAX_CLASSES = 16
+
+
+class ScanLevels(ctypes.Structure):
+    _fields_ = [("n_levels", c_int32), ("n_images", c_int32),
+                ("h", c_int32 * SCAN_MAX_LEVELS), ("w", c_int32 * SCAN_MAX_LEVELS),
+                ("stride", c_int32 * SCAN_MAX_LEVELS)]
+
+
+class ScanSampleMeta(ctypes.Structure):
+    _fields_ = [("n_nodes", c_int32), ("n_neg_nodes", c_int32), ("error", c_int32), ("reserved", c_int32),
+                ("n_pos", c_int32 * SCAN_MAX_LEVELS), ("n_neg", c_int32 * SCAN_MAX_LEVELS),
+                ("n_neg_sel", c_int32 * SCAN_MAX_LEVELS), ("neg_off", c_int32 * SCAN_MAX_LEVELS),
+                ("pos_off", c_int32 * SCAN_MAX_LEVELS)]
+
+
+_P = c_void_p
+_LV = ctypes.POINTER(ScanLevels)
+
+# name -> (restype, argtypes): every symbol include/scan_b200.h declares
+SIGNATURES = {
+    "scan_abi_version": (c_int32, []),
+    "scan_strerror": (c_char_p, [c_int32]),
+    "scan_last_cuda_error": (c_char_p, []),
+    "scan_init": (c_int32, [c_int32]),
+    "scan_pack_rows": (c_int32, [_LV, _P, c_int32, _P, _P]),
+    "scan_unpack_rows": (c_int32, [_LV, _P, c_int32, _P, c_int32, _P]),
+    "scan_fcos_assign": (c_int32, [_LV, _P, _P, _P, c_int32, _P, _P]),
+    "scan_sample_workspace_bytes": (c_int64, [c_int64]),
+    "scan_sample_nodes": (c_int32, [_LV, c_int32, c_int32, _P, _P, _P, _P, _P, c_int32, _P, _P, c_int64, _P]),
+    "scan_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
+    "scan_scatter_add_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
+    "scan_condconv_num_partials": (c_int32, []),
+    "scan_condconv_fwd": (c_int32, [_LV, _P, _P, _P, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
+    "scan_condconv_bwd_workspace_bytes": (c_int64, [c_int32]),
+    "scan_condconv_bwd": (c_int32, [_LV, _P, _P, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
+    "scan_attn_fwd": (c_int32, [_P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P]),
+    "scan_attn_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P, _P, _P]),
+    "scan_class_sums": (c_int32, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "scan_proto_update": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P]),
+    "scan_dbscan_workspace_bytes": (c_int64, [c_int64]),
+    "scan_dbscan_level": (c_int32, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_float, c_double, c_int32, c_int32,
+                                    _P, _P, _P, _P, _P, c_int64, _P]),
+    "scan_dbscan_points": (c_int32, [_P, c_int32, c_int32, c_double, c_int32, _P, _P, _P, c_int64, _P]),
+    "scan_sigmoid_focal_fwd": (c_int32, [_P, _P, c_int64, c_int32, c_float, c_float, _P, _P]),
+    "scan_sigmoid_focal_bwd": (c_int32, [_P, _P, _P, c_int64, c_int32, c_float, c_float, _P, _P]),
+    "scan_ensemble": (c_int32, [_P, _P, c_int32, c_int32, c_int64, c_int32, _P, _P]),
+}
+
+_lib = None
+CALLS = {"n": 0}  # launches issued through the ABI (bench.py's gpu_launches evidence)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "scan_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or scan_b200/csrc/build.sh); there is no fallback path" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if handle.scan_abi_version() != 1:
+            raise RuntimeError("scan_b200: ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        L = lib()
+        msg = L.scan_strerror(code).decode()
+        if code == -2:
+            msg += ": " + L.scan_last_cuda_error().decode()
+        raise RuntimeError("scan_b200.%s failed: %s" % (what, msg))
+
+
+def call(name, *args):
+    CALLS["n"] += 1
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,443 @@
+"""B200-native condgraph middle head: host-side mirror of the reference's GRAPHModule.
+
+Same constructor (`build_condgraph(cfg, in_channels)`), same forward signature and 4-tuple result,
+same `state_dict()` keys/shapes, same MODEL.MIDDLE_HEAD.* keys as
+/root/reference/fcos_core/modeling/rpn/fcos/condgraph.py (GRAPHModule :122-669, build_condgraph :672) and the node
+sampling of .../fcos/loss.py (PrototypeComputation :239-520) -- but the hot path runs in hand-written sm_100a kernels
+behind the C ABI of include/scan_b200.h:
+
+    head_in (torch/cuDNN, out of the kernel scope: SURVEY §8a a1)
+      -> scan_pack_rows            NCHW -> rows [R,256] (level-first, image-major: the reference's flattening)
+      -> scan_fcos_assign          K1  GT -> location assignment                      (loss.py:262-343)
+      -> scan_sample_nodes         K1  node index generation, balanced negatives      (loss.py:430-458 / 497-516)
+      -> scan_gather_rows          K1  node rows
+      -> scan_attn_fwd/bwd         K3  affinity + softmax + aggregation               (transformer.py:5-34)
+      -> scan_class_sums + scan_proto_update   K3  per-class means + paradigm EMA     (condgraph.py:395-398, 558-617)
+      -> manifestation (cuDNN RNN / cuBLAS; tiny)                                     (condgraph.py:313-336)
+      -> scan_condconv_fwd/bwd     K4  conditional conv + softmax + focal loss, tcgen05 (condgraph.py:619-629, 338-370)
+      -> scan_dbscan_level         K2  target-domain sampling                         (loss.py:397-423)
+    head_out (torch/cuDNN)
+
+There is no CPU path: features must be CUDA tensors and libscan_b200.so must be loadable.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .config import CfgNode  # noqa: F401  (re-exported for users without yacs)
+
+
+class PROTOTYPECounter(object):
+    """condgraph.py:46-65: stop=True yields 0,1,..,cycle,cycle,...; stop=False cycles 0..cycle-1."""
+
+    def __init__(self, cycle=3, stop=False):
+        self.cycle = cycle
+        self.counter = -1
+        self.stop = stop
+
+    def __call__(self, *args, **kwargs):
+        if self.stop:
+            if self.counter != self.cycle:
+                self.counter += 1
+            return self.counter
+        self.counter += 1
+        if self.counter == self.cycle:
+            self.counter = 0
+        return self.counter
+
+
+class GRAPHHead(nn.Module):
+    """condgraph.py:68-119: [Conv3x3 (+GN/IN/BN) + ReLU] x num_convs, shared over FPN levels (stays torch/cuDNN)."""
+
+    def __init__(self, cfg, in_channels, out_channel, mode="in"):
+        super().__init__()
+        mh = cfg.MODEL.MIDDLE_HEAD
+        if mode == "in":
+            num_convs = mh.NUM_CONVS_IN
+        elif mode == "out":
+            num_convs = mh.NUM_CONVS_OUT
+        else:
+            num_convs = cfg.MODEL.FCOS.NUM_CONVS
+        tower = []
+        for _ in range(num_convs):
+            tower.append(nn.Conv2d(in_channels, out_channel, kernel_size=3, stride=1, padding=1))
+            if mode == "in":
+                if mh.IN_NORM == "GN":
+                    tower.append(nn.GroupNorm(32, in_channels))
+                elif mh.IN_NORM == "IN":
+                    tower.append(nn.InstanceNorm2d(in_channels))
+                elif mh.IN_NORM == "BN":
+                    tower.append(nn.BatchNorm2d(in_channels))
+            tower.append(nn.ReLU())
+        self.add_module("middle_tower", nn.Sequential(*tower))
+        for layer in self.middle_tower.modules():
+            if isinstance(layer, nn.Conv2d):
+                nn.init.normal_(layer.weight, std=0.01)
+                nn.init.constant_(layer.bias, 0)
+
+    def forward(self, x):
+        return [self.middle_tower(f) for f in x]
+
+
+class MultiHeadAttention(nn.Module):
+    """Parameters of layers/transformer.py:36-90; the attention itself runs in scan_attn_fwd/bwd."""
+
+    def __init__(self, model_dim=256, num_heads=4, dropout=0.1):
+        super().__init__()
+        self.dim_per_head = model_dim // num_heads
+        self.num_heads = num_heads
+        self.linear_k = nn.Linear(model_dim, model_dim)
+        self.linear_v = nn.Linear(model_dim, model_dim)
+        self.linear_q = nn.Linear(model_dim, model_dim)
+        self.linear_final = nn.Linear(model_dim, model_dim)
+        self.layer_norm = nn.LayerNorm(model_dim)
+        self.p_drop = dropout
+        self._calls = 0
+
+    def forward(self, x):
+        """x [M,256] (the reference passes (key, value, query) = (x, x, x), condgraph.py:392)."""
+        q, k, v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
+        scale = float((self.dim_per_head // self.num_heads) ** -0.5)      # transformer.py:75 -> 0.25
+        p = self.p_drop if self.training else 0.0
+        seed = 0
+        if p > 0:
+            seed = int(torch.initial_seed() * 1000003 + self._calls) & 0x7FFFFFFFFFFFFFFF
+            self._calls += 1
+        ctx = ops.chunked_attention(q, k, v, scale, p, seed)
+        out = self.linear_final(ctx)
+        out = F.dropout(out, p, self.training)
+        return self.layer_norm(x + out)
+
+
+def sim_matrix(a, b, eps=1e-8):
+    """condgraph.py:35-43."""
+    a_n, b_n = a.norm(dim=1)[:, None], b.norm(dim=1)[:, None]
+    return torch.mm(a / torch.clamp(a_n, min=eps), (b / torch.clamp(b_n, min=eps)).t())
+
+
+class GRAPHModule(nn.Module):
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        self.cfg = cfg.clone()
+        mh = cfg.MODEL.MIDDLE_HEAD
+        self.debug_cfg = cfg.MODEL.DEBUG_CFG
+        if self.debug_cfg:
+            raise RuntimeError("MODEL.DEBUG_CFG (t-SNE / map dumps with os._exit) is out of scope")
+        self.with_bg_proto = bool(mh.PROTO_WITH_BG)
+        self.with_bias_dc = bool(mh.COND_WITH_BIAS)
+        self.with_concated_maps = bool(mh.CAT_ACT_MAP)
+        self.with_shortcut_GCNs = bool(mh.GCN_SHORTCUT)
+        self.with_global_gcn = bool(mh.GLOBAL_GCN)
+        self.with_self_training = bool(mh.GCN_SELF_TRAINING)
+        self.fpn_strides = list(cfg.MODEL.FCOS.FPN_STRIDES)
+        self.num_classes_fg = cfg.MODEL.FCOS.NUM_CLASSES - 1
+        self.used_num_classes = self.num_classes_fg + int(self.with_bg_proto)
+        self.transfer_cfg = tuple(mh.TRANSFER_CFG)
+        self.act_loss_cfg = mh.ACT_LOSS
+        self.GCN_norm_cfg = mh.GCN_EDGE_NORM
+        self.GCN_out_act_cfg = mh.GCN_OUT_ACTIVATION
+        self.lamda1, self.lamda2 = mh.GCN_LOSS_WEIGHT, mh.ACT_LOSS_WEIGHT
+        self.lamda3, self.lamda4 = mh.CON_LOSS_WEIGHT, mh.GCN_LOSS_WEIGHT_TG
+        self.use_rnn = mh.USE_RNN
+        self.prototype_iter = mh.PROTO_ITER
+        self.cosine_update = bool(mh.COSINE_UPDATE_ON)
+        self.target_sampling = mh.TARGET_SAMPLING_CFG
+        self.dbscan_eps = float(mh.DBSCAN_EPS)
+        self.dbscan_thr = float(mh.DBSCAN_THR)
+        self.plabel_th = float(cfg.SOLVER.MIDDLE_HEAD.PLABEL_TH[0])
+        self.dbscan_cap = 65536          # points per level the DBSCAN workspace is sized for
+        channel = mh.PROTO_CHANNEL
+        hidden = mh.COND_HIDDEN_CHANNEL
+        if channel != ops.C or in_channels != ops.C:
+            raise RuntimeError("the sm_100a kernels are built for 256 channels")
+        if self.used_num_classes > 16:
+            raise RuntimeError("used_num_classes > 16 is not supported by the conditional-conv kernel")
+        if self.act_loss_cfg == "sigmoidFL" and self.used_num_classes != 2:
+            raise RuntimeError("sigmoidFL is hard-wired to 2 classes in the reference (condgraph.py:362-363)")
+
+        self.head_in = GRAPHHead(cfg, in_channels, in_channels, mode="in")
+        if self.prototype_iter == 1:
+            self.register_buffer("prototype", torch.randn(self.used_num_classes, channel))
+        else:
+            self.register_buffer("prototype", torch.randn(self.used_num_classes, channel, self.prototype_iter))
+        if self.with_concated_maps:
+            self.head_out = GRAPHHead(cfg, in_channels + self.used_num_classes, in_channels, mode="out")
+        self.proto_cls_hidden = nn.Linear(mh.GCN2_OUT_CHANNEL, 512)
+        self.proto_cls = nn.Linear(512, self.used_num_classes)
+        if self.with_global_gcn:
+            self.multihead_attn = MultiHeadAttention(256, 4, dropout=0.1)
+        else:
+            if self.GCN_norm_cfg not in ("NO", "cosine_detached"):
+                # 'softmax' / 'cosine' reference the never-defined edge_project_u/v (condgraph.py:289, 296)
+                raise AttributeError("GCN_EDGE_NORM %r needs edge_project_u/v, which the reference never defines"
+                                     % (self.GCN_norm_cfg,))
+            self.gcn_layer1 = nn.Linear(256, mh.GCN1_OUT_CHANNEL)
+            self.gcn_layer2 = nn.Linear(mh.GCN1_OUT_CHANNEL, mh.GCN2_OUT_CHANNEL)
+            for layer in (self.gcn_layer1, self.gcn_layer2):
+                nn.init.normal_(layer.weight, std=0.01)
+                nn.init.constant_(layer.bias, 0)
+        if self.use_rnn:
+            self.cond_nx1 = nn.Conv2d(512, 256, kernel_size=(self.prototype_iter, 1))
+            self.cond_rnn = nn.RNN(256, 512, 2, nonlinearity="tanh")
+            self.counter_rnn = PROTOTYPECounter(self.prototype_iter, stop=True)
+        elif self.prototype_iter > 1:
+            self.counter = PROTOTYPECounter(self.prototype_iter)
+            self.cond_nx1 = nn.Conv2d(channel, hidden, kernel_size=(self.prototype_iter, 1))
+            nn.init.normal_(self.cond_nx1.weight)
+            nn.init.constant_(self.cond_nx1.bias, 0)
+            self.cond_nx1_norm = nn.GroupNorm(32, hidden)
+        else:
+            self.cond_1 = nn.Linear(channel, hidden)
+            nn.init.normal_(self.cond_1.weight, std=0.01)
+            nn.init.constant_(self.cond_1.bias, 0)
+        self.cond_2 = nn.Linear(hidden, 256 + int(self.with_bias_dc))
+        for layer in (self.cond_2, self.proto_cls, self.proto_cls_hidden):
+            nn.init.normal_(layer.weight, std=0.01)
+            nn.init.constant_(layer.bias, 0)
+        self.last = {}     # intermediate results of the last call (labels, node indices, masks) for parity tests
+        self.dist_group = None   # set by scan_b200.dist.attach() to all-reduce the prototype sums
+
+    # ------------------------------------------------------------------ manifestation (condgraph.py:313-336)
+    def get_conded_weight(self):
+        if self.use_rnn:
+            h, _ = self.cond_rnn(self.prototype.permute(2, 0, 1).contiguous())       # [P,K,512]
+            w = self.cond_nx1.weight[:, :, :, 0]                                     # [256,512,P]
+            return torch.einsum("pkc,ocp->ko", h, w) + self.cond_nx1.bias
+        if self.prototype_iter > 1:
+            w = self.cond_nx1.weight[:, :, :, 0]
+            hcat = torch.einsum("kcp,ocp->ko", self.prototype, w) + self.cond_nx1.bias
+            hcat = F.group_norm(hcat, 32, self.cond_nx1_norm.weight, self.cond_nx1_norm.bias, 1e-5)
+            return self.cond_2(torch.relu(hcat))
+        return self.cond_2(torch.relu(self.cond_1(self.prototype)))
+
+    def _split_kernel(self, kernel_par):
+        if self.with_bias_dc:
+            return kernel_par[:, :-1].contiguous(), kernel_par[:, -1].contiguous()
+        return kernel_par, None
+
+    def _act_mode(self):
+        return 0 if self.act_loss_cfg == "softmaxFL" else 1   # condgraph.py:344-346: anything else is sigmoid
+
+    # ------------------------------------------------------------------ graph aggregation (condgraph.py:386-421)
+    def _forward_gcns(self, pos_points, pos_labels):
+        k = self.used_num_classes
+        shift = 0 if self.with_bg_proto else 1
+        if self.with_global_gcn:
+            nodes = self.multihead_attn(pos_points)
+            if self.with_shortcut_GCNs:
+                nodes = nodes + pos_points
+        else:
+            nodes = self._local_gcn(pos_points, pos_labels, shift)
+        packed = ops.class_sums(nodes, pos_labels, k, shift)
+        logits = self.proto_cls(torch.relu(self.proto_cls_hidden(nodes)))
+        node_loss = self.lamda1 * F.cross_entropy(logits, pos_labels - shift)
+        return node_loss, packed, nodes
+
+    def _local_gcn(self, pos_points, pos_labels, shift):
+        """Per-class GCN (condgraph.py:262-302, 404-414): Adj = softmax(affinity).detach(); two graph convolutions."""
+        out = pos_points.clone()
+        labels_host = pos_labels.cpu()
+        for i in range(self.used_num_classes):
+            idx = torch.nonzero(labels_host == i + shift).reshape(-1)
+            if idx.numel() == 0:
+                continue
+            idx = idx.to(pos_points.device)
+            sub = pos_points[idx]
+            if self.GCN_norm_cfg == "NO":
+                adj = torch.mm(sub, sub.t()).softmax(-1).detach()
+            else:
+                adj = sim_matrix(sub, sub).softmax(-1).detach()
+            x = torch.relu(self.gcn_layer1(torch.mm(adj, sub)))
+            y = self.gcn_layer2(torch.mm(adj, x))
+            act = self.GCN_out_act_cfg
+            if act == "softmax":
+                y = y.softmax(dim=-1)
+            elif act == "sigmoid":
+                y = y.sigmoid()
+            elif act == "tanh":
+                y = y.tanh()
+            elif act == "relu":
+                y = torch.relu(y)
+            elif act != "NO":
+                raise KeyError("unknown gcn output activation")
+            if self.with_shortcut_GCNs:
+                y = y + sub
+            out = out.index_copy(0, idx, y)
+        return out
+
+    # ------------------------------------------------------------------ paradigm update (condgraph.py:304-311, 558-617)
+    @torch.no_grad()
+    def update_prototype_ensemble(self, packed):
+        if self.dist_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.dist_group)
+        shift = False
+        if self.use_rnn:
+            it = self.counter_rnn()
+            if it == self.prototype_iter:
+                slot, shift = it - 1, True
+            else:
+                slot = it
+        elif self.prototype_iter > 1:
+            slot = self.counter()
+        else:
+            slot = 0
+        return ops.proto_update(packed, self.prototype, slot, shift, self.cosine_update, 0.95)
+
+    # ------------------------------------------------------------------ head_out (condgraph.py:379-384)
+    def features_post_processing(self, features, act_maps):
+        if self.with_concated_maps:
+            return self.head_out([torch.cat([f, a], dim=1) for f, a in zip(features, act_maps)])
+        return features
+
+    # ------------------------------------------------------------------ branches
+    def _forward_train_source(self, images, features, targets=None, return_maps=False):
+        geo = ops.Geometry.of(features, self.fpn_strides)
+        dev = features[0].device
+        rows = ops.pack_rows(geo, features)
+        boxes, box_labels, box_count, g_max = ops.pad_targets(targets, dev)
+        labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
+        smp = ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels)
+        self._record_nodes(geo, smp, labels=labels)
+        pos_points = ops.gather_rows(rows, smp.node_rows)
+        node_loss, packed, _ = self._forward_gcns(pos_points, smp.node_labels)
+        self.last["prototype_batch"] = self.update_prototype_ensemble(packed)
+        weight, bias = self._split_kernel(self.get_conded_weight())
+        self.last["conded_weight"] = weight
+        with_loss = self.act_loss_cfg in ("softmaxFL", "sigmoidFL")
+        acts, act_loss, flags = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode(),
+                                             labels if with_loss else None, self.lamda2)
+        self.last["act_loss_flags"] = flags
+        out = self.features_post_processing(features, acts)
+        return out, (node_loss, 0), act_loss, acts
+
+    def get_transfer_loss(self, tg_prototype, tg_nodes, tg_labels):
+        """condgraph.py:457-498."""
+        losses = []
+        sr = self.prototype.mean(dim=-1).detach() if self.prototype_iter > 1 else self.prototype.detach()
+        cfgt = self.transfer_cfg
+        if "NODES" in cfgt or "NODE" in cfgt:
+            losses.append(F.kl_div(tg_nodes.softmax(-1).log(), sr[tg_labels].softmax(-1), reduction="mean"))
+        if "PROTOTYPE" in cfgt:
+            idx = tg_prototype.sum(-1).bool()
+            losses.append(F.kl_div(tg_prototype[idx].softmax(-1).log(), sr[idx].softmax(-1), reduction="mean"))
+        if "ADJ" in cfgt:
+            idx = tg_prototype.sum(dim=-1).bool()
+            a = sim_matrix(sr[idx], sr[idx]).view(1, -1)
+            b = sim_matrix(tg_prototype[idx], tg_prototype[idx]).view(1, -1)
+            losses.append(F.cosine_embedding_loss(a, b, a.new_ones(1), margin=0.0))
+        if "ADJ_COMPLETE" in cfgt:
+            idx = ~(tg_prototype.sum(dim=-1).bool())
+            comp = torch.where(idx[:, None], sr, tg_prototype)
+            a = sim_matrix(sr, sr).view(1, -1)
+            b = sim_matrix(comp, comp).view(1, -1)
+            losses.append(F.cosine_embedding_loss(a, b, a.new_ones(1), margin=0.0))
+        if losses:
+            return sum(losses)
+        return None
+
+    def _sample_target(self, geo, rows, acts):
+        dev = rows.device
+        k = self.used_num_classes
+        pos_mask = torch.empty((geo.R,), device=dev, dtype=torch.uint8)
+        plabel = torch.empty((geo.R,), device=dev, dtype=torch.int64)
+        infos = []
+        if self.target_sampling == "dbscan":
+            caps = [min(geo.n_images * (k - 1) * h * w, self.dbscan_cap) for h, w in geo.shapes]
+            ws = ops.dbscan_workspace(max(caps), dev)
+            for l in range(len(geo.shapes)):
+                a, b = geo.row_off[l], geo.row_off[l + 1]
+                _, info = ops.dbscan_level(rows.detach()[a:b], acts[l].detach(), self.dbscan_thr, self.dbscan_eps, caps[l],
+                                           pos_mask[a:b], plabel[a:b], ws)
+                infos.append(info)
+        elif self.target_sampling == "score_threshold":
+            # loss.py:479-481 (alternative sampler; torch ops, not a north-star kernel)
+            for l, act in enumerate(acts):
+                a, b = geo.row_off[l], geo.row_off[l + 1]
+                flat = act.detach().permute(0, 2, 3, 1).reshape(-1, k)
+                pos_mask[a:b] = (flat[:, 1:] > self.plabel_th).sum(dim=-1).bool().to(torch.uint8)
+                plabel[a:b] = flat[:, 1:].argmax(dim=-1) + 1
+        else:
+            raise KeyError("unknown target labels!")   # 'mean_shift' / 'kmeans' samplers are out of scope
+        smp = ops.sample_nodes(geo, 1, True, pos_mask=pos_mask, plabel=plabel)
+        if infos:
+            info = torch.stack(infos).cpu()
+            if bool((info[:, 4] != 0).any()):
+                raise RuntimeError("DBSCAN point capacity (%d per level) exceeded: raise module.dbscan_cap" % self.dbscan_cap)
+            self.last["dbscan_info"] = info
+            self.last["dbscan_masks"] = [m.bool() for m in geo.split_rows(pos_mask)]
+        return smp
+
+    def _forward_train_target(self, images, features, targets=None, return_maps=False):
+        geo = ops.Geometry.of(features, self.fpn_strides)
+        rows = ops.pack_rows(geo, features)
+        weight, bias = self._split_kernel(self.get_conded_weight())   # identical at every level (condgraph.py:507)
+        acts, _, _ = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode())
+        smp = self._sample_target(geo, rows, acts)
+        self._record_nodes(geo, smp)
+        out = self.features_post_processing(features, acts)
+        if smp.n_nodes > 0 and (self.transfer_cfg[0] is not None or self.with_self_training):
+            pos_points = ops.gather_rows(rows, smp.node_rows)
+            node_loss, packed, nodes = self._forward_gcns(pos_points, smp.node_labels)
+            node_loss = self.lamda4 * node_loss
+            cnt = packed[:, -1:]
+            tg_proto = torch.where(cnt > 0, packed[:, :-1] / cnt.clamp(min=1.0), torch.zeros_like(packed[:, :-1]))
+            # the class means feed the transfer losses WITH gradient in the reference (condgraph.py:398, 526)
+            tg_proto = self._class_means_with_grad(nodes, smp.node_labels, tg_proto)
+            # with GLOBAL_GCN=False the reference has overwritten the sampled rows in place (condgraph.py:413)
+            tl_nodes = pos_points if self.with_global_gcn else nodes
+            transfer_loss = self.get_transfer_loss(tg_proto, tl_nodes, smp.node_labels)
+            if transfer_loss is not None:
+                transfer_loss = self.lamda3 * transfer_loss
+            if self.with_self_training:
+                return out, (node_loss, transfer_loss), None, acts
+            return out, (None, transfer_loss), None, acts
+        return out, None, None, acts
+
+    def _class_means_with_grad(self, nodes, labels, proto_values):
+        """prototype_batch[c] = nodes[labels == c].mean(0) as a differentiable function of `nodes`
+        (condgraph.py:395-398); values come from the scan_class_sums kernel, the gradient is the mean's."""
+        shift = 0 if self.with_bg_proto else 1
+        onehot = F.one_hot(labels - shift, self.used_num_classes).to(nodes.dtype)       # [M,K]
+        cnt = onehot.sum(0).clamp(min=1.0)
+        mean = (onehot / cnt).t() @ nodes
+        return mean + (proto_values - mean).detach()
+
+    def _forward_inference(self, images, features, targets=None, return_maps=False):
+        geo = ops.Geometry.of(features, self.fpn_strides)
+        rows = ops.pack_rows(geo, features)
+        weight, bias = self._split_kernel(self.get_conded_weight())
+        acts, _, _ = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode())
+        return self.features_post_processing(features, acts), None, None, acts
+
+    def forward(self, images, features, targets=None, return_maps=False, mode="source", forward_target=False):
+        features = self.head_in(list(features))
+        if not features[0].is_cuda:
+            raise RuntimeError("scan_b200.GRAPHModule runs on CUDA only (no CPU fallback)")
+        self.last = {"features_in": features}
+        if self.training and targets and mode == "source":
+            return self._forward_train_source(images, features, targets, return_maps)
+        elif self.training and mode == "target" and forward_target:
+            return self._forward_train_target(images, features, targets=None, return_maps=return_maps)
+        return self._forward_inference(images, features, targets=None, return_maps=return_maps)
+
+    # ------------------------------------------------------------------ bookkeeping for tests
+    def _record_nodes(self, geo, smp, labels=None):
+        if labels is not None:
+            self.last["labels"] = geo.split_rows(labels)
+        if smp.n_nodes == 0:
+            self.last["node_rows"] = None
+            return
+        g = smp.node_rows.long()
+        off = torch.tensor(geo.row_off[:-1], device=g.device)
+        lv = torch.bucketize(g, off, right=True) - 1
+        self.last["node_level"] = lv
+        self.last["node_rows"] = g - off[lv]
+        self.last["node_labels"] = smp.node_labels
+        self.last["sample_meta"] = smp.meta
+
+
+def build_condgraph(cfg, in_channels):
+    """Drop-in for fcos_core.modeling.rpn.fcos.condgraph.build_condgraph (condgraph.py:672-673)."""
+    return GRAPHModule(cfg, in_channels)

@@ -1,0 +1,374 @@
+"""Host-side operators: torch tensors in, C-ABI calls on the current CUDA stream, torch tensors out.
+
+torch is plumbing here (device memory, streams, autograd bookkeeping); the arithmetic happens in
+libscan_b200.so.  Every op raises if its input is not a CUDA tensor: there is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ScanLevels, ScanSampleMeta, call
+
+C = 256  # channel width of the middle head (PROTO_CHANNEL / FPN channels)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("scan_b200 ops need CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _ptr_array(tensors, n=8):
+    arr = (ctypes.c_void_p * n)()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class Geometry(object):
+    """FPN level shapes of one call: the `rows` layout of include/scan_b200.h."""
+
+    def __init__(self, shapes, strides, n_images):
+        if len(shapes) > _lib.SCAN_MAX_LEVELS:
+            raise RuntimeError("at most %d FPN levels" % _lib.SCAN_MAX_LEVELS)
+        self.shapes = [(int(h), int(w)) for h, w in shapes]
+        self.strides = [int(s) for s in strides][:len(shapes)]
+        self.n_images = int(n_images)
+        lv = ScanLevels()
+        lv.n_levels = len(shapes)
+        lv.n_images = self.n_images
+        off = [0]
+        for l, (h, w) in enumerate(self.shapes):
+            lv.h[l], lv.w[l], lv.stride[l] = h, w, self.strides[l]
+            off.append(off[-1] + self.n_images * h * w)
+        self.levels = lv
+        self.row_off = off
+        self.R = off[-1]
+
+    def ref(self):
+        return ctypes.byref(self.levels)
+
+    def split_rows(self, t):
+        """[R, ...] tensor -> list of per-level views."""
+        return [t[self.row_off[l]:self.row_off[l + 1]] for l in range(len(self.shapes))]
+
+    @classmethod
+    def of(cls, features, strides):
+        return cls([tuple(f.shape[-2:]) for f in features], strides, features[0].shape[0])
+
+
+# ----------------------------------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------------------------------
+class _PackRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geo, *feats):
+        feats = [f.contiguous() for f in feats]
+        rows = torch.empty((geo.R, C), device=feats[0].device, dtype=torch.float32)
+        call("scan_pack_rows", geo.ref(), _ptr_array(feats), C, _ptr(rows), _stream())
+        ctx.geo = geo
+        ctx.shapes = [f.shape for f in feats]
+        return rows
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_rows):
+        d_rows = d_rows.contiguous()
+        grads = [torch.empty(s, device=d_rows.device, dtype=torch.float32) for s in ctx.shapes]
+        call("scan_unpack_rows", ctx.geo.ref(), _ptr(d_rows), C, _ptr_array(grads), 0, _stream())
+        return (None,) + tuple(grads)
+
+
+def pack_rows(geo, feats):
+    for f in feats:
+        if f.dtype != torch.float32 or f.shape[1] != C:
+            raise RuntimeError("features must be fp32 with %d channels" % C)
+    return _PackRows.apply(geo, *feats)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K1: assignment, sampling, gather
+# ----------------------------------------------------------------------------------------------------
+def pad_targets(targets, device):
+    """list[BoxList] -> (boxes [N,G,4] fp32, labels [N,G] int64, count [N] int32) on `device`."""
+    n = len(targets)
+    counts = []
+    for t in targets:
+        if t.mode != "xyxy":
+            raise AssertionError("targets must be in xyxy mode (loss.py:308)")
+        counts.append(int(t.bbox.shape[0]))
+    if min(counts) == 0:
+        raise RuntimeError("an image without ground-truth boxes is unsupported (the reference's empty min, loss.py:333)")
+    g = max(counts)
+    boxes = torch.zeros((n, g, 4), dtype=torch.float32)
+    labels = torch.zeros((n, g), dtype=torch.int64)
+    for i, t in enumerate(targets):
+        boxes[i, :counts[i]] = t.bbox.detach().to("cpu", torch.float32)
+        labels[i, :counts[i]] = t.get_field("labels").detach().to("cpu", torch.int64)
+    cnt = torch.tensor(counts, dtype=torch.int32)
+    return (boxes.to(device, non_blocking=True), labels.to(device, non_blocking=True),
+            cnt.to(device, non_blocking=True), g)
+
+
+def fcos_assign(geo, boxes, box_labels, box_count, g_max):
+    labels = torch.empty((geo.R,), device=boxes.device, dtype=torch.int64)
+    call("scan_fcos_assign", geo.ref(), _ptr(boxes), _ptr(box_labels), _ptr(box_count), g_max, _ptr(labels), _stream())
+    return labels
+
+
+class SampleResult(object):
+    __slots__ = ("node_rows", "node_labels", "meta", "n_nodes")
+
+
+def sample_nodes(geo, mode, with_bg, labels=None, pos_mask=None, plabel=None):
+    """Returns SampleResult (one device->host read of the 176-byte meta record)."""
+    dev = (labels if labels is not None else pos_mask).device
+    cap = 2 * geo.R
+    node_rows = torch.empty((cap,), device=dev, dtype=torch.int32)
+    node_labels = torch.empty((cap,), device=dev, dtype=torch.int64)
+    meta = torch.zeros((ctypes.sizeof(ScanSampleMeta) // 4,), device=dev, dtype=torch.int32)
+    ws_bytes = _lib.lib().scan_sample_workspace_bytes(geo.R)
+    ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+    call("scan_sample_nodes", geo.ref(), mode, int(bool(with_bg)), _ptr(labels), _ptr(pos_mask), _ptr(plabel),
+         _ptr(node_rows), _ptr(node_labels), cap, _ptr(meta), _ptr(ws), ws_bytes, _stream())
+    host = meta.cpu().numpy()
+    m = ScanSampleMeta.from_buffer_copy(host.tobytes())
+    if m.error == 1:
+        raise IndexError("no negative location left at a level with positives (reference: loss.py:503-504)")
+    if m.error == 2:
+        raise RuntimeError("scan_sample_nodes: node capacity exceeded")
+    out = SampleResult()
+    out.meta = m
+    out.n_nodes = int(m.n_nodes)
+    out.node_rows = node_rows[:out.n_nodes]
+    out.node_labels = node_labels[:out.n_nodes]
+    return out
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, node_rows):
+        rows = rows.contiguous()
+        m = node_rows.numel()
+        out = torch.empty((m, rows.shape[1]), device=rows.device, dtype=torch.float32)
+        call("scan_gather_rows", _ptr(rows), _ptr(node_rows), m, rows.shape[1], _ptr(out), _stream())
+        ctx.save_for_backward(node_rows)
+        ctx.n_rows = rows.shape[0]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_nodes):
+        (node_rows,) = ctx.saved_tensors
+        d_nodes = d_nodes.contiguous()
+        d_rows = torch.zeros((ctx.n_rows, d_nodes.shape[1]), device=d_nodes.device, dtype=torch.float32)
+        call("scan_scatter_add_rows", _ptr(d_nodes), _ptr(node_rows), node_rows.numel(), d_nodes.shape[1],
+             _ptr(d_rows), _stream())
+        return d_rows, None
+
+
+def gather_rows(rows, node_rows):
+    return _GatherRows.apply(rows, node_rows)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K4b: conditional convolution + activation + focal loss
+# ----------------------------------------------------------------------------------------------------
+CONDCONV_IMPL = {"impl": 0}  # 0 = tcgen05 (product), 1 = fp32 FFMA verification kernel (tests only)
+
+
+class _CondConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geo, num_classes, act_mode, loss_weight, rows, weight, bias, labels):
+        rows = rows.contiguous()
+        weight = weight.contiguous()
+        dev = rows.device
+        acts = [torch.empty((geo.n_images, num_classes, h, w), device=dev, dtype=torch.float32) for h, w in geo.shapes]
+        n_part = _lib.lib().scan_condconv_num_partials()
+        partials = torch.empty((n_part,), device=dev, dtype=torch.float64) if labels is not None else None
+        flags = torch.empty((1,), device=dev, dtype=torch.int32)
+        call("scan_condconv_fwd", geo.ref(), _ptr(rows), _ptr(weight), _ptr(bias), num_classes, act_mode,
+             _ptr_array(acts), _ptr(labels), _ptr(partials), _ptr(flags), CONDCONV_IMPL["impl"], _stream())
+        norm = float(geo.R) if act_mode == 0 else float(geo.R * num_classes)
+        if labels is not None:
+            loss = (partials.sum() * (loss_weight / norm)).to(torch.float32)
+        else:
+            loss = torch.zeros((), device=dev, dtype=torch.float32)
+        ctx.geo, ctx.k, ctx.act_mode = geo, num_classes, act_mode
+        ctx.loss_scale = loss_weight / norm if labels is not None else 0.0
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(rows, weight, labels, *acts)
+        ctx.mark_non_differentiable(flags)
+        return (loss, flags) + tuple(acts)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_loss, _d_flags, *d_acts):
+        rows, weight, labels = ctx.saved_tensors[:3]
+        acts = ctx.saved_tensors[3:]
+        geo, k = ctx.geo, ctx.k
+        dev = rows.device
+        d_acts = [None if g is None else g.contiguous() for g in d_acts]
+        # d(total)/d(act_loss) stays on the device (read by the kernel): no host sync in backward
+        d_loss_dev = None
+        if ctx.loss_scale != 0.0 and d_loss is not None:
+            d_loss_dev = d_loss.to(torch.float32).reshape(1).contiguous()
+        d_rows = torch.empty_like(rows)
+        d_weight = torch.empty_like(weight)
+        d_bias = torch.empty((k,), device=dev, dtype=torch.float32) if ctx.has_bias else None
+        ws_bytes = _lib.lib().scan_condconv_bwd_workspace_bytes(k)
+        ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+        call("scan_condconv_bwd", geo.ref(), _ptr(rows), _ptr(weight), k, ctx.act_mode, _ptr_array(acts),
+             _ptr_array(d_acts), _ptr(labels), ctx.loss_scale, _ptr(d_loss_dev), _ptr(d_rows), _ptr(d_weight),
+             _ptr(d_bias), _ptr(ws), ws_bytes, _stream())
+        return None, None, None, None, d_rows, d_weight, d_bias, None
+
+
+def condconv(geo, rows, weight, bias, num_classes, act_mode, labels=None, loss_weight=1.0):
+    """Returns (act_maps: list of [N,K,H_l,W_l], loss or None, flags)."""
+    if num_classes > _lib.SCAN_MAX_CLASSES:
+        raise RuntimeError("used_num_classes > %d is not supported" % _lib.SCAN_MAX_CLASSES)
+    out = _CondConv.apply(geo, num_classes, act_mode, float(loss_weight), rows, weight, bias, labels)
+    loss, flags, acts = out[0], out[1], list(out[2:])
+    return acts, (loss if labels is not None else None), flags
+
+
+# ----------------------------------------------------------------------------------------------------
+# K3a: attention
+# ----------------------------------------------------------------------------------------------------
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale, drop_p, seed):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        m = q.shape[0]
+        out = torch.empty_like(q)
+        lse = torch.empty((4 * m,), device=q.device, dtype=torch.float32)
+        call("scan_attn_fwd", _ptr(q), _ptr(k), _ptr(v), m, scale, drop_p, seed, _ptr(out), _ptr(lse), _stream())
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.cfg = (scale, drop_p, seed)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_out):
+        q, k, v, out, lse = ctx.saved_tensors
+        scale, drop_p, seed = ctx.cfg
+        d_out = d_out.contiguous()
+        m = q.shape[0]
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        delta = torch.empty((4 * m,), device=q.device, dtype=torch.float32)
+        call("scan_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), _ptr(d_out), m, scale, drop_p, seed,
+             _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta), _stream())
+        return dq, dk, dv, None, None, None
+
+
+def chunked_attention(q, k, v, scale=0.25, drop_p=0.0, seed=0):
+    if q.shape[1] != C:
+        raise RuntimeError("attention expects [M,256] projections (4 chunks of 64-d sub-tokens)")
+    return _Attention.apply(q, k, v, float(scale), float(drop_p), int(seed))
+
+
+# ----------------------------------------------------------------------------------------------------
+# K3b: prototype sums + EMA
+# ----------------------------------------------------------------------------------------------------
+def class_sums(nodes, labels, num_classes, label_shift):
+    nodes = nodes.detach().contiguous()
+    packed = torch.empty((num_classes, nodes.shape[1] + 1), device=nodes.device, dtype=torch.float32)
+    call("scan_class_sums", _ptr(nodes), _ptr(labels), nodes.shape[0], nodes.shape[1], num_classes, label_shift,
+         _ptr(packed), _stream())
+    return packed
+
+
+def proto_update(packed, prototype, slot, shift, cosine_on, momentum):
+    k = prototype.shape[0]
+    c = prototype.shape[1]
+    p = prototype.shape[2] if prototype.dim() == 3 else 1
+    if not prototype.is_contiguous():
+        raise RuntimeError("prototype buffer must be contiguous")
+    batch = torch.empty((k, c), device=prototype.device, dtype=torch.float32)
+    call("scan_proto_update", _ptr(packed), k, c, p, slot, int(shift), int(bool(cosine_on)), momentum,
+         _ptr(prototype), _ptr(batch), _stream())
+    return batch
+
+
+# ----------------------------------------------------------------------------------------------------
+# K2: DBSCAN
+# ----------------------------------------------------------------------------------------------------
+def dbscan_workspace(cap, device):
+    nbytes = _lib.lib().scan_dbscan_workspace_bytes(cap)
+    return torch.empty((nbytes,), device=device, dtype=torch.uint8)
+
+
+def dbscan_level(rows_level, act, thr, eps, cap, pos_mask, plabel, workspace, min_samples=5):
+    """act [N,K,H,W]; writes pos_mask [N*H*W] uint8 / plabel [N*H*W] int64 views; returns (labels int32 [cap], info int32[8])."""
+    n, k, h, w = act.shape
+    labels = torch.empty((cap,), device=act.device, dtype=torch.int32)
+    info = torch.empty((8,), device=act.device, dtype=torch.int32)
+    call("scan_dbscan_level", _ptr(rows_level), _ptr(act), n, k, h, w, float(thr), float(eps), min_samples, cap,
+         _ptr(pos_mask), _ptr(plabel), _ptr(labels), _ptr(info), _ptr(workspace), workspace.numel(), _stream())
+    return labels, info
+
+
+def dbscan_points(points, eps, min_samples=5):
+    points = points.contiguous()
+    n, dim = points.shape
+    labels = torch.empty((max(n, 1),), device=points.device, dtype=torch.int32)
+    info = torch.empty((8,), device=points.device, dtype=torch.int32)
+    ws = dbscan_workspace(max(n, 1), points.device)
+    call("scan_dbscan_points", _ptr(points), n, dim, float(eps), min_samples, _ptr(labels), _ptr(info), _ptr(ws),
+         ws.numel(), _stream())
+    return labels[:n], info
+
+
+# ----------------------------------------------------------------------------------------------------
+# K5: sigmoid focal loss, ensembling
+# ----------------------------------------------------------------------------------------------------
+class _SigmoidFocal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, gamma, alpha):
+        logits = logits.contiguous()
+        targets = targets.contiguous().to(torch.int32)
+        losses = torch.empty_like(logits)
+        call("scan_sigmoid_focal_fwd", _ptr(logits), _ptr(targets), logits.shape[0], logits.shape[1], gamma, alpha,
+             _ptr(losses), _stream())
+        ctx.save_for_backward(logits, targets)
+        ctx.cfg = (gamma, alpha)
+        return losses
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_losses):
+        logits, targets = ctx.saved_tensors
+        gamma, alpha = ctx.cfg
+        d_losses = d_losses.contiguous()
+        d_logits = torch.empty_like(logits)
+        call("scan_sigmoid_focal_bwd", _ptr(logits), _ptr(targets), _ptr(d_losses), logits.shape[0], logits.shape[1],
+             gamma, alpha, _ptr(d_logits), _stream())
+        return d_logits, None, None, None
+
+
+def sigmoid_focal_loss(logits, targets, gamma, alpha):
+    """Element-wise losses [R, C]; mirrors `_C.sigmoid_focalloss_forward/backward` (layers/sigmoid_focal_loss.py:9-37)."""
+    if logits.dim() != 2:
+        raise RuntimeError("logits must be [R, num_classes]")
+    return _SigmoidFocal.apply(logits, targets, float(gamma), float(alpha))
+
+
+_MODES = {"common": 0, "light": 1, "precision": 2}
+
+
+def ensemble(mode, cls_logits, act):
+    """TEST.MODE map ensembling of one level (fcos.py:162-169 + inference.py:68): class probabilities [N,K-1,H,W]."""
+    act = act.contiguous()
+    n, k, h, w = act.shape
+    out = torch.empty((n, k - 1, h, w), device=act.device, dtype=torch.float32)
+    cls = None if cls_logits is None else cls_logits.contiguous()
+    call("scan_ensemble", _ptr(cls), _ptr(act), n, k, h * w, _MODES[mode], _ptr(out), _stream())
+    return out

@@ -45,10 +45,11 @@ def build_case(name, boxlist_cls=BoxList):
         cfg.SOLVER.MIDDLE_HEAD.PLABEL_TH = (case["plabel_th"],)
     num_fg = cfg.MODEL.FCOS.NUM_CLASSES - 1
     n = case["n"]
-    src_feats, src_targets = make_workload(n, num_fg, seed=1234, boxes_per_image=6, level_shapes=SMALL_SHAPES,
-                                           image_hw=SMALL_HW, boxlist_cls=boxlist_cls)
-    tgt_feats, _ = make_workload(n, num_fg, seed=4321, boxes_per_image=6, level_shapes=SMALL_SHAPES,
-                                 image_hw=SMALL_HW, boxlist_cls=boxlist_cls)
+    shapes, hw, nb = (None, (800, 1344), 18) if case.get("full") else (SMALL_SHAPES, SMALL_HW, 6)
+    src_feats, src_targets = make_workload(n, num_fg, seed=1234, boxes_per_image=nb, level_shapes=shapes,
+                                           image_hw=hw, boxlist_cls=boxlist_cls)
+    tgt_feats, _ = make_workload(n, num_fg, seed=4321, boxes_per_image=nb, level_shapes=shapes,
+                                 image_hw=hw, boxlist_cls=boxlist_cls)
     return cfg, case, src_feats, src_targets, tgt_feats
 
 

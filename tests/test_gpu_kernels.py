@@ -1,0 +1,326 @@
+"""Kernel-level parity (B200): each C-ABI entry point against the CPU oracle / plain torch fp32 on seeded inputs.
+Bit-exact for labels, indices and DBSCAN labels; rtol 1e-3 for the tensor-core path, tighter for fp32 kernels."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from scan_b200 import ops  # noqa: E402
+from scan_b200.synthetic import make_boxes, make_features  # noqa: E402
+from oracle import condgraph_oracle as orc  # noqa: E402
+
+SHAPES = [(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)]
+FULL = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+STRIDES = [8, 16, 32, 64, 128]
+DEV = "cuda"
+
+
+def _close(a, b, rtol, what):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    scale = max(float(b.abs().max()), 1e-30)
+    err = float((a - b).abs().max())
+    assert err <= rtol * scale, "%s: max|d|=%.3e scale=%.3e" % (what, err, scale)
+
+
+@pytest.mark.parametrize("shapes,n", [(SHAPES, 3), (FULL, 2)])
+def test_pack_unpack_rows(shapes, n):
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(n, 256, h, w, generator=g) for h, w in shapes]
+    geo = ops.Geometry(shapes, STRIDES, n)
+    dfeats = [f.to(DEV).requires_grad_(True) for f in feats]
+    rows = ops.pack_rows(geo, dfeats)
+    want = torch.cat([orc.nhwc_rows(f) for f in feats])
+    assert torch.equal(rows.cpu(), want)
+    cot = torch.randn(rows.shape, generator=g)
+    rows.backward(cot.to(DEV))
+    for l, f in enumerate(dfeats):
+        a, b = geo.row_off[l], geo.row_off[l + 1]
+        h, w = shapes[l]
+        assert torch.equal(f.grad.cpu(), cot[a:b].reshape(n, h, w, 256).permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("shapes,hw,n,nb,seed", [(SHAPES, (200, 336), 3, 6, 1), (FULL, (800, 1344), 2, 18, 2),
+                                                 (FULL, (800, 1344), 8, 18, 1234), (SHAPES, (200, 336), 2, 1, 5)])
+def test_fcos_assign_and_source_sampling_bit_exact(shapes, hw, n, nb, seed):
+    boxes = make_boxes(n, 8, nb, hw, seed)
+    # ragged box counts + a duplicated box (area tie -> first index wins)
+    bl = [(b[: max(1, nb - i)], l[: max(1, nb - i)]) for i, (b, l) in enumerate(boxes)]
+    if nb > 2:
+        b0, l0 = bl[0]
+        bl[0] = (torch.cat([b0, b0[:1]]), torch.cat([l0, (l0[:1] % 8) + 1]))
+    geo = ops.Geometry(shapes, STRIDES, n)
+
+    class T(object):
+        mode = "xyxy"
+
+        def __init__(self, b, l):
+            self.bbox, self._l = b, l
+
+        def get_field(self, k):
+            return self._l
+
+    pb, pl, pc, gmax = ops.pad_targets([T(b, l) for b, l in bl], DEV)
+    labels = ops.fcos_assign(geo, pb, pl, pc, gmax)
+    want = orc.fcos_assign(shapes, STRIDES, [b for b, _ in bl], [l for _, l in bl])
+    assert torch.equal(labels.cpu(), torch.cat(want))
+    for with_bg in (True, False):
+        smp = ops.sample_nodes(geo, 0, with_bg, labels=labels)
+        lv, rows, labs = orc.source_node_indices(want, with_bg)
+        off = torch.tensor(geo.row_off[:-1])
+        assert torch.equal(smp.node_rows.cpu().long(), rows + off[lv])
+        assert torch.equal(smp.node_labels.cpu(), labs)
+
+
+def test_target_sampling_edge_cases_bit_exact():
+    shapes = [(6, 7), (3, 4), (2, 2)]
+    n = 2
+    geo = ops.Geometry(shapes, STRIDES[:3], n)
+    rs = np.random.RandomState(3)
+    for trial in range(12):
+        masks = []
+        for l, (h, w) in enumerate(shapes):
+            m = rs.rand(n * h * w) < [0.3, 0.9, 0.0][(l + trial) % 3]
+            if trial == 5 and l == 0:
+                m[:] = True
+                m[7] = False          # n_neg == 1: negative indices wrap
+            masks.append(m)
+        mask = torch.from_numpy(np.concatenate(masks).astype(np.uint8))
+        plabel = torch.from_numpy(rs.randint(1, 9, geo.R).astype(np.int64))
+        smp = ops.sample_nodes(geo, 1, True, pos_mask=mask.to(DEV), plabel=plabel.to(DEV))
+        rows_w, labs_w = [], []
+        neg_w, negl_w = [], []
+        for l in range(len(shapes)):
+            a = geo.row_off[l]
+            mk = masks[l]
+            p = np.nonzero(mk)[0]
+            q = np.nonzero(~mk)[0]
+            if len(p) == 0:
+                continue
+            k = orc.floor_linspace(len(q) - 2, len(p))
+            neg_w.append(q[k] + a)
+            negl_w.append(np.zeros(len(p), np.int64))
+            rows_w.append(p + a)
+            labs_w.append(plabel.numpy()[p + a])
+        if not rows_w:
+            assert smp.n_nodes == 0
+            continue
+        assert np.array_equal(smp.node_rows.cpu().numpy(), np.concatenate(neg_w + rows_w))
+        assert np.array_equal(smp.node_labels.cpu().numpy(), np.concatenate(negl_w + labs_w))
+    # a level whose locations are all positive: the reference raises IndexError (loss.py:503-504)
+    mask = torch.ones(geo.R, dtype=torch.uint8)
+    with pytest.raises(IndexError):
+        ops.sample_nodes(geo, 1, True, pos_mask=mask.to(DEV), plabel=torch.ones(geo.R, dtype=torch.int64, device=DEV))
+
+
+def test_gather_scatter_rows():
+    g = torch.Generator().manual_seed(1)
+    rows = torch.randn(5000, 256, generator=g)
+    idx = torch.randint(0, 5000, (1777,), generator=g).sort().values
+    r = rows.to(DEV).requires_grad_(True)
+    out = ops.gather_rows(r, idx.to(DEV).int())
+    assert torch.equal(out.cpu(), rows[idx])
+    cot = torch.randn(out.shape, generator=g)
+    out.backward(cot.to(DEV))
+    want = torch.zeros_like(rows).index_add_(0, idx, cot)
+    _close(r.grad, want, 1e-6, "scatter_add")
+
+
+def _condconv_reference(feats, weight, bias, labels, mode, lam):
+    k = weight.shape[0]
+    logits = [torch.nn.functional.conv2d(f, weight.reshape(k, -1, 1, 1), bias) for f in feats]
+    acts = [lg.softmax(1) if mode == 0 else lg.sigmoid() for lg in logits]
+    loss = None
+    if labels is not None:
+        flat = torch.cat([lg.permute(0, 2, 3, 1).reshape(-1, k) for lg in logits])
+        if mode == 0:
+            loss = lam * orc.softmax_focal_loss(flat, labels)
+        else:
+            onehot = torch.zeros(labels.numel(), 2, dtype=flat.dtype)
+            onehot[torch.arange(labels.numel()), labels] = 1
+            loss = lam * orc.bce_focal_loss(flat, onehot)
+    return acts, loss
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("k,mode,with_bias,shapes,n", [(9, 0, False, SHAPES, 2), (2, 1, False, SHAPES, 3), (9, 0, True, SHAPES, 1),
+                                                       (2, 0, False, SHAPES, 2), (9, 0, False, FULL, 1), (16, 0, False, SHAPES, 1)])
+def test_condconv_forward_backward(impl, k, mode, with_bias, shapes, n):
+    """tcgen05 tf32 path (impl 0) within rtol 1e-3 of the fp32 torch reference; FFMA kernel (impl 1) within 1e-5."""
+    rtol = 1e-3 if impl == 0 else 2e-5
+    g = torch.Generator().manual_seed(10 + k)
+    feats = [torch.relu(torch.randn(n, 256, h, w, generator=g)) for h, w in shapes]
+    weight = torch.randn(k, 256, generator=g) * 0.08
+    bias = torch.randn(k, generator=g) if with_bias else None
+    geo = ops.Geometry(shapes, STRIDES, n)
+    labels = torch.randint(0, k, (geo.R,), generator=g)
+    lam = 0.7
+    # reference (CPU fp64-free fp32 torch)
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    wr = weight.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True) if with_bias else None
+    acts_r, loss_r = _condconv_reference(fr, wr, br, labels, mode, lam)
+    cots = [torch.randn(a.shape, generator=g) / a.numel() * 50 for a in acts_r]
+    (loss_r * 1.3 + sum((a * c).sum() for a, c in zip(acts_r, cots))).backward()
+    # device
+    old = ops.CONDCONV_IMPL["impl"]
+    ops.CONDCONV_IMPL["impl"] = impl
+    try:
+        fd = [f.to(DEV).requires_grad_(True) for f in feats]
+        wd = weight.to(DEV).requires_grad_(True)
+        bd = bias.to(DEV).requires_grad_(True) if with_bias else None
+        rows = ops.pack_rows(geo, fd)
+        acts_d, loss_d, _ = ops.condconv(geo, rows, wd, bd, k, mode, labels.to(DEV), lam)
+        (loss_d * 1.3 + sum((a * c.to(DEV)).sum() for a, c in zip(acts_d, cots))).backward()
+    finally:
+        ops.CONDCONV_IMPL["impl"] = old
+    for l in range(len(shapes)):
+        _close(acts_d[l], acts_r[l], rtol, "act level %d" % l)
+        _close(fd[l].grad, fr[l].grad, rtol, "d_feat level %d" % l)
+    _close(loss_d, loss_r, rtol, "loss")
+    _close(wd.grad, wr.grad, rtol, "d_weight")
+    if with_bias:
+        _close(bd.grad, br.grad, rtol, "d_bias")
+
+
+@pytest.mark.parametrize("m,drop", [(1, 0.0), (10, 0.0), (13, 0.0), (64, 0.0), (257, 0.0), (1048, 0.0)])
+def test_attention_matches_reference_view_semantics(m, drop):
+    g = torch.Generator().manual_seed(m)
+    q, k, v = [torch.randn(m, 256, generator=g) for _ in range(3)]
+    qr, kr, vr = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    att = torch.softmax(torch.bmm(qr.reshape(4, m, 64), kr.reshape(4, m, 64).transpose(1, 2)) * 0.25, dim=2)
+    ctx_r = torch.bmm(att, vr.reshape(4, m, 64)).reshape(m, 256)
+    cot = torch.randn(m, 256, generator=g)
+    (ctx_r * cot).sum().backward()
+    qd, kd, vd = [t.to(DEV).requires_grad_(True) for t in (q, k, v)]
+    ctx_d = ops.chunked_attention(qd, kd, vd, 0.25)
+    (ctx_d * cot.to(DEV)).sum().backward()
+    _close(ctx_d, ctx_r, 2e-5, "ctx")
+    _close(qd.grad, qr.grad, 5e-5, "dq")
+    _close(kd.grad, kr.grad, 5e-5, "dk")
+    _close(vd.grad, vr.grad, 5e-5, "dv")
+
+
+def test_attention_dropout_is_consistent_between_forward_and_backward():
+    m = 300
+    g = torch.Generator().manual_seed(0)
+    q, k, v = [torch.randn(m, 256, generator=g).to(DEV) for _ in range(3)]
+    v1 = v.clone().requires_grad_(True)
+    out = ops.chunked_attention(q, k, v1, 0.25, 0.1, 1234)
+    out2 = ops.chunked_attention(q, k, v, 0.25, 0.1, 1234)
+    assert torch.equal(out, out2)                       # same seed -> same mask
+    out3 = ops.chunked_attention(q, k, v, 0.25, 0.1, 99)
+    assert not torch.equal(out, out3)
+    # out is linear in v for a fixed mask: d(sum(out*c))/dv evaluated by finite differences of the kernel itself
+    c = torch.randn(m, 256, generator=g).to(DEV)
+    (out * c).sum().backward()
+    dv = torch.zeros_like(v)
+    dv[5, 7] = 1.0
+    fd = ((ops.chunked_attention(q, k, v + dv, 0.25, 0.1, 1234) - out2) * c).sum()
+    _close(v1.grad[5, 7], fd, 2e-3, "dropout dv")
+    # mean preserved: E[mask/keep] = 1
+    base = ops.chunked_attention(q, k, torch.ones_like(v), 0.25, 0.0, 0)
+    dropped = ops.chunked_attention(q, k, torch.ones_like(v), 0.25, 0.1, 7)
+    assert abs(float(dropped.mean()) - float(base.mean())) < 0.02
+
+
+def test_class_sums_and_proto_update():
+    g = torch.Generator().manual_seed(4)
+    m, k = 3000, 9
+    nodes = torch.randn(m, 256, generator=g)
+    labels = torch.randint(0, k, (m,), generator=g)
+    labels[labels == 3] = 4          # class 3 absent
+    packed = ops.class_sums(nodes.to(DEV), labels.to(DEV), k, 0).cpu()
+    for c in range(k):
+        sel = nodes[labels == c]
+        assert float(packed[c, 256]) == sel.shape[0]
+        _close(packed[c, :256], sel.sum(0) if sel.shape[0] else torch.zeros(256), 1e-5 if sel.shape[0] else 1, "class sum")
+    for p, slot, shift, cosine in [(3, 0, False, True), (3, 2, True, True), (3, 1, False, False), (1, 0, False, True)]:
+        proto = torch.randn(k, 256, p, generator=g) if p > 1 else torch.randn(k, 256, generator=g)
+        want = proto.clone()
+        batch = torch.zeros(k, 256)
+        for c in range(k):
+            if (labels == c).any():
+                batch[c] = nodes[labels == c].mean(0)
+        exist = batch.sum(-1).bool()
+        old = want[exist, :, slot] if p > 1 else want[exist]
+        mom = torch.cosine_similarity(old, batch[exist]).unsqueeze(1) if cosine else 0.95
+        if shift:
+            for i in range(p - 1):
+                want[:, :, i] = want[:, :, i + 1].clone()
+        new = old * mom + batch[exist] * (1 - mom)
+        if p > 1:
+            want[exist, :, slot] = new
+        else:
+            want[exist] = new
+        dproto = proto.to(DEV).contiguous()
+        got_batch = ops.proto_update(ops.class_sums(nodes.to(DEV), labels.to(DEV), k, 0), dproto, slot, shift, cosine, 0.95)
+        _close(got_batch, batch, 1e-5, "prototype_batch")
+        _close(dproto, want, 1e-5, "prototype p=%d slot=%d" % (p, slot))
+
+
+def _blobs(rs, n, kind):
+    if kind == "planar":
+        p2 = rs.uniform(0, 0.12 * np.sqrt(n) * 3, (n, 2))
+        basis = np.linalg.qr(rs.standard_normal((256, 2)))[0]
+        return (p2 @ basis.T).astype(np.float32)
+    if kind == "dup":
+        base = rs.standard_normal((max(n // 7, 1), 256)).astype(np.float32) * 0.2
+        return base[rs.randint(0, base.shape[0], n)]
+    centers = rs.standard_normal((5, 256)) * 3
+    return (centers[rs.randint(0, 5, n)] + rs.standard_normal((n, 256)) * 0.17).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,kind,eps", [(1, "blob", 3.0), (4, "blob", 3.0), (63, "blob", 3.0), (64, "planar", 3.0), (65, "dup", 0.5),
+                                        (500, "planar", 3.0), (777, "blob", 3.0), (2000, "planar", 2.0), (3000, "blob", 4.0),
+                                        (1500, "planar", 0.7)])
+def test_dbscan_points_bit_exact_vs_sklearn(n, kind, eps):
+    from sklearn.cluster import DBSCAN
+    rs = np.random.RandomState(n)
+    x = _blobs(rs, n, kind)
+    want = DBSCAN(eps=eps).fit_predict(x)
+    labels, info = ops.dbscan_points(torch.from_numpy(x).to(DEV), eps)
+    got = labels.cpu().numpy()
+    assert np.array_equal(got, want), "mismatch at %s" % np.nonzero(got != want)[0][:10]
+    info = info.cpu().numpy()
+    assert info[1] == want.max() + 1 and info[2] == int((want < 0).sum())
+
+
+def test_dbscan_threshold_band_is_rechecked_in_fp64():
+    """Points at distance exactly eps (and one ulp either side) from a dense core: fp32 alone would flip them."""
+    from sklearn.cluster import DBSCAN
+    rs = np.random.RandomState(0)
+    core = np.zeros((8, 256), np.float32)
+    core[:, 0] = rs.uniform(0, 1e-3, 8)
+    ring = np.zeros((40, 256), np.float32)
+    for i in range(40):
+        d = rs.standard_normal(255)
+        d = d / np.linalg.norm(d) * 3.0
+        ring[i, 1:] = d.astype(np.float32) * np.float32(1 + (i - 20) * 1e-7)
+    x = np.concatenate([core, ring])
+    want = DBSCAN(eps=3.0).fit_predict(x)
+    labels, info = ops.dbscan_points(torch.from_numpy(x).to(DEV), 3.0)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert int(info.cpu()[5]) > 0   # the fp64 path was actually taken
+
+
+def test_sigmoid_focal_and_ensemble():
+    g = torch.Generator().manual_seed(2)
+    r, c = 5000, 8
+    logits = torch.randn(r, c, generator=g) * 3
+    targets = torch.randint(-1, c + 1, (r,), generator=g).int()
+    lr = logits.clone().requires_grad_(True)
+    want = orc.sigmoid_focal_loss_elementwise(lr, targets, 2.0, 0.25)
+    cot = torch.randn(r, c, generator=g)
+    (want * cot).sum().backward()
+    ld = logits.to(DEV).requires_grad_(True)
+    got = ops.sigmoid_focal_loss(ld, targets.to(DEV), 2.0, 0.25)
+    (got * cot.to(DEV)).sum().backward()
+    _close(got, want, 1e-5, "sigmoid focal fwd")
+    _close(ld.grad, lr.grad, 1e-5, "sigmoid focal bwd")
+    act = torch.rand(2, 9, 13, 21, generator=g)
+    cls = torch.randn(2, 8, 13, 21, generator=g)
+    for mode in ("common", "light", "precision"):
+        want = orc.ensemble(mode, [cls], [act])[0]
+        got = ops.ensemble(mode, None if mode == "light" else cls.to(DEV), act.to(DEV))
+        _close(got, want, 1e-6, "ensemble " + mode)
