@@ -136,6 +136,39 @@ def gather_nodes(features, lv, rows):
 # --------------------------------------------------------------------------------------
 # a13: DBSCAN target-domain sampling
 # --------------------------------------------------------------------------------------
+_C_DBSCAN = None
+
+
+def _c_dbscan():
+    """oracle/dbscan_oracle.c, when `make -C oracle` has been run (the same restatement in plain C, OpenMP)."""
+    global _C_DBSCAN
+    if _C_DBSCAN is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdbscan_oracle.so")
+        if os.path.exists(path):
+            lib = ctypes.CDLL(path)
+            lib.dbscan_oracle.restype = ctypes.c_int
+            lib.dbscan_oracle.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_long, ctypes.c_double, ctypes.c_int,
+                                          ctypes.c_void_p]
+            _C_DBSCAN = lib
+        else:
+            _C_DBSCAN = False
+    return _C_DBSCAN
+
+
+def dbscan_labels_c(points, eps, min_samples=5):
+    lib = _c_dbscan()
+    if not lib:
+        raise RuntimeError("oracle/libdbscan_oracle.so not built (make -C oracle)")
+    x = np.ascontiguousarray(points, dtype=np.float32)
+    labels = np.empty(x.shape[0], dtype=np.int32)
+    rc = lib.dbscan_oracle(x.ctypes.data, x.shape[0], x.shape[1], float(eps), int(min_samples), labels.ctypes.data)
+    if rc != 0:
+        raise MemoryError("dbscan_oracle failed")
+    return labels.astype(np.int64)
+
+
 def dbscan_labels(points, eps, min_samples=5, block=2048):
     """sklearn.cluster.DBSCAN(eps, min_samples=5, euclidean).fit_predict restated
     (sklearn 1.9.0: neighbors/_base.py brute radius query with float64 accumulation,
@@ -227,6 +260,8 @@ def dbscan_location_mask(act_fg, feature, eps, thr, use_sklearn=True):
         if use_sklearn:
             from sklearn.cluster import DBSCAN
             labels = DBSCAN(eps=eps, n_jobs=-1).fit_predict(pts.numpy())
+        elif _c_dbscan():
+            labels = dbscan_labels_c(pts.numpy(), eps)
         else:
             labels = dbscan_labels(pts.numpy(), eps)
         y = labels.copy()

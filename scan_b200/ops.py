@@ -181,7 +181,8 @@ def gather_rows(rows, node_rows):
 # ----------------------------------------------------------------------------------------------------
 # K4b: conditional convolution + activation + focal loss
 # ----------------------------------------------------------------------------------------------------
-CONDCONV_IMPL = {"impl": 0}  # 0 = tcgen05 (product), 1 = fp32 FFMA verification kernel (tests only)
+# 0 = tcgen05 (product), 1 = fp32 FFMA verification kernel (tests / bring-up only; SCAN_B200_CONDCONV_IMPL=1)
+CONDCONV_IMPL = {"impl": int(__import__("os").environ.get("SCAN_B200_CONDCONV_IMPL", "0"))}
 
 
 class _CondConv(torch.autograd.Function):

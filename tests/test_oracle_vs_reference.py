@@ -5,9 +5,10 @@ import pytest
 
 import harness
 
-pytestmark = pytest.mark.reference
+pytestmark = []
 
 
+@pytest.mark.reference
 @pytest.mark.parametrize("name", ["c2f_small", "gcn_small", "sim10k_small"])
 def test_reference_still_matches_golden(name, golden_dir):
     import os
@@ -49,3 +50,24 @@ def test_dbscan_restatement_matches_sklearn():
             x = (centers[rs.randint(0, 4, n)] + rs.standard_normal((n, 256)) * 0.17).astype(np.float32)
         want = DBSCAN(eps=3.0).fit_predict(x)
         assert np.array_equal(dbscan_labels(x, 3.0), want)
+
+
+def test_dbscan_c_oracle_matches_sklearn():
+    from sklearn.cluster import DBSCAN
+    from oracle.condgraph_oracle import dbscan_labels_c, _c_dbscan
+    if not _c_dbscan():
+        import subprocess, os
+        subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")])
+        import oracle.condgraph_oracle as o
+        o._C_DBSCAN = None
+    rs = np.random.RandomState(7)
+    for trial in range(10):
+        n = int(rs.randint(1, 900))
+        if trial % 2:
+            p2 = rs.uniform(0, 40, (n, 2))
+            basis = np.linalg.qr(rs.standard_normal((256, 2)))[0]
+            x = (p2 @ basis.T).astype(np.float32)
+        else:
+            centers = rs.standard_normal((4, 256)) * 3
+            x = (centers[rs.randint(0, 4, n)] + rs.standard_normal((n, 256)) * 0.17).astype(np.float32)
+        assert np.array_equal(dbscan_labels_c(x, 3.0), DBSCAN(eps=3.0).fit_predict(x))
