@@ -8,9 +8,35 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ScanLevels, ScanSampleMeta, call
+from ._lib import ScanLevels, ScanSampleMeta
 
 C = 256  # channel width of the middle head (PROTO_CHANNEL / FPN channels)
+
+# Optional per-entry-point device timing (bench.py): CUDA events on the launching stream around every ABI call.
+TIMING = {"on": False}
+TIMERS = []
+
+
+def call(name, *args):
+    if TIMING["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        TIMERS.append((name, e0, e1))
+    else:
+        _lib.call(name, *args)
+
+
+def timers_summary():
+    """{entry point: {"ms": total device ms, "calls": n}} of the calls recorded since TIMERS.clear()."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in TIMERS:
+        d = out.setdefault(name.replace("scan_", "", 1), {"ms": 0.0, "calls": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["calls"] += 1
+    return out
 
 
 def _stream():

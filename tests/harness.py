@@ -127,6 +127,11 @@ def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture
         sd = fixture_state_dict(module, seed=99, kernel_gain=kg, gn_gain=gg)
         module.load_state_dict(sd)
     module.to(device) if impl != "reference" else None
+    if device != "cpu":
+        # parity runs compare against an fp32 CPU reference: keep torch's own conv / matmul kernels (the towers,
+        # which stay on cuDNN/cuBLAS) in true fp32; the only tf32 arithmetic left is the tcgen05 conditional conv
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     # dropout off everywhere: parity runs are deterministic
     if hasattr(module, "multihead_attn"):
         a = module.multihead_attn

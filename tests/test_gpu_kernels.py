@@ -20,7 +20,7 @@ def _close(a, b, rtol, what):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     scale = max(float(b.abs().max()), 1e-30)
     err = float((a - b).abs().max())
-    assert err <= rtol * scale, "%s: max|d|=%.3e scale=%.3e" % (what, err, scale)
+    assert err <= rtol * scale + 2e-6, "%s: max|d|=%.3e scale=%.3e" % (what, err, scale)
 
 
 @pytest.mark.parametrize("shapes,n", [(SHAPES, 3), (FULL, 2)])
@@ -87,6 +87,10 @@ def test_target_sampling_edge_cases_bit_exact():
             masks.append(m)
         mask = torch.from_numpy(np.concatenate(masks).astype(np.uint8))
         plabel = torch.from_numpy(rs.randint(1, 9, geo.R).astype(np.int64))
+        if any(m.all() for m in masks):   # a level without any negative: the reference raises (loss.py:503-504)
+            with pytest.raises(IndexError):
+                ops.sample_nodes(geo, 1, True, pos_mask=mask.to(DEV), plabel=plabel.to(DEV))
+            continue
         smp = ops.sample_nodes(geo, 1, True, pos_mask=mask.to(DEV), plabel=plabel.to(DEV))
         rows_w, labs_w = [], []
         neg_w, negl_w = [], []
