@@ -6,8 +6,9 @@
 One step = one pass of the hot path over one batch: source branch fwd+bwd on `--images` source images, then target
 branch fwd+bwd on `--images` target images (synthetic FPN features of Cityscapes shape, 800x1344 padded, 22 400
 locations/image, 256 channels, K = 9 classes; BASELINE.json configs[1]: 8 + 8 images per GPU).  Weights are the seeded
-fixture followed by `--pretrain` source-only SGD steps (untimed), which makes the activation maps background-
-dominant like a trained model so that the target-domain DBSCAN sees a realistic number of points.
+fixture, `--settle` untimed source steps that fill the paradigm buffer, then `fixtures.fit_trained_like`: a closed-form
+fit of the manifestation layer that makes the activation maps background-dominant with confident object regions like
+a trained model, so that the target-domain DBSCAN sees a realistic number of points.
 
   value      whole-job images/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same through the public module call with HOST (pinned) inputs: H2D of the step's FPN features and
@@ -44,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="scan_b200", choices=["scan_b200", "reference"])
     ap.add_argument("--images", type=int, default=8, help="source images (= target images) per GPU per step")
-    ap.add_argument("--pretrain", type=int, default=30, help="untimed source-only SGD steps that shape the fixture")
+    ap.add_argument("--settle", type=int, default=6, help="untimed source steps that fill the paradigm buffer before the fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="attention dropout (reference train-mode value 0.1)")
     return ap.parse_args()
@@ -89,25 +90,22 @@ class ClockSampler(threading.Thread):
 
 def make_batches(n_images, device=None, pinned=False):
     from scan_b200.synthetic import make_workload
-    src_f, src_t = make_workload(n_images, 8, seed=1234)
-    tgt_f, _ = make_workload(n_images, 8, seed=4321)
+    src_f, src_t = make_workload(n_images, 8, seed=1234, dir_seed=77)
+    tgt_f, _ = make_workload(n_images, 8, seed=4321, dir_seed=77)
     if pinned:
         src_f = [f.pin_memory() for f in src_f]
         tgt_f = [f.pin_memory() for f in tgt_f]
     return src_f, src_t, tgt_f
 
 
-def pretrain(module, feats, targets, steps, lr=0.02):
-    """source-only SGD (momentum 0.9) on one synthetic image; shapes the fixture into a trained-like model"""
-    if steps <= 0:
-        return
-    opt = torch.optim.SGD(module.parameters(), lr=lr, momentum=0.9)
+def pretrain(module, feats, targets, steps):
+    """`steps` source forward passes on one image (they fill the 3 paradigm slots), then the closed-form trained-like fit"""
+    from scan_b200.fixtures import fit_trained_like
     module.train()
-    for _ in range(steps):
-        opt.zero_grad(set_to_none=True)
-        out = module(None, [f[:1] for f in feats], targets=targets[:1], mode="source")
-        (out[1][0] + out[2]).backward()
-        opt.step()
+    with torch.no_grad():
+        for _ in range(steps):
+            module(None, [f[:1] for f in feats], targets=targets[:1], mode="source")
+    fit_trained_like(module, [f[:1] for f in feats], targets[:1])
 
 
 def one_step(module, src, src_targets, tgt, cots):
@@ -146,7 +144,7 @@ def cpu_reference_run(args, steps, warmup):
     m.load_state_dict(fixture_state_dict(m, seed=99))
     m.multihead_attn.p_drop = args.dropout
     src_f, src_t, tgt_f = make_batches(1)
-    pretrain(m, src_f, src_t, args.pretrain)
+    pretrain(m, src_f, src_t, args.settle)
     m.train()
     shapes_f = [(1, 256, h, w) for h, w in FULL_SHAPES]
     shapes_a = [(1, 9, h, w) for h, w in FULL_SHAPES]
@@ -176,7 +174,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "Cityscapes->Foggy VGG16 SCAN config, condgraph middle head fwd+bwd, 800x1344 FPN features, "
-                                       "8 classes + bg; CPU arm runs 1+1 images per step", "pretrain_steps": args.pretrain},
+                                       "8 classes + bg; CPU arm runs 1+1 images per step", "settle_steps": args.settle},
                 "cpu_baseline": {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
                 "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -201,7 +199,7 @@ def main():
     src_h, src_t, tgt_h = make_batches(n, pinned=True)
     src_d = [f.to(dev) for f in src_h]
     tgt_d = [f.to(dev) for f in tgt_h]
-    pretrain(module, src_d, src_t, args.pretrain)
+    pretrain(module, src_d, src_t, args.settle)
     if world > 1:
         from scan_b200 import dist as sdist
         sdist.attach(module)
@@ -292,7 +290,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "Cityscapes->Foggy VGG16 SCAN config, condgraph middle head fwd+bwd, %d source + %d target "
                                        "synthetic images per GPU per step, 800x1344 FPN features, 8 classes + bg" % (n, n),
-                           "parallelism": "dp%d (image shards, prototype all-reduce)" % world, "pretrain_steps": args.pretrain,
+                           "parallelism": "dp%d (image shards, prototype all-reduce)" % world, "settle_steps": args.settle,
                            "attention_dropout": args.dropout,
                            "l2_note": "inputs 2x%d MB per step exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

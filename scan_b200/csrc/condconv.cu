@@ -5,11 +5,15 @@
 //
 // Forward = one skinny GEMM  logits[R, K] = rows[R, 256] . W[K, 256]^T  (K <= 16), HBM-bound (AI ~ 4 flop/B).
 //   * persistent CTAs, one per SM; tile = 128 pixels x 256 channels;
-//   * A (pixels x channels, K-major) streamed by TMA in 8 stages of [128 x 32] fp32 = 16 KB with the 128-byte
-//     swizzle, 10-stage mbarrier ring (160 KB in flight per SM);
+//   * A (pixels x channels, K-major) streamed by TMA in 8 k-blocks of [128 x 32] fp32 = 16 KB with the 128-byte
+//     swizzle, 6-stage mbarrier ring (96 KB in flight per SM);
+//   * 3xTF32 error compensation so the tensor-core path keeps fp32-level accuracy (a plain tf32 read truncates the
+//     activations: measured 1e-3..5e-3 absolute error on the maps, coherent bias in the weight gradients): a
+//     converter warpgroup splits every landed stage IN SHARED MEMORY into hi = rna_tf32(x) (in place) and
+//     lo = x - hi (second buffer), element-wise and therefore swizzle-agnostic; the MMA warp issues
+//     hi*Whi + hi*Wlo + lo*Whi (3 MMAs per k-step; the tensor pipe stays < 15 % busy);
 //   * B = the conditioned kernels, zero-padded to N = 16 by TMA out-of-bounds fill, resident in shared memory
-//     for the whole kernel, split once into tf32-exact hi + lo parts so that only the activation operand
-//     carries tf32 rounding (2 MMAs per k-step; the tensor pipe is < 10 % busy either way);
+//     for the whole kernel, split once into hi + lo the same way;
 //   * tcgen05.mma kind::tf32, M=128 N=16 K=8, fp32 accumulators in TMEM, 4-deep accumulator ring;
 //   * epilogue warps: one TMEM lane = one pixel, so softmax / sigmoid, the NCHW activation-map store and the
 //     focal-loss term are computed per thread in registers (tcgen05.ld 32x32b.x16).
@@ -25,13 +29,13 @@ constexpr int CC_BM = 128;
 constexpr int CC_BK = 32;
 constexpr int CC_KB = CC_C / CC_BK;  // 8 k-blocks per tile
 constexpr int CC_N = 16;
-constexpr int CC_STAGES = 10;
+constexpr int CC_STAGES = 6;
 constexpr int CC_ACC = 4;
 constexpr int CC_STAGE_BYTES = CC_BM * CC_BK * 4;  // 16384
 constexpr int CC_WBLK_BYTES = CC_N * CC_BK * 4;    // 2048
 constexpr int CC_W_BYTES = CC_KB * CC_WBLK_BYTES;  // 16384
-constexpr int CC_SMEM = 1024 + 2 * CC_W_BYTES + CC_STAGES * CC_STAGE_BYTES + 1024;
-constexpr int CC_THREADS = 256;
+constexpr int CC_SMEM = 1024 + 2 * CC_W_BYTES + 2 * CC_STAGES * CC_STAGE_BYTES + 1024;  // hi + lo per stage
+constexpr int CC_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: epilogue, 8-11: tf32 hi/lo converter
 constexpr int CC_MAX_PARTIALS = 1024;
 
 struct ActPtrs {
@@ -179,13 +183,15 @@ __global__ void __launch_bounds__(CC_THREADS, 1)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* w_hi = smem;
   uint8_t* w_lo = smem + CC_W_BYTES;
-  uint8_t* stages = smem + 2 * CC_W_BYTES;
-  uint64_t* bars = (uint64_t*)(stages + CC_STAGES * CC_STAGE_BYTES);
-  uint64_t* full_bar = bars;                         // [CC_STAGES]
-  uint64_t* empty_bar = bars + CC_STAGES;            // [CC_STAGES]
-  uint64_t* acc_full = bars + 2 * CC_STAGES;         // [CC_ACC]
-  uint64_t* acc_empty = bars + 2 * CC_STAGES + CC_ACC;  // [CC_ACC]
-  uint64_t* w_bar = bars + 2 * CC_STAGES + 2 * CC_ACC;
+  uint8_t* stages = smem + 2 * CC_W_BYTES;                    // hi parts (TMA destination, converted in place)
+  uint8_t* stages_lo = stages + CC_STAGES * CC_STAGE_BYTES;   // lo parts
+  uint64_t* bars = (uint64_t*)(stages_lo + CC_STAGES * CC_STAGE_BYTES);
+  uint64_t* full_bar = bars;                         // [CC_STAGES] TMA -> converter
+  uint64_t* empty_bar = bars + CC_STAGES;            // [CC_STAGES] MMA -> TMA
+  uint64_t* ready_bar = bars + 2 * CC_STAGES;        // [CC_STAGES] converter -> MMA
+  uint64_t* acc_full = bars + 3 * CC_STAGES;         // [CC_ACC]
+  uint64_t* acc_empty = bars + 3 * CC_STAGES + CC_ACC;  // [CC_ACC]
+  uint64_t* w_bar = bars + 3 * CC_STAGES + 2 * CC_ACC;
   uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
   __shared__ double red[4];
 
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(CC_THREADS, 1)
     for (int i = 0; i < CC_STAGES; ++i) {
       mbar_init(smem_u32(full_bar + i), 1);
       mbar_init(smem_u32(empty_bar + i), 1);
+      mbar_init(smem_u32(ready_bar + i), 128);
     }
     for (int i = 0; i < CC_ACC; ++i) {
       mbar_init(smem_u32(acc_full + i), 1);
@@ -254,22 +261,52 @@ __global__ void __launch_bounds__(CC_THREADS, 1)
         tcgen05_fence_after();
         const uint32_t d = tmem_base + acc * CC_N;
         for (int kb = 0; kb < CC_KB; ++kb) {
-          mbar_wait(smem_u32(full_bar + stage), phase);
+          mbar_wait(smem_u32(ready_bar + stage), phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(stages + stage * CC_STAGE_BYTES);
+          const uint32_t al_addr = smem_u32(stages_lo + stage * CC_STAGE_BYTES);
           const uint32_t bh_addr = smem_u32(w_hi + kb * CC_WBLK_BYTES);
           const uint32_t bl_addr = smem_u32(w_lo + kb * CC_WBLK_BYTES);
 #pragma unroll
           for (int k = 0; k < CC_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
             const uint64_t da = umma_desc_sw128(a_addr + k * 32);
-            umma_tf32(d, da, umma_desc_sw128(bh_addr + k * 32), CC_IDESC, (kb | k) != 0);
+            const uint64_t dbh = umma_desc_sw128(bh_addr + k * 32);
+            umma_tf32(d, da, dbh, CC_IDESC, (kb | k) != 0);
             umma_tf32(d, da, umma_desc_sw128(bl_addr + k * 32), CC_IDESC, 1);
+            umma_tf32(d, umma_desc_sw128(al_addr + k * 32), dbh, CC_IDESC, 1);
           }
           umma_commit(smem_u32(empty_bar + stage));  // frees the smem stage when these MMAs retire
           if (++stage == CC_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(acc_full + acc));
         if (++acc == CC_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== converter: fp32 stage -> tf32 hi (in place) + lo (second buffer); element-wise, swizzle-agnostic =====
+    const int t = threadIdx.x - 256;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < CC_KB; ++kb) {
+        mbar_wait(smem_u32(full_bar + stage), phase);
+        float4* hi = reinterpret_cast<float4*>(stages + stage * CC_STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(stages_lo + stage * CC_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < CC_STAGE_BYTES / 16 / 128; ++j) {
+          const float4 v = hi[j * 128 + t];
+          uint32_t hx, hy, hz, hw;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(v.z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(v.w));
+          const float4 h = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
+          hi[j * 128 + t] = h;
+          lo[j * 128 + t] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
+        mbar_arrive(smem_u32(ready_bar + stage));
+        if (++stage == CC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {

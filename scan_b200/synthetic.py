@@ -39,12 +39,14 @@ def make_boxes(n_images, num_fg, boxes_per_image=18, image_hw=(800, 1344), seed=
 
 
 def make_features(n_images, num_fg, level_shapes=None, strides=(8, 16, 32, 64, 128), channels=256,
-                  boxes=None, seed=1234, signal=2.0):
-    """Returns list of 5 fp32 NCHW CPU tensors."""
+                  boxes=None, seed=1234, signal=2.0, dir_seed=None):
+    """Returns list of 5 fp32 NCHW CPU tensors.  `dir_seed` fixes the per-class directions independently of the
+    noise seed (source and target domains of the benchmark share the classes but not the images)."""
     if level_shapes is None:
         level_shapes = CITYSCAPES_LEVEL_SHAPES
     rs = np.random.RandomState(seed + 7919)
-    dirs = torch.from_numpy(rs.standard_normal((num_fg + 1, channels)).astype(np.float32))
+    drs = rs if dir_seed is None else np.random.RandomState(dir_seed)
+    dirs = torch.from_numpy(drs.standard_normal((num_fg + 1, channels)).astype(np.float32))
     dirs = dirs / dirs.norm(dim=1, keepdim=True)
     feats = []
     for (h, w), s in zip(level_shapes, strides):
@@ -61,9 +63,10 @@ def make_features(n_images, num_fg, level_shapes=None, strides=(8, 16, 32, 64, 1
 
 
 def make_workload(n_images, num_fg, seed=1234, boxes_per_image=18, level_shapes=None, image_hw=(800, 1344),
-                  boxlist_cls=BoxList, with_targets=True):
+                  boxlist_cls=BoxList, with_targets=True, signal=2.0, dir_seed=None):
     boxes = make_boxes(n_images, num_fg, boxes_per_image, image_hw, seed)
-    feats = make_features(n_images, num_fg, level_shapes=level_shapes, boxes=boxes, seed=seed)
+    feats = make_features(n_images, num_fg, level_shapes=level_shapes, boxes=boxes, seed=seed, signal=signal,
+                          dir_seed=dir_seed)
     targets = None
     if with_targets:
         targets = []
