@@ -256,7 +256,18 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=()):
                 bad.append("noise-floor mismatch %s: max|d|=%.3e" % (k, err))
             continue
         if err > rtol * scale + atol_scale * 1e-6:
-            bad.append("float mismatch %s: max|d|=%.3e scale=%.3e" % (k, err, scale))
+            # Gradients that pass through a ReLU (head_in / head_out towers, both torch ops) are discontinuous: an
+            # activation within ~1e-6 of zero gets the opposite mask on the GPU and on the CPU, which changes a FEW
+            # gradient entries by O(1) relative amounts (measured: tools/diag_grad.py; the same happens between the
+            # reference on CPU and the reference on GPU).  Such tensors pass if the outliers are sparse and the
+            # relative L2 error is small; everything else must meet the max-norm bound.
+            d = np.abs(g.astype(np.float64) - w.astype(np.float64))
+            frac = float((d > rtol * scale).mean())
+            rel_l2 = float(np.linalg.norm(d) / max(np.linalg.norm(w.astype(np.float64)), 1e-30))
+            relu_path = ("dfeat_l" in k) or ("head_in." in k) or ("head_out." in k)
+            if relu_path and frac <= 0.02 and rel_l2 <= 3 * rtol:
+                continue
+            bad.append("float mismatch %s: max|d|=%.3e scale=%.3e outliers=%.2f%% relL2=%.2e" % (k, err, scale, 100 * frac, rel_l2))
     for k in got:
         if k not in want and not any(s in k for s in skip):
             bad.append("unexpected %s" % k)
