@@ -18,9 +18,7 @@
 //   * epilogue warps: one TMEM lane = one pixel, so softmax / sigmoid, the NCHW activation-map store and the
 //     focal-loss term are computed per thread in registers (tcgen05.ld 32x32b.x16).
 // Backward = one pass over rows producing d_rows (dense write) and per-CTA partial d_weight (fp32 FFMA).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace scan {
 
@@ -45,56 +43,7 @@ struct ConstActPtrs {
   const float* p[SCAN_MAX_LEVELS];
 };
 
-// ---------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// K-major operand tile with 128-byte rows and the 128B swizzle: 8-row groups are 1024 B apart (SBO),
-// LBO unused for swizzled K-major layouts, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (2 at bits 7-9 / 10-12), both K-major, N>>3 at 17, M>>4 at 24
-constexpr uint32_t CC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CC_N >> 3) << 17) | ((uint32_t)(CC_BM >> 4) << 24);
+constexpr uint32_t CC_IDESC = umma_idesc_tf32(CC_BM, CC_N);
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -520,31 +469,33 @@ __global__ void __launch_bounds__(256) condconv_bwd_reduce_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-static int get_encode() {
-  if (g_encode) return SCAN_OK;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  SCAN_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  if (!fn || qres != cudaDriverEntryPointSuccess) {
-    set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point not found");
-    return SCAN_ECUDA;
+int get_tensormap_encoder(EncodeTiledFn* out) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SCAN_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point not found");
+      return SCAN_ECUDA;
+    }
+    g_encode = (EncodeTiledFn)fn;
   }
-  g_encode = (EncodeTiledFn)fn;
+  *out = g_encode;
   return SCAN_OK;
 }
 
-static int make_map(CUtensorMap* m, const float* base, uint64_t n_rows, uint32_t box_rows) {
-  cuuint64_t dims[2] = {CC_C, n_rows};
-  cuuint64_t strides[1] = {CC_C * sizeof(float)};
-  cuuint32_t box[2] = {CC_BK, box_rows};
+int make_rowmajor_map(CUtensorMap* m, const float* base, uint64_t n_rows, uint64_t n_cols, uint32_t box_rows) {
+  EncodeTiledFn enc;
+  int rc = get_tensormap_encoder(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {n_cols, n_rows};
+  cuuint64_t strides[1] = {n_cols * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed");
     return SCAN_ECUDA;
@@ -588,12 +539,10 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
     return SCAN_OK;
   }
   if (impl != 0) return SCAN_EINVAL;
-  rc = get_encode();
-  if (rc) return rc;
   CUtensorMap mx, mw;
-  rc = make_map(&mx, rows, (uint64_t)R, CC_BM);
+  rc = make_rowmajor_map(&mx, rows, (uint64_t)R, CC_C, CC_BM);
   if (rc) return rc;
-  rc = make_map(&mw, weight, (uint64_t)num_classes, CC_N);
+  rc = make_rowmajor_map(&mw, weight, (uint64_t)num_classes, CC_C, CC_N);
   if (rc) return rc;
   if (!g_fwd_attr_set) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));

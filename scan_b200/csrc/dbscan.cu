@@ -9,7 +9,9 @@
 // Kernels: ordered compaction of the selected (n, cls, y, x) entries; point build (feature row x activation);
 // 64x64 pairwise-distance tiles in shared memory (fp32 FFMA Gram, fp64 re-evaluation inside a band around eps^2)
 // producing a bit adjacency matrix; popcount neighbour counts; warp-per-row union-find; root ranking; labelling.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "dbscan_common.cuh"
 
 namespace scan {
 
@@ -39,7 +41,7 @@ static long long dbws_layout(long long cap, long long n_entries, int dim, char* 
     return p;
   };
   const long long nb = (n_entries + DB_SB - 1) / DB_SB + 1;
-  const long long wpr = align_up((cap + 31) / 32, 2);
+  const long long wpr = align_up((cap + 31) / 32, 4);  // whole 128-column tiles
   DbWs w;
   w.block_cnt = (int*)take(nb * 4);
   w.sel_flat = (int*)take(cap * 4);
@@ -198,20 +200,6 @@ constexpr int DT = 64;    // tile edge
 constexpr int DKC = 32;   // reduction chunk
 constexpr int DLD = 36;   // padded leading dimension (floats)
 
-// exact sklearn test: float64 accumulation of the fp32 inputs
-__device__ __noinline__ bool exact_within(const float* __restrict__ a, const float* __restrict__ b, int dim, double eps2) {
-  double sa = 0.0, sb = 0.0, ab = 0.0;
-  for (int d = 0; d < dim; ++d) {
-    const double x = (double)__ldg(a + d), y = (double)__ldg(b + d);
-    sa = fma(x, x, sa);
-    sb = fma(y, y, sb);
-    ab = fma(x, y, ab);
-  }
-  double d2 = sa + sb - 2.0 * ab;
-  if (d2 < 0.0) d2 = 0.0;
-  return d2 <= eps2;
-}
-
 __global__ void __launch_bounds__(256) db_adj_kernel(const float* __restrict__ points, const float* __restrict__ sq, const int* info,
                                                      int n_fixed, int dim, float eps2f, double eps2, long long wpr,
                                                      uint32_t* __restrict__ adj, int* info_w) {
@@ -276,7 +264,7 @@ __global__ void __launch_bounds__(256) db_adj_kernel(const float* __restrict__ p
             const float d2 = si + sj - 2.f * acc[a][c];
             const float tol = 1e-4f * (si + sj + eps2f);
             if (fabsf(d2 - eps2f) <= tol) {
-              within = exact_within(points + (long long)i * dim, points + (long long)j * dim, dim, eps2);
+              within = db_exact_within(points + (long long)i * dim, points + (long long)j * dim, dim, eps2);
               ++n_re;
             } else {
               within = d2 < eps2f;
@@ -472,8 +460,14 @@ static int cluster_points(const DbWs& ws, const float* points, const float* sq, 
                           int min_samples, int* labels, int* info_w, cudaStream_t st) {
   const int sms = sm_count();
   const float eps2f = (float)(eps * eps);
-  db_adj_kernel<<<4 * sms, 256, 0, st>>>(points, sq, info, n_fixed, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w);
-  SCAN_LAUNCH_CHECK("db_adj_kernel");
+  static const int simt = getenv("SCAN_B200_DBSCAN_SIMT") ? atoi(getenv("SCAN_B200_DBSCAN_SIMT")) : 0;
+  if (simt) {  // fp32 FFMA verification kernel (bring-up / tests only)
+    db_adj_kernel<<<4 * sms, 256, 0, st>>>(points, sq, info, n_fixed, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w);
+    SCAN_LAUNCH_CHECK("db_adj_kernel");
+  } else {
+    int rc = launch_db_adj_tc(points, sq, info, n_fixed, cap, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w, st);
+    if (rc) return rc;
+  }
   db_count_rows_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, ws.count, ws.parent);
   SCAN_LAUNCH_CHECK("db_count_rows_kernel");
   db_union_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, min_samples, ws.count, ws.parent);
