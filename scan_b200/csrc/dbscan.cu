@@ -328,21 +328,68 @@ __global__ void __launch_bounds__(256) db_count_rows_kernel(const uint32_t* __re
   }
 }
 
-__global__ void __launch_bounds__(256) db_union_kernel(const uint32_t* __restrict__ adj, const int* info, int n_fixed,
-                                                       long long wpr, int min_samples, const int* __restrict__ count,
-                                                       int* __restrict__ parent) {
+// Connected components of the core-core graph in three cheap passes instead of one union per edge (a single dense
+// cluster of n points has n^2/2 edges):
+//   1. every core point hooks onto its SMALLEST-index core neighbour (one union per point, early exit);
+//   2. flatten (parent[i] = root);
+//   3. every core point re-scans its neighbours j < i and unions only where the flattened roots differ -- one
+//      coalesced-ish load of parent[j] per edge, real unions are rare after pass 1.
+__global__ void __launch_bounds__(256) db_union_min_kernel(const uint32_t* __restrict__ adj, const int* info, int n_fixed, long long wpr,
+                                                           int min_samples, const int* __restrict__ count, int* __restrict__ parent) {
   const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     if (count[i] < min_samples) continue;
-    const int nw = (i >> 5) + 1;  // only j < i
+    const int nw = (i >> 5) + 1;
+    int found = 0x7fffffff;
+    for (int w0 = 0; w0 < nw && found == 0x7fffffff; w0 += 32) {
+      const int w = w0 + lane;
+      int cand = 0x7fffffff;
+      if (w < nw) {
+        uint32_t bits = __ldg(adj + (long long)i * wpr + w);
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int j = (w << 5) + b;
+          if (j < i && count[j] >= min_samples) { cand = j; break; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+      found = cand;
+    }
+    if (lane == 0 && found != 0x7fffffff) uf_union(parent, i, found);
+  }
+}
+
+__global__ void __launch_bounds__(256) db_flatten_kernel(const int* info, int n_fixed, int* __restrict__ parent) {
+  const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = i;
+    while (true) {
+      const int p = parent[r];
+      if (p == r) break;
+      r = p;
+    }
+    parent[i] = r;  // only ever written with an ancestor: safe against concurrent readers
+  }
+}
+
+__global__ void __launch_bounds__(256) db_union_rest_kernel(const uint32_t* __restrict__ adj, const int* info, int n_fixed, long long wpr,
+                                                            int min_samples, const int* __restrict__ count, int* parent) {
+  const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    if (count[i] < min_samples) continue;
+    const int ri = parent[i];  // flattened root at the start of this pass
+    const int nw = (i >> 5) + 1;
     for (int w = lane; w < nw; w += 32) {
       uint32_t bits = __ldg(adj + (long long)i * wpr + w);
       while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
         const int j = (w << 5) + b;
-        if (j < i && count[j] >= min_samples) uf_union(parent, i, j);
+        if (j < i && count[j] >= min_samples && parent[j] != ri) uf_union(parent, i, j);
       }
     }
   }
@@ -470,8 +517,12 @@ static int cluster_points(const DbWs& ws, const float* points, const float* sq, 
   }
   db_count_rows_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, ws.count, ws.parent);
   SCAN_LAUNCH_CHECK("db_count_rows_kernel");
-  db_union_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, min_samples, ws.count, ws.parent);
-  SCAN_LAUNCH_CHECK("db_union_kernel");
+  db_union_min_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, min_samples, ws.count, ws.parent);
+  SCAN_LAUNCH_CHECK("db_union_min_kernel");
+  db_flatten_kernel<<<2 * sms, 256, 0, st>>>(info, n_fixed, ws.parent);
+  SCAN_LAUNCH_CHECK("db_flatten_kernel");
+  db_union_rest_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, min_samples, ws.count, ws.parent);
+  SCAN_LAUNCH_CHECK("db_union_rest_kernel");
   const int nb = (cap + DB_SB - 1) / DB_SB;
   db_roots_kernel<<<nb, DB_SB, 0, st>>>(info, n_fixed, min_samples, ws.count, ws.parent, ws.cid, ws.block_cnt2);
   SCAN_LAUNCH_CHECK("db_roots_kernel");

@@ -108,6 +108,9 @@ class ReferenceProbe(object):
         inner.DBSCAN_batch_cpu = db
 
     def __call__(self, locations=None, features=None, targets=None):
+        for f in features:
+            if f.requires_grad:
+                f.retain_grad()       # d(loss)/d(head_in output): what the hot path's backward produces
         out = self.inner(locations, features, targets)
         self.rec["features_in"] = list(features)  # the reference later overwrites the list entries in place (condgraph.py:382)
         # cloned: with GLOBAL_GCN=False the reference overwrites the sampled rows in place (condgraph.py:413)
@@ -132,6 +135,8 @@ def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture
         # which stay on cuDNN/cuBLAS) in true fp32; the only tf32 arithmetic left is the tcgen05 conditional conv
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
     # dropout off everywhere: parity runs are deterministic
     if hasattr(module, "multihead_attn"):
         a = module.multihead_attn
@@ -163,6 +168,11 @@ def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture
             else:
                 out = module(None, feats, targets=None, mode="target", forward_target=True)
         out_feats, loss_graph, act_loss, acts = out
+        fin = (probe.rec.get("features_in") if probe else module.last.get("features_in")) if step != "eval" else None
+        if fin is not None and not probe:
+            for f in fin:
+                if f.requires_grad:
+                    f.retain_grad()
         # ---- intermediate results ----
         if impl == "reference":
             rec = probe.rec
@@ -211,6 +221,10 @@ def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture
             total.backward()
             for l, f in enumerate(feats):
                 res[pre + "dfeat_l%d" % l] = _sample(f.grad)
+            if fin is not None:
+                for l, f in enumerate(fin):
+                    if f.grad is not None:
+                        res[pre + "dfin_l%d" % l] = _sample(f.grad)
             for pname, p in params.items():
                 if p.grad is not None:
                     res[pre + "grad/" + pname] = _sample(p.grad)
@@ -231,7 +245,7 @@ NOISE_KEYS = ("grad/cond_nx1.bias", "gradnorm/cond_nx1.bias", "grad/cond_2.bias"
 NOISE_ATOL = 5e-6
 
 
-def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=()):
+def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False):
     """Bit-exact for integer results, rtol (relative to the tensor's max magnitude) for floats.
     Returns list of human-readable mismatches."""
     bad = []
@@ -264,8 +278,16 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=()):
             d = np.abs(g.astype(np.float64) - w.astype(np.float64))
             frac = float((d > rtol * scale).mean())
             rel_l2 = float(np.linalg.norm(d) / max(np.linalg.norm(w.astype(np.float64)), 1e-30))
-            relu_path = ("dfeat_l" in k) or ("head_in." in k) or ("head_out." in k)
+            relu_path = ("dfeat_l" in k) or ("dfin_l" in k) or ("head_in." in k) or ("head_out." in k)
             if relu_path and frac <= 0.02 and rel_l2 <= 3 * rtol:
+                continue
+            # d(input features) and the head_in parameter gradients are produced by torch's OWN backward (cuDNN
+            # backward-data / backward-filter, GroupNorm) from d(features_in) = "dfin", which is what the scan_b200
+            # kernels produce and which is held to rtol above.  cuDNN's backward at the P3 shape differs from the CPU
+            # implementation by up to ~3e-3 relL2 on identical inputs (tools/diag_grad2.py: dfin agrees to 1e-6 while
+            # dfeat_l0 does not), so those torch-only tensors get a looser L2 bound.
+            torch_only = ("dfeat_l" in k) or ("grad/head_in." in k) or ("gradnorm/head_in." in k)
+            if device_run and torch_only and rel_l2 <= 2e-2:
                 continue
             bad.append("float mismatch %s: max|d|=%.3e scale=%.3e outliers=%.2f%% relL2=%.2e" % (k, err, scale, 100 * frac, rel_l2))
     for k in got:

@@ -18,7 +18,7 @@ def test_product_matches_reference_golden(name, golden_dir):
     want.pop("__meta__")
     cfg = harness.build_case(name)[0]
     got = harness.run_case(name, build_condgraph(cfg, 256), "product", device="cuda")
-    bad = harness.compare(got, want, rtol=1e-3)
+    bad = harness.compare(got, want, rtol=1e-3, device_run=True)
     assert not bad, "\n".join(bad[:25])
 
 
@@ -30,7 +30,7 @@ def test_full_size_source_target_eval_vs_oracle():
     cfg = harness.build_case("_full")[0]
     want = harness.run_case("_full", build_oracle(cfg), "oracle")
     got = harness.run_case("_full", build_condgraph(cfg, 256), "product", device="cuda")
-    bad = harness.compare(got, want, rtol=1e-3)
+    bad = harness.compare(got, want, rtol=1e-3, device_run=True)
     assert not bad, "\n".join(bad[:25])
 
 
