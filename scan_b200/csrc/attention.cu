@@ -5,9 +5,22 @@
 // makes 4 independent chunks of M 64-d sub-tokens; chunk b = rows [bM, (b+1)M) of the
 // row-major [4M, 64] reinterpretation.  fp32 FFMA arithmetic, 64x64 tiles staged in shared memory,
 // 4x4 register blocking, online softmax; backward recomputes P from the saved log-sum-exp.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace scan {
+
+// tensor-core versions (attention_tc.cu); the FFMA kernels below remain as the fp32 verification path
+// (SCAN_B200_ATTN_SIMT=1, tests / bring-up only)
+int launch_attn_fwd_tc(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
+                       float* lse, cudaStream_t st);
+int launch_attn_bwd_tc(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
+                       float scale, float drop_p, uint64_t seed, float* dq, float* dk, float* dv, cudaStream_t st);
+static int attn_simt() {
+  static const int v = getenv("SCAN_B200_ATTN_SIMT") ? atoi(getenv("SCAN_B200_ATTN_SIMT")) : 0;
+  return v;
+}
 
 constexpr int AT_D = 64;   // sub-token width
 constexpr int AT_T = 64;   // tile edge
@@ -305,6 +318,7 @@ extern "C" int scan_attn_fwd(const float* q, const float* k, const float* v, int
   using namespace scan;
   if (m == 0) return SCAN_OK;
   if (!q || !k || !v || !ctx || !lse || m < 0 || dropout_p < 0.f || dropout_p >= 1.f) return SCAN_EINVAL;
+  if (!attn_simt()) return launch_attn_fwd_tc(q, k, v, m, scale, dropout_p, seed, ctx, lse, (cudaStream_t)stream);
   int rc = set_attn_attrs();
   if (rc) return rc;
   dim3 grid((m + AT_T - 1) / AT_T, 4);
@@ -326,6 +340,7 @@ extern "C" int scan_attn_bwd(const float* q, const float* k, const float* v, con
   SCAN_CUDA_CHECK(cudaMemsetAsync(dq, 0, sizeof(float) * n_rows * AT_D, st));
   attn_delta_kernel<<<(unsigned)ceil_div(n_rows * 16, 256), 256, 0, st>>>(ctx, d_ctx, n_rows, delta_ws);
   SCAN_LAUNCH_CHECK("attn_delta_kernel");
+  if (!attn_simt()) return launch_attn_bwd_tc(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv, st);
   dim3 grid((m + AT_T - 1) / AT_T, 4);
   attn_bwd_kernel<<<grid, 256, 6 * AT_TILE * 4, st>>>(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv);
   SCAN_LAUNCH_CHECK("attn_bwd_kernel");

@@ -33,7 +33,8 @@ constexpr int CC_STAGE_BYTES = CC_BM * CC_BK * 4;  // 16384
 constexpr int CC_WBLK_BYTES = CC_N * CC_BK * 4;    // 2048
 constexpr int CC_W_BYTES = CC_KB * CC_WBLK_BYTES;  // 16384
 constexpr int CC_SMEM = 1024 + 2 * CC_W_BYTES + 2 * CC_STAGES * CC_STAGE_BYTES + 1024;  // hi + lo per stage
-constexpr int CC_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: epilogue, 8-11: tf32 hi/lo converter
+constexpr int CC_CONV_GROUPS = 2;  // converter warpgroups; group c converts the k-blocks with index % CC_CONV_GROUPS == c
+constexpr int CC_THREADS = 256 + 128 * CC_CONV_GROUPS;  // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: epilogue, 8..: converters
 constexpr int CC_MAX_PARTIALS = 1024;
 
 struct ActPtrs {
@@ -233,11 +234,14 @@ __global__ void __launch_bounds__(CC_THREADS, 1)
     }
   } else if (warp >= 8) {
     // ===== converter: fp32 stage -> tf32 hi (in place) + lo (second buffer); element-wise, swizzle-agnostic =====
-    const int t = threadIdx.x - 256;
-    int stage = 0;
-    uint32_t phase = 0;
+    const int t = (threadIdx.x - 256) & 127;
+    const int group = (threadIdx.x - 256) >> 7;
+    long long it = 0;  // running k-block index of this CTA: stage = it % CC_STAGES, phase = (it / CC_STAGES) & 1
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < CC_KB; ++kb) {
+      for (int kb = 0; kb < CC_KB; ++kb, ++it) {
+        if ((int)(it % CC_CONV_GROUPS) != group) continue;
+        const int stage = (int)(it % CC_STAGES);
+        const uint32_t phase = (uint32_t)((it / CC_STAGES) & 1);
         mbar_wait(smem_u32(full_bar + stage), phase);
         float4* hi = reinterpret_cast<float4*>(stages + stage * CC_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(stages_lo + stage * CC_STAGE_BYTES);
@@ -255,7 +259,6 @@ __global__ void __launch_bounds__(CC_THREADS, 1)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
         mbar_arrive(smem_u32(ready_bar + stage));
-        if (++stage == CC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {

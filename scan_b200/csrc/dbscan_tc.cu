@@ -6,9 +6,11 @@
 // tile overlaps the MMAs of the next).  Only tiles with bi <= bj are computed; the epilogue writes the bit block and
 // its transpose (warp ballots), so the full symmetric adjacency matrix is produced from half of the flops.
 //
-// Exactness: the tensor core reads the fp32 operands as tf32 (truncation, <= 2^-10 relative per operand), so the
-// Gram entry is only trusted outside a band |d2 - eps^2| > 2.2e-3 (|p_i|^2 + |p_j|^2); inside the band the pair is
-// re-evaluated exactly as sklearn does it (float64 accumulation of the fp32 inputs, scan::db_exact_within).
+// Exactness: operands are pre-split into tf32 hi + lo parts (db_split_kernel) and the Gram entry is accumulated as
+// hi.hi + hi.lo + lo.hi (3xTF32, fp32 accumulate): ~1e-6 relative.  It is only trusted outside the band
+// |d2 - eps^2| > 2.5e-5 (|p_i|^2 + |p_j|^2) (worst-case fp32 accumulation bound over 256 terms); inside the band the
+// pair is re-evaluated exactly as sklearn does it (float64 accumulation of the fp32 inputs, scan::db_exact_within).
+// (A single-tf32 Gram needs a 2.2e-3 band: measured 13 ms of divergent fp64 rechecks at n = 36 k -- round-1 run 5.)
 // Labels therefore stay bit-exact with sklearn (tests/test_gpu_kernels.py) while the bulk of the n^2 x 256
 // arithmetic runs at tensor-core speed.
 #include "dbscan_common.cuh"
@@ -18,8 +20,9 @@ namespace scan {
 
 constexpr int GT = 128;                       // tile edge (points)
 constexpr int GK = 32;                        // channels per stage
-constexpr int G_STAGES = 6;
-constexpr int G_STAGE_BYTES = 2 * GT * GK * 4;  // A + B boxes: 32 KB
+constexpr int G_STAGES = 3;
+constexpr int G_BOX_BYTES = GT * GK * 4;        // 16 KB
+constexpr int G_STAGE_BYTES = 4 * G_BOX_BYTES;  // A_hi, A_lo, B_hi, B_lo boxes: 64 KB
 constexpr int G_SMEM = 1024 + G_STAGES * G_STAGE_BYTES + 1024;
 constexpr int G_THREADS = 256;
 constexpr uint32_t G_IDESC = umma_idesc_tf32(GT, GT);
@@ -104,8 +107,11 @@ __global__ void __launch_bounds__(G_THREADS, 1)
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           mbar_expect_tx(smem_u32(full_bar + stage), G_STAGE_BYTES);
           uint8_t* st = stages + stage * G_STAGE_BYTES;
-          tma_load_2d(smem_u32(st), &tmap, smem_u32(full_bar + stage), kb * GK, bi * GT);
-          tma_load_2d(smem_u32(st + GT * GK * 4), &tmap, smem_u32(full_bar + stage), kb * GK, bj * GT);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          tma_load_2d(smem_u32(st), &tmap, fb, kb * GK, bi * GT);                          // A hi
+          tma_load_2d(smem_u32(st + G_BOX_BYTES), &tmap, fb, dim + kb * GK, bi * GT);      // A lo
+          tma_load_2d(smem_u32(st + 2 * G_BOX_BYTES), &tmap, fb, kb * GK, bj * GT);        // B hi
+          tma_load_2d(smem_u32(st + 3 * G_BOX_BYTES), &tmap, fb, dim + kb * GK, bj * GT);  // B lo
           if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -121,11 +127,15 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(smem_u32(full_bar + stage), phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(stages + stage * G_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + GT * GK * 4;
+          const uint32_t ah = smem_u32(stages + stage * G_STAGE_BYTES);
+          const uint32_t al = ah + G_BOX_BYTES, bh = ah + 2 * G_BOX_BYTES, bl = ah + 3 * G_BOX_BYTES;
 #pragma unroll
-          for (int k = 0; k < GK / 8; ++k)
-            umma_tf32(d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), G_IDESC, (kb | k) != 0);
+          for (int k = 0; k < GK / 8; ++k) {
+            const uint64_t dah = umma_desc_sw128(ah + k * 32), dbh = umma_desc_sw128(bh + k * 32);
+            umma_tf32(d, umma_desc_sw128(al + k * 32), dbh, G_IDESC, (kb | k) != 0);
+            umma_tf32(d, dah, umma_desc_sw128(bl + k * 32), G_IDESC, 1);
+            umma_tf32(d, dah, dbh, G_IDESC, 1);
+          }
           umma_commit(smem_u32(empty_bar + stage));
           if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             } else {
               const float sj = __ldg(sq + j);
               const float d2 = si + sj - 2.f * g[c];
-              const float tol = 2.2e-3f * (si + sj) + 1e-6f * eps2f;
+              const float tol = 2.5e-5f * (si + sj) + 1e-7f * eps2f;
               if (fabsf(d2 - eps2f) <= tol) {
                 within = db_exact_within(points + (long long)i * dim, points + (long long)j * dim, dim, eps2);
                 ++n_re;
@@ -195,11 +205,11 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 
 static int g_adj_attr = 0;
 
-int launch_db_adj_tc(const float* points, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
-                     long long wpr, uint32_t* adj, int* info_w, cudaStream_t st) {
-  if (dim % GK || ((uintptr_t)points & 15) || wpr % 4) return SCAN_EINVAL;
+int launch_db_adj_tc(const float* points, const float* points_hl, const float* sq, const int* info, int n_fixed, int cap, int dim,
+                     float eps2f, double eps2, long long wpr, uint32_t* adj, int* info_w, cudaStream_t st) {
+  if (dim % GK || ((uintptr_t)points_hl & 15) || wpr % 4) return SCAN_EINVAL;
   CUtensorMap map;
-  int rc = make_rowmajor_map(&map, points, (uint64_t)cap, (uint64_t)dim, GT);
+  int rc = make_rowmajor_map(&map, points_hl, (uint64_t)cap, (uint64_t)(2 * dim), GT);
   if (rc) return rc;
   if (!g_adj_attr) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(db_adj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));

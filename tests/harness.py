@@ -286,7 +286,7 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False):
             d = np.abs(g.astype(np.float64) - w.astype(np.float64))
             frac = float((d > rtol * scale).mean())
             rel_l2 = float(np.linalg.norm(d) / max(np.linalg.norm(w.astype(np.float64)), 1e-30))
-            relu_path = ("dfeat_l" in k) or ("dfin_l" in k) or ("head_in." in k) or ("head_out." in k) or ("proto_cls_hidden" in k)
+            relu_path = ("dfeat_l" in k) or ("dfin_l" in k) or ("dfin_direct" in k) or ("head_in." in k) or ("head_out." in k) or ("proto_cls_hidden" in k)
             if relu_path and frac <= 0.02 and rel_l2 <= 3 * rtol:
                 continue
             # d(input features) and the head_in parameter gradients are produced by torch's OWN backward (cuDNN
