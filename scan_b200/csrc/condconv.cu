@@ -292,6 +292,8 @@ __global__ void __launch_bounds__(CC_THREADS, 1)
   }
 }
 
+#include "condconv_ts.inl"
+
 // ---------------------------------------------------------------------------- forward, fp32 FFMA (verification)
 __global__ void __launch_bounds__(128) condconv_fwd_simt_kernel(Levels lv, const float* __restrict__ rows, const float* __restrict__ weight,
                                                                 ActPtrs act, const float* __restrict__ bias,
@@ -541,7 +543,7 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
     SCAN_LAUNCH_CHECK("condconv_fwd_simt_kernel");
     return SCAN_OK;
   }
-  if (impl != 0) return SCAN_EINVAL;
+  if (impl != 0 && impl != 2) return SCAN_EINVAL;
   CUtensorMap mx, mw;
   rc = make_rowmajor_map(&mx, rows, (uint64_t)R, CC_C, CC_BM);
   if (rc) return rc;
@@ -550,6 +552,17 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
   if (!g_fwd_attr_set) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
     g_fwd_attr_set = 1;
+  }
+  if (impl == 2) {  // A operands in tensor memory (condconv_ts.inl)
+    static int ts_attr = 0;
+    if (!ts_attr) {
+      SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+      ts_attr = 1;
+    }
+    condconv_fwd_ts_kernel<<<grid, TS_THREADS, TS_SMEM, st>>>(mx, mw, lv, act, bias, labels, labels ? loss_partials : nullptr, flags,
+                                                             num_classes, act_mode, num_tiles);
+    SCAN_LAUNCH_CHECK("condconv_fwd_ts_kernel");
+    return SCAN_OK;
   }
   condconv_fwd_tc_kernel<<<grid, CC_THREADS, CC_SMEM, st>>>(mx, mw, lv, act, bias, labels, labels ? loss_partials : nullptr, flags,
                                                            num_classes, act_mode, num_tiles);

@@ -161,15 +161,18 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         float g[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GT + c0, g);
         uint32_t word = 0;
+        // |p_j|^2 of the 32 columns of this block: ONE coalesced load per lane, broadcast by shuffle below (a dependent
+        // global load per column cost 38 k cycles per tile: ncu source view, profiles/r01_dbscan_adj.txt)
+        const float sj_lane = (j0 + c0 + lane < n) ? __ldg(sq + j0 + c0 + lane) : 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int j = j0 + c0 + c;
           bool within = false;
+          const float sj = __shfl_sync(0xffffffffu, sj_lane, c);
           if (i < n && j < n) {
             if (i == j) {
               within = true;
             } else {
-              const float sj = __ldg(sq + j);
               const float d2 = si + sj - 2.f * g[c];
               const float tol = 2.5e-5f * (si + sj) + 1e-7f * eps2f;
               if (fabsf(d2 - eps2f) <= tol) {
