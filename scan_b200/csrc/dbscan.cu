@@ -22,7 +22,6 @@ struct DbWs {
   int* sel_flat;       // [cap] flat entry index ((n*CLS+cls)*H+y)*W+x
   float* sel_act;      // [cap]
   float* points;       // [cap, dim]
-  float* points_hl;    // [cap, 2*dim]: tf32 hi part | lo part of every point (operands of the 3xTF32 Gram)
   float* sq;           // [cap]
   uint32_t* adj;       // [cap, wpr]
   int* count;          // [cap]
@@ -48,7 +47,6 @@ static long long dbws_layout(long long cap, long long n_entries, int dim, char* 
   w.sel_flat = (int*)take(cap * 4);
   w.sel_act = (float*)take(cap * 4);
   w.points = (float*)take(cap * dim * 4);
-  w.points_hl = (float*)take(cap * dim * 8);
   w.sq = (float*)take(cap * 4);
   w.adj = (uint32_t*)take(cap * wpr * 4);
   w.count = (int*)take(cap * 4);
@@ -178,27 +176,6 @@ __global__ void __launch_bounds__(256) db_points_kernel(const float* __restrict_
     s = warp_sum(s);
     if (lane == 0) sq[i] = s;
     if (__any_sync(0xffffffffu, nz) && lane == 0) atomicOr(info_w + 6, 1);
-  }
-}
-
-// x -> (hi = rna_tf32(x), lo = x - hi): row i of points_hl = [hi(0..dim) | lo(0..dim)]
-__global__ void __launch_bounds__(256) db_split_kernel(const float* __restrict__ points, const int* info, int n_fixed, int dim,
-                                                       float* __restrict__ points_hl) {
-  const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
-  const long long total = (long long)n * (dim / 4);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / (dim / 4);
-    const int c4 = (int)(i - row * (dim / 4));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(points + row * dim) + c4);
-    float4 h;
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u);
-    float4* dst = reinterpret_cast<float4*>(points_hl + row * 2 * dim);
-    dst[c4] = h;
-    dst[dim / 4 + c4] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   }
 }
 
@@ -535,9 +512,12 @@ static int cluster_points(const DbWs& ws, const float* points, const float* sq, 
     db_adj_kernel<<<4 * sms, 256, 0, st>>>(points, sq, info, n_fixed, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w);
     SCAN_LAUNCH_CHECK("db_adj_kernel");
   } else {
-    db_split_kernel<<<4 * sms, 256, 0, st>>>(points, info, n_fixed, dim, ws.points_hl);
-    SCAN_LAUNCH_CHECK("db_split_kernel");
-    int rc = launch_db_adj_tc(points, ws.points_hl, sq, info, n_fixed, cap, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w, st);
+    int rc = launch_db_adj_tc(points, sq, info, n_fixed, cap, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w, st);
+    if (rc == SCAN_ENOTSUP) {  // point width other than 256: FFMA tiles
+      db_adj_kernel<<<4 * sms, 256, 0, st>>>(points, sq, info, n_fixed, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w);
+      SCAN_LAUNCH_CHECK("db_adj_kernel");
+      rc = SCAN_OK;
+    }
     if (rc) return rc;
   }
   db_count_rows_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, ws.count, ws.parent);

@@ -19,7 +19,7 @@ static __device__ __noinline__ bool db_exact_within(const float* __restrict__ a,
 }
 
 
-int launch_db_adj_tc(const float* points, const float* points_hl, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
+int launch_db_adj_tc(const float* points, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
                      long long wpr, uint32_t* adj, int* info_w, cudaStream_t st);
 
 }  // namespace scan

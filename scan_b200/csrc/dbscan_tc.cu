@@ -1,43 +1,36 @@
 // K2 (distance phase): pairwise squared distances of the DBSCAN point set on the tensor cores.
 //
-// Gram tiles G = P_i . P_j^T (128 x 128, reduction 256) with tcgen05.mma kind::tf32: both operands are K-major row
-// blocks of the same [n, 256] point matrix, streamed by TMA ([128 x 32] fp32 boxes, 128-byte swizzle) through a
-// 6-stage mbarrier ring; fp32 accumulators live in TMEM (2 x 128 columns, double-buffered so the epilogue of one
-// tile overlaps the MMAs of the next).  Only tiles with bi <= bj are computed; the epilogue writes the bit block and
-// its transpose (warp ballots), so the full symmetric adjacency matrix is produced from half of the flops.
+// Gram tiles G = P_i . P_j^T (128 x 128, reduction 256) with tcgen05.mma kind::tf32 straight from the fp32 point
+// matrix (K-major rows, TMA [128 x 32] boxes, 128-byte swizzle).  The kernel is L2-bandwidth bound, not MMA bound
+// (a 128x128x256 tile needs 256 KB of operands for 8.4 MFLOP), so the schedule maximises operand reuse:
+//   * a CTA works on a UNIT = one row block bi and a run of up to DB_CHUNK column blocks bj >= bi; the A tile (128 points
+//     x 256 dims = 128 KB) is loaded ONCE per unit and stays resident in shared memory, only B tiles stream through a
+//     4-stage ring -> 128 KB of L2 traffic per tile instead of 256 KB (and instead of 512 KB for a 3xTF32 variant:
+//     measured 5.1 ms at n = 36 k, round-1 run 7);
+//   * only tiles with bj >= bi are computed; the epilogue writes the bit block and its transpose (warp ballots);
+//   * fp32 accumulators in TMEM, 2 x 128 columns, so the epilogue of one tile overlaps the MMAs of the next.
 //
-// Exactness: operands are pre-split into tf32 hi + lo parts (db_split_kernel) and the Gram entry is accumulated as
-// hi.hi + hi.lo + lo.hi (3xTF32, fp32 accumulate): ~1e-6 relative.  It is only trusted outside the band
-// |d2 - eps^2| > 2.5e-5 (|p_i|^2 + |p_j|^2) (worst-case fp32 accumulation bound over 256 terms); inside the band the
-// pair is re-evaluated exactly as sklearn does it (float64 accumulation of the fp32 inputs, scan::db_exact_within).
-// (A single-tf32 Gram needs a 2.2e-3 band: measured 13 ms of divergent fp64 rechecks at n = 36 k -- round-1 run 5.)
-// Labels therefore stay bit-exact with sklearn (tests/test_gpu_kernels.py) while the bulk of the n^2 x 256
-// arithmetic runs at tensor-core speed.
+// Exactness: the tensor core truncates the fp32 operands to tf32 (<= 2^-10 relative per operand), so a Gram entry is
+// only trusted outside the band |d2 - eps^2| > 2.2e-3 (|p_i|^2 + |p_j|^2); pairs inside the band are re-evaluated
+// exactly as sklearn does (float64 accumulation of the fp32 inputs) by the WHOLE WARP cooperatively (8 dims per lane,
+// shuffle reduction) -- a per-thread recheck serialises 256-step fp64 loops behind one lane (measured 13 ms).
+// Labels stay bit-exact with sklearn (tests/test_gpu_kernels.py::test_dbscan_*).
 #include "dbscan_common.cuh"
 #include "tc_common.cuh"
 
 namespace scan {
 
-constexpr int GT = 128;                       // tile edge (points)
-constexpr int GK = 32;                        // channels per stage
-constexpr int G_STAGES = 3;
-constexpr int G_BOX_BYTES = GT * GK * 4;        // 16 KB
-constexpr int G_STAGE_BYTES = 4 * G_BOX_BYTES;  // A_hi, A_lo, B_hi, B_lo boxes: 64 KB
-constexpr int G_SMEM = 1024 + G_STAGES * G_STAGE_BYTES + 1024;
+constexpr int GT = 128;   // tile edge (points)
+constexpr int GK = 32;    // channels per TMA box
+constexpr int G_DIM = 256;
+constexpr int G_KB = G_DIM / GK;                 // 8 k-blocks
+constexpr int G_BOX_BYTES = GT * GK * 4;         // 16 KB
+constexpr int G_A_BYTES = G_KB * G_BOX_BYTES;    // 128 KB resident A tile
+constexpr int G_STAGES = 4;                      // B ring
+constexpr int G_SMEM = 1024 + G_A_BYTES + G_STAGES * G_BOX_BYTES + 1024;
 constexpr int G_THREADS = 256;
+constexpr int DB_CHUNK = 48;                     // column blocks per unit
 constexpr uint32_t G_IDESC = umma_idesc_tf32(GT, GT);
-
-__device__ __forceinline__ void tile_of(long long t, int nt, int& bi, int& bj) {
-  // t enumerates (bi, bj), bi <= bj, row by row: row bi starts at bi*nt - bi*(bi-1)/2
-  double x = (2.0 * nt + 1.0 - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5;
-  int b = (int)x;
-  if (b < 0) b = 0;
-  if (b > nt - 1) b = nt - 1;
-  while ((long long)b * nt - (long long)b * (b - 1) / 2 > t) --b;
-  while ((long long)(b + 1) * nt - (long long)(b + 1) * b / 2 <= t) ++b;
-  bi = b;
-  bj = b + (int)(t - ((long long)b * nt - (long long)b * (b - 1) / 2));
-}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -55,35 +48,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Work enumeration shared by the three roles: units (bi, [j_begin, j_end)) in row order, unit u belongs to CTA u % grid.
+struct UnitIter {
+  int nt, bi, jb, u;
+  __device__ UnitIter(int nt_) : nt(nt_), bi(0), jb(0), u(0) {}
+  // advances to the next unit owned by this CTA; returns false when exhausted
+  __device__ bool next(int& row, int& j0, int& j1) {
+    while (bi < nt) {
+      const int mine = (u % (int)gridDim.x) == (int)blockIdx.x;
+      row = bi;
+      j0 = bi + jb;
+      j1 = min(nt, j0 + DB_CHUNK);
+      ++u;
+      jb += DB_CHUNK;
+      if (bi + jb >= nt) { ++bi; jb = 0; }
+      if (mine) return true;
+    }
+    return false;
+  }
+};
+
+// exact sklearn test by the whole warp: lanes split the dims, fp64 accumulation, shuffle reduction
+__device__ __forceinline__ bool warp_exact_within(const float* __restrict__ a, const float* __restrict__ b, int dim, double eps2, int lane) {
+  double sa = 0.0, sb = 0.0, ab = 0.0;
+  for (int d = lane; d < dim; d += 32) {
+    const double x = (double)__ldg(a + d), y = (double)__ldg(b + d);
+    sa = fma(x, x, sa);
+    sb = fma(y, y, sb);
+    ab = fma(x, y, ab);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+  }
+  double d2 = sa + sb - 2.0 * ab;
+  if (d2 < 0.0) d2 = 0.0;
+  return d2 <= eps2;
+}
+
 __global__ void __launch_bounds__(G_THREADS, 1)
     db_adj_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ points, const float* __restrict__ sq,
-                     const int* info, int n_fixed, int dim, float eps2f, double eps2, long long wpr, uint32_t* __restrict__ adj,
-                     int* info_w) {
+                     const int* info, int n_fixed, float eps2f, double eps2, long long wpr, uint32_t* __restrict__ adj, int* info_w) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stages = smem;
-  uint64_t* bars = (uint64_t*)(stages + G_STAGES * G_STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + G_STAGES;
-  uint64_t* acc_full = bars + 2 * G_STAGES;       // [2]
-  uint64_t* acc_empty = bars + 2 * G_STAGES + 2;  // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * G_STAGES + 4);
+  uint8_t* a_tile = smem;
+  uint8_t* stages = smem + G_A_BYTES;
+  uint64_t* bars = (uint64_t*)(stages + G_STAGES * G_BOX_BYTES);
+  uint64_t* b_full = bars;                         // [G_STAGES]
+  uint64_t* b_empty = bars + G_STAGES;             // [G_STAGES]
+  uint64_t* acc_full = bars + 2 * G_STAGES;        // [2]
+  uint64_t* acc_empty = bars + 2 * G_STAGES + 2;   // [2]
+  uint64_t* a_full = bars + 2 * G_STAGES + 4;
+  uint64_t* a_free = bars + 2 * G_STAGES + 5;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * G_STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
   const int nt = (n + GT - 1) / GT;
-  const long long total = (long long)nt * (nt + 1) / 2;
-  const int kblocks = dim / GK;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < G_STAGES; ++i) {
-      mbar_init(smem_u32(full_bar + i), 1);
-      mbar_init(smem_u32(empty_bar + i), 1);
+      mbar_init(smem_u32(b_full + i), 1);
+      mbar_init(smem_u32(b_empty + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(acc_full + i), 1);
       mbar_init(smem_u32(acc_empty + i), 128);
     }
+    mbar_init(smem_u32(a_full), 1);
+    mbar_init(smem_u32(a_free), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -97,105 +132,109 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===== TMA producer =====
     if (lane == 0) {
-      int stage = 0;
+      UnitIter it(nt);
+      int row, j0, j1, stage = 0, units = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        int bi, bj;
-        tile_of(t, nt, bi, bj);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-          mbar_expect_tx(smem_u32(full_bar + stage), G_STAGE_BYTES);
-          uint8_t* st = stages + stage * G_STAGE_BYTES;
-          const uint32_t fb = smem_u32(full_bar + stage);
-          tma_load_2d(smem_u32(st), &tmap, fb, kb * GK, bi * GT);                          // A hi
-          tma_load_2d(smem_u32(st + G_BOX_BYTES), &tmap, fb, dim + kb * GK, bi * GT);      // A lo
-          tma_load_2d(smem_u32(st + 2 * G_BOX_BYTES), &tmap, fb, kb * GK, bj * GT);        // B hi
-          tma_load_2d(smem_u32(st + 3 * G_BOX_BYTES), &tmap, fb, dim + kb * GK, bj * GT);  // B lo
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+      while (it.next(row, j0, j1)) {
+        if (units > 0) mbar_wait(smem_u32(a_free), (uint32_t)((units - 1) & 1));  // MMAs of the previous unit retired
+        mbar_expect_tx(smem_u32(a_full), G_A_BYTES);
+        for (int kb = 0; kb < G_KB; ++kb) tma_load_2d(smem_u32(a_tile + kb * G_BOX_BYTES), &tmap, smem_u32(a_full), kb * GK, row * GT);
+        for (int bj = j0; bj < j1; ++bj) {
+          for (int kb = 0; kb < G_KB; ++kb) {
+            mbar_wait(smem_u32(b_empty + stage), phase ^ 1);
+            mbar_expect_tx(smem_u32(b_full + stage), G_BOX_BYTES);
+            tma_load_2d(smem_u32(stages + stage * G_BOX_BYTES), &tmap, smem_u32(b_full + stage), kb * GK, bj * GT);
+            if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
+        ++units;
       }
     }
   } else if (warp == 1) {
+    // ===== MMA issuer =====
     if (lane == 0) {
-      int stage = 0, acc = 0;
+      UnitIter it(nt);
+      int row, j0, j1, stage = 0, acc = 0, units = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        mbar_wait(smem_u32(acc_empty + acc), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + acc * GT;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(smem_u32(full_bar + stage), phase);
+      while (it.next(row, j0, j1)) {
+        mbar_wait(smem_u32(a_full), (uint32_t)(units & 1));
+        for (int bj = j0; bj < j1; ++bj) {
+          mbar_wait(smem_u32(acc_empty + acc), acc_phase ^ 1);
           tcgen05_fence_after();
-          const uint32_t ah = smem_u32(stages + stage * G_STAGE_BYTES);
-          const uint32_t al = ah + G_BOX_BYTES, bh = ah + 2 * G_BOX_BYTES, bl = ah + 3 * G_BOX_BYTES;
+          const uint32_t d = tmem_base + acc * GT;
+          for (int kb = 0; kb < G_KB; ++kb) {
+            mbar_wait(smem_u32(b_full + stage), phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(a_tile + kb * G_BOX_BYTES);
+            const uint32_t b_addr = smem_u32(stages + stage * G_BOX_BYTES);
 #pragma unroll
-          for (int k = 0; k < GK / 8; ++k) {
-            const uint64_t dah = umma_desc_sw128(ah + k * 32), dbh = umma_desc_sw128(bh + k * 32);
-            umma_tf32(d, umma_desc_sw128(al + k * 32), dbh, G_IDESC, (kb | k) != 0);
-            umma_tf32(d, dah, umma_desc_sw128(bl + k * 32), G_IDESC, 1);
-            umma_tf32(d, dah, dbh, G_IDESC, 1);
+            for (int k = 0; k < GK / 8; ++k)
+              umma_tf32(d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), G_IDESC, (kb | k) != 0);
+            umma_commit(smem_u32(b_empty + stage));
+            if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(smem_u32(empty_bar + stage));
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(smem_u32(acc_full + acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(smem_u32(acc_full + acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        umma_commit(smem_u32(a_free));  // arrives when every MMA reading this A tile has retired
+        ++units;
       }
     }
   } else if (warp >= 4) {
+    // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) = rows of the tile =====
     const int q = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     int n_re = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-      int bi, bj;
-      tile_of(t, nt, bi, bj);
-      const int i0 = bi * GT, j0 = bj * GT;
+    UnitIter it(nt);
+    int row, jb0, jb1;
+    while (it.next(row, jb0, jb1)) {
+      const int i0 = row * GT;
       const int i = i0 + q * 32 + lane;
       const float si = i < n ? __ldg(sq + i) : 0.f;
-      mbar_wait(smem_u32(acc_full + acc), acc_phase);
-      tcgen05_fence_after();
+      for (int bj = jb0; bj < jb1; ++bj) {
+        const int j0 = bj * GT;
+        mbar_wait(smem_u32(acc_full + acc), acc_phase);
+        tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < GT; c0 += 32) {
-        float g[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GT + c0, g);
-        uint32_t word = 0;
-        // |p_j|^2 of the 32 columns of this block: ONE coalesced load per lane, broadcast by shuffle below (a dependent
-        // global load per column cost 38 k cycles per tile: ncu source view, profiles/r01_dbscan_adj.txt)
-        const float sj_lane = (j0 + c0 + lane < n) ? __ldg(sq + j0 + c0 + lane) : 0.f;
+        for (int c0 = 0; c0 < GT; c0 += 32) {
+          float g[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GT + c0, g);
+          const float sj_lane = (j0 + c0 + lane < n) ? __ldg(sq + j0 + c0 + lane) : 0.f;
+          uint32_t word = 0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int j = j0 + c0 + c;
-          bool within = false;
-          const float sj = __shfl_sync(0xffffffffu, sj_lane, c);
-          if (i < n && j < n) {
-            if (i == j) {
-              within = true;
-            } else {
-              const float d2 = si + sj - 2.f * g[c];
-              const float tol = 2.5e-5f * (si + sj) + 1e-7f * eps2f;
-              if (fabsf(d2 - eps2f) <= tol) {
-                within = db_exact_within(points + (long long)i * dim, points + (long long)j * dim, dim, eps2);
-                ++n_re;
-              } else {
-                within = d2 < eps2f;
-              }
+          for (int c = 0; c < 32; ++c) {
+            const int j = j0 + c0 + c;
+            const float sj = __shfl_sync(0xffffffffu, sj_lane, c);
+            const bool valid = (i < n) && (j < n);
+            const float d2 = si + sj - 2.f * g[c];
+            const float tol = 2.2e-3f * (si + sj) + 1e-6f * eps2f;
+            bool within = valid && (i == j || d2 < eps2f);
+            const bool unsure = valid && (i != j) && (fabsf(d2 - eps2f) <= tol);
+            uint32_t todo = __ballot_sync(0xffffffffu, unsure);
+            while (todo) {  // warp-cooperative exact re-evaluation of every in-band pair of this column
+              const int src = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const int ii = i0 + q * 32 + src;
+              const bool r = warp_exact_within(points + (long long)ii * G_DIM, points + (long long)j * G_DIM, G_DIM, eps2, lane);
+              if (lane == src) within = r;
+              ++n_re;
+            }
+            word |= (within ? 1u : 0u) << c;
+            if (row != bj) {  // transposed block: one ballot = the word of row j for this warp's 32 rows
+              const uint32_t tw = __ballot_sync(0xffffffffu, within);
+              if (lane == c && j < n) adj[(long long)j * wpr + (i0 >> 5) + q] = tw;
             }
           }
-          word |= (within ? 1u : 0u) << c;
-          if (bi != bj) {  // transposed block: bit (row j, column i); one ballot = the word of row j for this warp's 32 rows
-            const uint32_t tw = __ballot_sync(0xffffffffu, within);
-            if (lane == c && j < n) adj[(long long)j * wpr + (i0 >> 5) + q] = tw;
-          }
+          if (i < n) adj[(long long)i * wpr + ((j0 + c0) >> 5)] = word;
         }
-        if (i < n) adj[(long long)i * wpr + ((j0 + c0) >> 5)] = word;
+        tcgen05_fence_before();
+        mbar_arrive(smem_u32(acc_empty + acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tcgen05_fence_before();
-      mbar_arrive(smem_u32(acc_empty + acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    n_re = (int)warp_sum((float)n_re);
     if (lane == 0 && n_re) atomicAdd(info_w + 5, n_re);
   }
   tcgen05_fence_before();
@@ -208,17 +247,18 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 
 static int g_adj_attr = 0;
 
-int launch_db_adj_tc(const float* points, const float* points_hl, const float* sq, const int* info, int n_fixed, int cap, int dim,
-                     float eps2f, double eps2, long long wpr, uint32_t* adj, int* info_w, cudaStream_t st) {
-  if (dim % GK || ((uintptr_t)points_hl & 15) || wpr % 4) return SCAN_EINVAL;
+int launch_db_adj_tc(const float* points, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
+                     long long wpr, uint32_t* adj, int* info_w, cudaStream_t st) {
+  if (dim != G_DIM) return SCAN_ENOTSUP;  // callers fall back to the FFMA tile kernel for other widths
+  if (((uintptr_t)points & 15) || wpr % 4) return SCAN_EINVAL;
   CUtensorMap map;
-  int rc = make_rowmajor_map(&map, points_hl, (uint64_t)cap, (uint64_t)(2 * dim), GT);
+  int rc = make_rowmajor_map(&map, points, (uint64_t)cap, (uint64_t)dim, GT);
   if (rc) return rc;
   if (!g_adj_attr) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(db_adj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     g_adj_attr = 1;
   }
-  db_adj_tc_kernel<<<sm_count(), G_THREADS, G_SMEM, st>>>(map, points, sq, info, n_fixed, dim, eps2f, eps2, wpr, adj, info_w);
+  db_adj_tc_kernel<<<sm_count(), G_THREADS, G_SMEM, st>>>(map, points, sq, info, n_fixed, eps2f, eps2, wpr, adj, info_w);
   SCAN_LAUNCH_CHECK("db_adj_tc_kernel");
   return SCAN_OK;
 }
