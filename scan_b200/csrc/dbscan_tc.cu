@@ -69,7 +69,7 @@ struct UnitIter {
 };
 
 // exact sklearn test by the whole warp: lanes split the dims, fp64 accumulation, shuffle reduction
-__device__ __forceinline__ bool warp_exact_within(const float* __restrict__ a, const float* __restrict__ b, int dim, double eps2, int lane) {
+__device__ __noinline__ bool warp_exact_within(const float* __restrict__ a, const float* __restrict__ b, int dim, double eps2, int lane) {
   double sa = 0.0, sb = 0.0, ab = 0.0;
   for (int d = lane; d < dim; d += 32) {
     const double x = (double)__ldg(a + d), y = (double)__ldg(b + d);
@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(G_THREADS, 1)
           float g[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GT + c0, g);
           const float sj_lane = (j0 + c0 + lane < n) ? __ldg(sq + j0 + c0 + lane) : 0.f;
-          uint32_t word = 0;
+          // pass 1 (unrolled, tiny body): fp32 decision + "inside the band" bit for each of the 32 columns
+          uint32_t word = 0, unsure = 0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const int j = j0 + c0 + c;
@@ -211,20 +212,30 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             const bool valid = (i < n) && (j < n);
             const float d2 = si + sj - 2.f * g[c];
             const float tol = 2.2e-3f * (si + sj) + 1e-6f * eps2f;
-            bool within = valid && (i == j || d2 < eps2f);
-            const bool unsure = valid && (i != j) && (fabsf(d2 - eps2f) <= tol);
-            uint32_t todo = __ballot_sync(0xffffffffu, unsure);
-            while (todo) {  // warp-cooperative exact re-evaluation of every in-band pair of this column
-              const int src = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const int ii = i0 + q * 32 + src;
-              const bool r = warp_exact_within(points + (long long)ii * G_DIM, points + (long long)j * G_DIM, G_DIM, eps2, lane);
-              if (lane == src) within = r;
+            word |= ((valid && (i == j || d2 < eps2f)) ? 1u : 0u) << c;
+            unsure |= ((valid && (i != j) && (fabsf(d2 - eps2f) <= tol)) ? 1u : 0u) << c;
+          }
+          // pass 2 (rolled): every in-band pair is re-evaluated exactly by the whole warp.  Keeping this out of the
+          // unrolled loop matters: the fully unrolled variant was 220 KB of SASS and instruction-fetch bound (ncu: no_inst)
+          uint32_t lanes = __ballot_sync(0xffffffffu, unsure != 0u);
+          while (lanes) {
+            const int src = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            uint32_t bits = __shfl_sync(0xffffffffu, unsure, src);
+            const float* pi = points + (long long)(i0 + q * 32 + src) * G_DIM;
+            while (bits) {
+              const int c = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const bool r = warp_exact_within(pi, points + (long long)(j0 + c0 + c) * G_DIM, G_DIM, eps2, lane);
+              if (lane == src) word = (word & ~(1u << c)) | ((r ? 1u : 0u) << c);
               ++n_re;
             }
-            word |= (within ? 1u : 0u) << c;
-            if (row != bj) {  // transposed block: one ballot = the word of row j for this warp's 32 rows
-              const uint32_t tw = __ballot_sync(0xffffffffu, within);
+          }
+          if (row != bj) {  // transposed block: ballot c = the word of row (j0+c0+c) for this warp's 32 rows
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) {
+              const uint32_t tw = __ballot_sync(0xffffffffu, (word >> c) & 1u);
+              const int j = j0 + c0 + c;
               if (lane == c && j < n) adj[(long long)j * wpr + (i0 >> 5) + q] = tw;
             }
           }
