@@ -7,7 +7,7 @@
 //     x 256 dims = 128 KB) is loaded ONCE per unit and stays resident in shared memory, only B tiles stream through a
 //     4-stage ring -> 128 KB of L2 traffic per tile instead of 256 KB (and instead of 512 KB for a 3xTF32 variant:
 //     measured 5.1 ms at n = 36 k, round-1 run 7);
-//   * only tiles with bj >= bi are computed; the epilogue writes the bit block and its transpose (warp ballots);
+//   * only tiles with bj >= bi are computed; db_mirror_kernel transposes the bit blocks afterwards;
 //   * fp32 accumulators in TMEM, 2 x 128 columns, so the epilogue of one tile overlaps the MMAs of the next.
 //
 // Exactness: the tensor core truncates the fp32 operands to tf32 (<= 2^-10 relative per operand), so a Gram entry is
@@ -28,7 +28,8 @@ constexpr int G_BOX_BYTES = GT * GK * 4;         // 16 KB
 constexpr int G_A_BYTES = G_KB * G_BOX_BYTES;    // 128 KB resident A tile
 constexpr int G_STAGES = 4;                      // B ring
 constexpr int G_SMEM = 1024 + G_A_BYTES + G_STAGES * G_BOX_BYTES + 1024;
-constexpr int G_THREADS = 256;
+constexpr int G_EPI_WARPS = 16;                 // epilogue warp e: TMEM lane quarter e % 4, 32-column block e / 4
+constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;
 constexpr int DB_CHUNK = 48;                     // column blocks per unit
 constexpr uint32_t G_IDESC = umma_idesc_tf32(GT, GT);
 
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(acc_full + i), 1);
-      mbar_init(smem_u32(acc_empty + i), 128);
+      mbar_init(smem_u32(acc_empty + i), 32 * G_EPI_WARPS);
     }
     mbar_init(smem_u32(a_full), 1);
     mbar_init(smem_u32(a_free), 1);
@@ -191,8 +192,13 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) = rows of the tile =====
-    const int q = warp - 4;
+    // ===== epilogue: 16 warps; warp e owns TMEM lanes [32q, 32q+32) (q = e % 4: rows of the tile) and the 32-column
+    // block c0 = 32 * (e / 4).  One warp per scheduler is latency-bound (IPC ~0.1, ncu round-1 run 9): four per
+    // scheduler hide the ALU / shuffle latencies.  Only the block itself is written; db_mirror_kernel adds the
+    // transposed blocks afterwards. =====
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int c0 = (e >> 2) * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     int n_re = 0;
@@ -204,54 +210,48 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       const float si = i < n ? __ldg(sq + i) : 0.f;
       for (int bj = jb0; bj < jb1; ++bj) {
         const int j0 = bj * GT;
+        const float sj_lane = (j0 + c0 + lane < n) ? __ldg(sq + j0 + c0 + lane) : 0.f;
         mbar_wait(smem_u32(acc_full + acc), acc_phase);
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < GT; c0 += 32) {
-          float g[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GT + c0, g);
-          const float sj_lane = (j0 + c0 + lane < n) ? __ldg(sq + j0 + c0 + lane) : 0.f;
-          // pass 1 (unrolled, tiny body): fp32 decision + "inside the band" bit for each of the 32 columns
-          uint32_t word = 0, unsure = 0;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int j = j0 + c0 + c;
-            const float sj = __shfl_sync(0xffffffffu, sj_lane, c);
-            const bool valid = (i < n) && (j < n);
-            const float d2 = si + sj - 2.f * g[c];
-            const float tol = 2.2e-3f * (si + sj) + 1e-6f * eps2f;
-            word |= ((valid && (i == j || d2 < eps2f)) ? 1u : 0u) << c;
-            unsure |= ((valid && (i != j) && (fabsf(d2 - eps2f) <= tol)) ? 1u : 0u) << c;
-          }
-          // pass 2 (rolled): every in-band pair is re-evaluated exactly by the whole warp.  Keeping this out of the
-          // unrolled loop matters: the fully unrolled variant was 220 KB of SASS and instruction-fetch bound (ncu: no_inst)
-          uint32_t lanes = __ballot_sync(0xffffffffu, unsure != 0u);
-          while (lanes) {
-            const int src = __ffs(lanes) - 1;
-            lanes &= lanes - 1;
-            uint32_t bits = __shfl_sync(0xffffffffu, unsure, src);
-            const float* pi = points + (long long)(i0 + q * 32 + src) * G_DIM;
-            while (bits) {
-              const int c = __ffs(bits) - 1;
-              bits &= bits - 1;
-              const bool r = warp_exact_within(pi, points + (long long)(j0 + c0 + c) * G_DIM, eps2, lane);
-              if (lane == src) word = (word & ~(1u << c)) | ((r ? 1u : 0u) << c);
-              ++n_re;
-            }
-          }
-          if (row != bj) {  // transposed block: ballot c = the word of row (j0+c0+c) for this warp's 32 rows
-#pragma unroll 4
-            for (int c = 0; c < 32; ++c) {
-              const uint32_t tw = __ballot_sync(0xffffffffu, (word >> c) & 1u);
-              const int j = j0 + c0 + c;
-              if (lane == c && j < n) adj[(long long)j * wpr + (i0 >> 5) + q] = tw;
-            }
-          }
-          if (i < n) adj[(long long)i * wpr + ((j0 + c0) >> 5)] = word;
-        }
+        float g[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GT + c0, g);
         tcgen05_fence_before();
-        mbar_arrive(smem_u32(acc_empty + acc));
+        mbar_arrive(smem_u32(acc_empty + acc));   // the accumulator block is in registers
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // pass 1: d = d2 - eps^2 = (si + sj - eps^2) - 2 g ; within <=> d < 0 ; unsure <=> |d| <= tol
+        uint32_t word = 0, unsure = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float t = si + __shfl_sync(0xffffffffu, sj_lane, c);
+          const float d = fmaf(-2.f, g[c], t - eps2f);
+          const float tol = fmaf(2.2e-3f, t, 1e-6f * eps2f);
+          word |= (d < 0.f ? 1u : 0u) << c;
+          unsure |= (fabsf(d) <= tol ? 1u : 0u) << c;
+        }
+        // validity: columns beyond n, rows beyond n; the diagonal is always "within" and never rechecked
+        const int ncol = n - (j0 + c0);
+        const uint32_t colmask = ncol >= 32 ? 0xffffffffu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));
+        const uint32_t rowmask = (i < n) ? colmask : 0u;
+        const int dcol = i - (j0 + c0);                      // column of the diagonal element inside this block
+        const uint32_t diag = (dcol >= 0 && dcol < 32) ? (1u << dcol) : 0u;
+        word = (word | diag) & rowmask;
+        unsure = unsure & rowmask & ~diag;
+        // pass 2 (rolled): exact re-evaluation of the in-band pairs by the whole warp
+        uint32_t lanes = __ballot_sync(0xffffffffu, unsure != 0u);
+        while (lanes) {
+          const int src = __ffs(lanes) - 1;
+          lanes &= lanes - 1;
+          uint32_t bits = __shfl_sync(0xffffffffu, unsure, src);
+          const float* pi = points + (long long)(i0 + q * 32 + src) * G_DIM;
+          while (bits) {
+            const int c = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const bool r = warp_exact_within(pi, points + (long long)(j0 + c0 + c) * G_DIM, eps2, lane);
+            if (lane == src) word = (word & ~(1u << c)) | ((r ? 1u : 0u) << c);
+            ++n_re;
+          }
+        }
+        if (i < n) adj[(long long)i * wpr + ((j0 + c0) >> 5)] = word;
       }
     }
     if (lane == 0 && n_re) atomicAdd(info_w + 5, n_re);
@@ -261,6 +261,30 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * GT));
+  }
+}
+
+// adjacency is symmetric: the tile kernel wrote the 32x32 bit blocks (I, J) of tiles with tile(I) <= tile(J); this adds
+// the transposed blocks (J, I) for tile(I) < tile(J).  One warp per block: lane r loads row r's word, 32 ballots
+// transpose it, lane c stores row c of the mirrored block.  Memory-bound pass over n^2/16 bytes.
+__global__ void __launch_bounds__(256) db_mirror_kernel(const int* info, int n_fixed, long long wpr, uint32_t* __restrict__ adj) {
+  const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
+  const int nb = (n + 31) >> 5;                       // 32-row / 32-column blocks
+  const long long total = (long long)nb * nb;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long b = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); b < total; b += (long long)gridDim.x * wpb) {
+    const int I = (int)(b / nb), J = (int)(b - (long long)I * nb);
+    if ((I >> 2) >= (J >> 2)) continue;               // only blocks strictly above the tile diagonal
+    const int r = I * 32 + lane;
+    const uint32_t word = r < n ? adj[(long long)r * wpr + J] : 0u;
+    uint32_t mine = 0;
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const uint32_t tw = __ballot_sync(0xffffffffu, (word >> c) & 1u);
+      if (lane == c) mine = tw;
+    }
+    const int rr = J * 32 + lane;
+    if (rr < n) adj[(long long)rr * wpr + I] = mine;
   }
 }
 
@@ -279,6 +303,8 @@ int launch_db_adj_tc(const float* points, const float* sq, const int* info, int 
   }
   db_adj_tc_kernel<<<sm_count(), G_THREADS, G_SMEM, st>>>(map, points, sq, info, n_fixed, eps2f, eps2, wpr, adj, info_w);
   SCAN_LAUNCH_CHECK("db_adj_tc_kernel");
+  db_mirror_kernel<<<8 * sm_count(), 256, 0, st>>>(info, n_fixed, wpr, adj);
+  SCAN_LAUNCH_CHECK("db_mirror_kernel");
   return SCAN_OK;
 }
 
