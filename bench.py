@@ -276,7 +276,7 @@ def main():
         cc = kernel_ms.get("condconv_fwd", {"ms": 0.0, "calls": 0})
         bytes_per_launch = n * L_PER_IMAGE * (1024 + 9 * 4) + n * L_PER_IMAGE * 8 * 0.5
         ach = bytes_per_launch / (cc["ms"] / max(cc["calls"], 1) / 1e3) / 1e9 if cc["calls"] else None
-        roofline = {"kernel": "condconv_fwd_tc_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"kernel": "condconv_fwd_ts_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src}
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -117,9 +117,11 @@ int scan_scatter_add_rows(const float* d_nodes, const int32_t* node_rows, int32_
  *                in the reference's own layout.
  * labels [R] int64 or NULL; when given, loss_partials[i] (fp64, i < scan_condconv_num_partials()) receives
  * per-CTA partial sums of the UN-normalised focal loss (caller divides by R for softmaxFL and by 2R for
- * sigmoidFL and multiplies by ACT_LOSS_WEIGHT); flags[0] is set when a p_t < 1e-15 was clamped.
- * Arithmetic: tcgen05.mma kind::tf32 with fp32 accumulation in TMEM (impl 0) or fp32 FFMA (impl 1,
- * verification kernel); tolerance of impl 0 against the fp32 reference: rtol 1e-3. */
+ * sigmoidFL and multiplies by ACT_LOSS_WEIGHT); flags[i] (int32, same length as loss_partials) is non-zero
+ * when CTA i clamped a p_t < 1e-15.
+ * Arithmetic: impl 0 = tcgen05.mma kind::tf32, 3xTF32 error compensation, activation operands in tensor memory,
+ * fp32 accumulation in TMEM (the product); impl 1 = fp32 FFMA verification kernel; impl 2 = as 0 with the operands in
+ * shared memory.  Tolerance of impl 0 / 2 against the fp32 reference: rtol 1e-3 (measured 3e-5). */
 int32_t scan_condconv_num_partials(void);
 int scan_condconv_fwd(const scan_levels_t* lv, const float* rows, const float* weight, const float* bias,
                       int32_t num_classes, int32_t act_mode, void* const* act_nchw_host,

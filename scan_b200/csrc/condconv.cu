@@ -524,6 +524,7 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
   if (!rows || !weight || !act_nchw_host || num_classes < 1 || num_classes > SCAN_MAX_CLASSES) return SCAN_EINVAL;
   if (act_mode != 0 && act_mode != 1) return SCAN_EINVAL;
   if (labels && !loss_partials) return SCAN_EINVAL;
+  // impl 0: tcgen05, operands in tensor memory (product); 1: fp32 FFMA (verification); 2: tcgen05, operands in shared memory
   if (((uintptr_t)rows & 15) || ((uintptr_t)weight & 15)) return SCAN_EINVAL;
   ActPtrs act;
   for (int l = 0; l < SCAN_MAX_LEVELS; ++l) {
@@ -532,8 +533,10 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
   }
   cudaStream_t st = (cudaStream_t)stream;
   const long long R = lv.row_off[SCAN_MAX_LEVELS];
-  if (loss_partials) SCAN_CUDA_CHECK(cudaMemsetAsync(loss_partials, 0, sizeof(double) * CC_MAX_PARTIALS, st));
-  if (flags) SCAN_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int32_t), st));
+  if (impl != 0) {  // the product kernel (impl 0) clears its own partial / flag slots
+    if (loss_partials) SCAN_CUDA_CHECK(cudaMemsetAsync(loss_partials, 0, sizeof(double) * CC_MAX_PARTIALS, st));
+    if (flags) SCAN_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int32_t) * CC_MAX_PARTIALS, st));
+  }
   const int num_tiles = (int)ceil_div(R, CC_BM);
   const int grid = std::min(std::min(num_tiles, sm_count()), CC_MAX_PARTIALS);
   if (impl == 1) {
@@ -553,7 +556,7 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
     g_fwd_attr_set = 1;
   }
-  if (impl == 2) {  // A operands in tensor memory (condconv_ts.inl)
+  if (impl == 0) {  // product kernel: A operands in tensor memory (condconv_ts.inl)
     static int ts_attr = 0;
     if (!ts_attr) {
       SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));

@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   uint64_t* op_empty = bars + 2 * TS_STAGES + TS_OPS;     // [TS_OPS] MMA commit -> converter
   uint64_t* acc_full = bars + 2 * TS_STAGES + 2 * TS_OPS; // [CC_ACC]
   uint64_t* acc_empty = acc_full + CC_ACC;                // [CC_ACC]
-  uint64_t* w_bar = acc_empty + CC_ACC;
-  uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
+  uint64_t* w_bar = acc_empty + CC_ACC;                   // TMA -> splitter threads
+  uint64_t* w_ready = w_bar + 1;                          // splitter threads (warps >= 4) -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(w_ready + 1);
   __shared__ double red[4];
+  __shared__ int flag_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long R = lv.row_off[SCAN_MAX_LEVELS];
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       mbar_init(smem_u32(acc_empty + i), 128);
     }
     mbar_init(smem_u32(w_bar), 1);
+    mbar_init(smem_u32(w_ready), TS_THREADS - 128);
+    flag_s = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -88,16 +92,26 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     mbar_expect_tx(smem_u32(w_bar), CC_W_BYTES);
     for (int kb = 0; kb < CC_KB; ++kb) tma_load_2d(smem_u32(w_hi + kb * CC_WBLK_BYTES), &tmap_w, smem_u32(w_bar), kb * CC_BK, 0);
   }
-  mbar_wait(smem_u32(w_bar), 0);
-  for (int i = threadIdx.x; i < CC_W_BYTES / 4; i += TS_THREADS) {
-    const float wv = ((float*)w_hi)[i];
-    uint32_t hi;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(wv));
-    ((float*)w_hi)[i] = __uint_as_float(hi);
-    ((float*)w_lo)[i] = wv - __uint_as_float(hi);
+  // The activation stream starts immediately (warp 0 below); the kernel weights are split by the epilogue / converter
+  // warps while the first stages are in flight, and only the MMA warp waits for them (w_ready).
+  if (warp >= 4) {
+    mbar_wait(smem_u32(w_bar), 0);
+    for (int i = threadIdx.x - 128; i < CC_W_BYTES / 4; i += TS_THREADS - 128) {
+      const float wv = ((float*)w_hi)[i];
+      uint32_t hi;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(wv));
+      ((float*)w_hi)[i] = __uint_as_float(hi);
+      ((float*)w_lo)[i] = wv - __uint_as_float(hi);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(smem_u32(w_ready));
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
+  if (blockIdx.x == 0) {  // no host-side memsets: unused partial / flag slots are cleared here
+    for (int i = gridDim.x + threadIdx.x; i < CC_MAX_PARTIALS; i += TS_THREADS) {
+      if (loss_partials) loss_partials[i] = 0.0;
+      if (flags) flags[i] = 0;
+    }
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -116,6 +130,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     if (lane == 0) {
       int op = 0, acc = 0;
       uint32_t op_phase = 0, acc_phase = 0;
+      mbar_wait(smem_u32(w_ready), 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(acc_empty + acc), acc_phase ^ 1);
         tcgen05_fence_after();
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       tcgen05_fence_before();
       mbar_arrive(smem_u32(acc_empty + acc));
       const long long g = (long long)tile * CC_BM + q * 32 + lane;
-      if (g < R) loss += act_epilogue(lv, act, g, z, K, act_mode, bias, labels, flags);
+      if (g < R) loss += act_epilogue(lv, act, g, z, K, act_mode, bias, labels, &flag_s);
       if (++acc == CC_ACC) { acc = 0; acc_phase ^= 1; }
     }
     if (loss_partials) {
@@ -203,7 +218,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0 && loss_partials) loss_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+  if (threadIdx.x == 0) {
+    if (loss_partials) loss_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+    if (flags) flags[blockIdx.x] = flag_s;
+  }
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));

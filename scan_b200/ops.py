@@ -220,7 +220,7 @@ class _CondConv(torch.autograd.Function):
         acts = [torch.empty((geo.n_images, num_classes, h, w), device=dev, dtype=torch.float32) for h, w in geo.shapes]
         n_part = _lib.lib().scan_condconv_num_partials()
         partials = torch.empty((n_part,), device=dev, dtype=torch.float64) if labels is not None else None
-        flags = torch.empty((1,), device=dev, dtype=torch.int32)
+        flags = torch.empty((n_part,), device=dev, dtype=torch.int32)
         call("scan_condconv_fwd", geo.ref(), _ptr(rows), _ptr(weight), _ptr(bias), num_classes, act_mode,
              _ptr_array(acts), _ptr(labels), _ptr(partials), _ptr(flags), CONDCONV_IMPL["impl"], _stream())
         norm = float(geo.R) if act_mode == 0 else float(geo.R * num_classes)

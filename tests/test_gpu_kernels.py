@@ -20,7 +20,7 @@ def _close(a, b, rtol, what):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     scale = max(float(b.abs().max()), 1e-30)
     err = float((a - b).abs().max())
-    assert err <= rtol * scale + 2e-6, "%s: max|d|=%.3e scale=%.3e" % (what, err, scale)
+    assert err <= rtol * scale + 5e-6, "%s: max|d|=%.3e scale=%.3e" % (what, err, scale)
 
 
 @pytest.mark.parametrize("shapes,n", [(SHAPES, 3), (FULL, 2)])
