@@ -18,6 +18,8 @@
 //   * epilogue warps: one TMEM lane = one pixel, so softmax / sigmoid, the NCHW activation-map store and the
 //     focal-loss term are computed per thread in registers (tcgen05.ld 32x32b.x16).
 // Backward = one pass over rows producing d_rows (dense write) and per-CTA partial d_weight (fp32 FFMA).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace scan {
@@ -562,8 +564,14 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
       SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
       ts_attr = 1;
     }
+    // layout experiment (tools/bench_kernels.py): SCAN_B200_CC_KMAJOR=1 -> `rows` holds the k-block-major copy [8][R][32]
+    static const int kmajor = getenv("SCAN_B200_CC_KMAJOR") ? atoi(getenv("SCAN_B200_CC_KMAJOR")) : 0;
+    if (kmajor) {
+      rc = make_rowmajor_map(&mx, rows, (uint64_t)R * CC_KB, CC_BK, CC_BM);
+      if (rc) return rc;
+    }
     condconv_fwd_ts_kernel<<<grid, TS_THREADS, TS_SMEM, st>>>(mx, mw, lv, act, bias, labels, labels ? loss_partials : nullptr, flags,
-                                                             num_classes, act_mode, num_tiles);
+                                                             num_classes, act_mode, num_tiles, kmajor ? R : 0);
     SCAN_LAUNCH_CHECK("condconv_fwd_ts_kernel");
     return SCAN_OK;
   }

@@ -38,7 +38,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __global__ void __launch_bounds__(TS_THREADS, 1)
     condconv_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, Levels lv,
                            ActPtrs act, const float* __restrict__ bias, const int64_t* __restrict__ labels,
-                           double* __restrict__ loss_partials, int* __restrict__ flags, int K, int act_mode, int num_tiles) {
+                           double* __restrict__ loss_partials, int* __restrict__ flags, int K, int act_mode, int num_tiles,
+                           long long kmajor_rows) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* w_hi = smem;
@@ -121,7 +122,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         for (int kb = 0; kb < CC_KB; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           mbar_expect_tx(smem_u32(full_bar + stage), CC_STAGE_BYTES);
-          tma_load_2d(smem_u32(stages + stage * CC_STAGE_BYTES), &tmap_x, smem_u32(full_bar + stage), kb * CC_BK, tile * CC_BM);
+          if (kmajor_rows)  // experiment: k-block-major tiled activations [8][R][32]: every box is 16 KB contiguous
+            tma_load_2d(smem_u32(stages + stage * CC_STAGE_BYTES), &tmap_x, smem_u32(full_bar + stage), 0,
+                        (int)(kb * kmajor_rows + (long long)tile * CC_BM));
+          else
+            tma_load_2d(smem_u32(stages + stage * CC_STAGE_BYTES), &tmap_x, smem_u32(full_bar + stage), kb * CC_BK, tile * CC_BM);
           if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
         }
       }

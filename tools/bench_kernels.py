@@ -37,6 +37,12 @@ for impl in (0, 2, 1):
     except Exception as e:
         res["condconv_fwd_impl%d" % impl] = repr(e)[:200]
 ops.CONDCONV_IMPL["impl"] = 0
+if os.environ.get("SCAN_B200_CC_KMAJOR") == "1":
+    rk = rows.view(geo.R, 8, 32).permute(1, 0, 2).contiguous().view(geo.R, 256)
+    a_ref, _, _ = ops.condconv(geo, rk, w, None, 9, 0, labels, 1.0)
+    ms = timeit(lambda: ops.condconv(geo, rk, w, None, 9, 0, labels, 1.0))
+    res["condconv_fwd_kmajor"] = {"ms": ms, "GBps": fwd_bytes / ms / 1e6, "frac_of_6457": fwd_bytes / ms / 1e6 / 6457.1}
+    print(json.dumps(res, indent=1)); sys.exit(0)
 rr = rows.clone().requires_grad_(True); ww = w.clone().requires_grad_(True)
 acts, loss, _ = ops.condconv(geo, rr, ww, None, 9, 0, labels, 1.0)
 cots = [torch.randn_like(a) for a in acts]
