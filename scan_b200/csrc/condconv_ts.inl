@@ -11,7 +11,15 @@
 
 constexpr int TS_STAGES = 12;
 constexpr int TS_OPS = 4;
-constexpr int TS_OP_COL0 = CC_ACC * CC_N;  // 64
+// Accumulators: a chain of MMAs into ONE accumulator is serialised by the tensor-pipe latency (96 dependent N=16 MMAs per
+// tile capped both operand variants at ~3.5 TB/s, round-1 run 12).  Per k-step the kernel therefore issues only two MMAs,
+//   Da[128 x 32] += A_hi . [Whi ; Wlo]^T   (N = 32: hi*Whi and hi*Wlo at once)      Db[128 x 16] += A_lo . Whi^T
+// and alternates between two accumulator sets by k-block parity: 4 independent chains of 16 MMAs.  The epilogue adds
+// the six 16-column groups.  One accumulator slot = Da0 | Da1 | Db0 | Db1 = 96 columns.
+constexpr int TS_ACC = 2;
+constexpr int TS_ACC_COLS = 96;
+constexpr int TS_OP_COL0 = TS_ACC * TS_ACC_COLS;  // 192
+constexpr uint32_t TS_IDESC32 = umma_idesc_tf32(CC_BM, 32);
 constexpr int TS_SMEM = 1024 + 2 * CC_W_BYTES + TS_STAGES * CC_STAGE_BYTES + 1024;
 constexpr int TS_THREADS = 512;  // warps 0-3 TMA / MMA / alloc / idle, 4-7 epilogue, 8-11 and 12-15 converters (alternate k-blocks)
 
@@ -42,17 +50,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
                            long long kmajor_rows) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_hi = smem;
-  uint8_t* w_lo = smem + CC_W_BYTES;
+  uint8_t* w_cat = smem;                                   // per k-block 4 KB: [Whi (16 rows) | Wlo (16 rows)]: one N = 32 operand
   uint8_t* stages = smem + 2 * CC_W_BYTES;
   uint64_t* bars = (uint64_t*)(stages + TS_STAGES * CC_STAGE_BYTES);
   uint64_t* full_bar = bars;                              // [TS_STAGES] TMA -> converter
   uint64_t* empty_bar = bars + TS_STAGES;                 // [TS_STAGES] converter -> TMA (128 arrivals)
   uint64_t* op_full = bars + 2 * TS_STAGES;               // [TS_OPS] converter -> MMA (128 arrivals)
   uint64_t* op_empty = bars + 2 * TS_STAGES + TS_OPS;     // [TS_OPS] MMA commit -> converter
-  uint64_t* acc_full = bars + 2 * TS_STAGES + 2 * TS_OPS; // [CC_ACC]
-  uint64_t* acc_empty = acc_full + CC_ACC;                // [CC_ACC]
-  uint64_t* w_bar = acc_empty + CC_ACC;                   // TMA -> splitter threads
+  uint64_t* acc_full = bars + 2 * TS_STAGES + 2 * TS_OPS; // [TS_ACC]
+  uint64_t* acc_empty = acc_full + TS_ACC;                // [TS_ACC]
+  uint64_t* w_bar = acc_empty + TS_ACC;                   // TMA -> splitter threads
   uint64_t* w_ready = w_bar + 1;                          // splitter threads (warps >= 4) -> MMA
   uint32_t* tmem_slot = (uint32_t*)(w_ready + 1);
   __shared__ double red[4];
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       mbar_init(smem_u32(op_full + i), 128);
       mbar_init(smem_u32(op_empty + i), 1);
     }
-    for (int i = 0; i < CC_ACC; ++i) {
+    for (int i = 0; i < TS_ACC; ++i) {
       mbar_init(smem_u32(acc_full + i), 1);
       mbar_init(smem_u32(acc_empty + i), 128);
     }
@@ -91,18 +98,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 
   if (threadIdx.x == 0) {
     mbar_expect_tx(smem_u32(w_bar), CC_W_BYTES);
-    for (int kb = 0; kb < CC_KB; ++kb) tma_load_2d(smem_u32(w_hi + kb * CC_WBLK_BYTES), &tmap_w, smem_u32(w_bar), kb * CC_BK, 0);
+    for (int kb = 0; kb < CC_KB; ++kb) tma_load_2d(smem_u32(w_cat + kb * 2 * CC_WBLK_BYTES), &tmap_w, smem_u32(w_bar), kb * CC_BK, 0);
   }
   // The activation stream starts immediately (warp 0 below); the kernel weights are split by the epilogue / converter
   // warps while the first stages are in flight, and only the MMA warp waits for them (w_ready).
   if (warp >= 4) {
     mbar_wait(smem_u32(w_bar), 0);
     for (int i = threadIdx.x - 128; i < CC_W_BYTES / 4; i += TS_THREADS - 128) {
-      const float wv = ((float*)w_hi)[i];
+      float* blk = (float*)(w_cat + (i / (CC_WBLK_BYTES / 4)) * 2 * CC_WBLK_BYTES);
+      const int e = i % (CC_WBLK_BYTES / 4);
+      const float wv = blk[e];
       uint32_t hi;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(wv));
-      ((float*)w_hi)[i] = __uint_as_float(hi);
-      ((float*)w_lo)[i] = wv - __uint_as_float(hi);
+      blk[e] = __uint_as_float(hi);
+      blk[CC_WBLK_BYTES / 4 + e] = wv - __uint_as_float(hi);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(smem_u32(w_ready));
@@ -139,26 +148,26 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(acc_empty + acc), acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t d = tmem_base + acc * CC_N;
         for (int kb = 0; kb < CC_KB; ++kb) {
+          const uint32_t da = tmem_base + acc * TS_ACC_COLS + (kb & 1) * 32;       // Da[parity]
+          const uint32_t db = tmem_base + acc * TS_ACC_COLS + 64 + (kb & 1) * 16;  // Db[parity]
           mbar_wait(smem_u32(op_full + op), op_phase);
           tcgen05_fence_after();
           const uint32_t a_hi = tmem_base + TS_OP_COL0 + op * 64;
           const uint32_t a_lo = a_hi + 32;
-          const uint32_t bh_addr = smem_u32(w_hi + kb * CC_WBLK_BYTES);
-          const uint32_t bl_addr = smem_u32(w_lo + kb * CC_WBLK_BYTES);
+          const uint32_t b_addr = smem_u32(w_cat + kb * 2 * CC_WBLK_BYTES);
 #pragma unroll
           for (int k = 0; k < CC_BK / 8; ++k) {
-            const uint64_t dbh = umma_desc_sw128(bh_addr + k * 32);
-            umma_tf32_ts(d, a_hi + k * 8, dbh, CC_IDESC, (kb | k) != 0);
-            umma_tf32_ts(d, a_hi + k * 8, umma_desc_sw128(bl_addr + k * 32), CC_IDESC, 1);
-            umma_tf32_ts(d, a_lo + k * 8, dbh, CC_IDESC, 1);
+            const uint64_t dwb = umma_desc_sw128(b_addr + k * 32);
+            const uint32_t first = ((kb >> 1) | k) != 0;   // first MMA of this parity's chains overwrites
+            umma_tf32_ts(da, a_hi + k * 8, dwb, TS_IDESC32, first);
+            umma_tf32_ts(db, a_lo + k * 8, dwb, CC_IDESC, first);
           }
           umma_commit(smem_u32(op_empty + op));
           if (++op == TS_OPS) { op = 0; op_phase ^= 1; }
         }
         umma_commit(smem_u32(acc_full + acc));
-        if (++acc == CC_ACC) { acc = 0; acc_phase ^= 1; }
+        if (++acc == TS_ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 8) {
@@ -208,13 +217,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(smem_u32(acc_full + acc), acc_phase);
       tcgen05_fence_after();
-      float z[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * CC_N, z);
+      float z[16], part[16];
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TS_ACC_COLS;
+      tmem_ld16(tacc, z);                      // Da0: hi*Whi (even k-blocks)
+#pragma unroll
+      for (int grp = 1; grp < 6; ++grp) {      // Da0 hi*Wlo, Da1 hi*Whi, Da1 hi*Wlo, Db0 lo*Whi, Db1 lo*Whi
+        tmem_ld16(tacc + grp * 16, part);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) z[kk] += part[kk];
+      }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(acc_empty + acc));
       const long long g = (long long)tile * CC_BM + q * 32 + lane;
       if (g < R) loss += act_epilogue(lv, act, g, z, K, act_mode, bias, labels, &flag_s);
-      if (++acc == CC_ACC) { acc = 0; acc_phase ^= 1; }
+      if (++acc == TS_ACC) { acc = 0; acc_phase ^= 1; }
     }
     if (loss_partials) {
       loss = warp_sum_d(loss);
