@@ -14,7 +14,7 @@ constexpr int TS_OPS = 4;
 // Accumulators: a chain of MMAs into ONE accumulator is serialised by the tensor-pipe latency (96 dependent N=16 MMAs per
 // tile capped both operand variants at ~3.5 TB/s, round-1 run 12).  Per k-step the kernel therefore issues only two MMAs,
 //   Da[128 x 32] += A_hi . [Whi ; Wlo]^T   (N = 32: hi*Whi and hi*Wlo at once)      Db[128 x 16] += A_lo . Whi^T
-// and alternates between two accumulator sets by k-block parity: 4 independent chains of 16 MMAs.  The epilogue adds
+// and alternates between two accumulator sets by k-step parity: 4 independent, interleaved chains of 16 MMAs.  The epilogue adds
 // the six 16-column groups.  One accumulator slot = Da0 | Da1 | Db0 | Db1 = 96 columns.
 constexpr int TS_ACC = 2;
 constexpr int TS_ACC_COLS = 96;
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
         mbar_wait(smem_u32(acc_empty + acc), acc_phase ^ 1);
         tcgen05_fence_after();
         for (int kb = 0; kb < CC_KB; ++kb) {
-          const uint32_t da = tmem_base + acc * TS_ACC_COLS + (kb & 1) * 32;       // Da[parity]
-          const uint32_t db = tmem_base + acc * TS_ACC_COLS + 64 + (kb & 1) * 16;  // Db[parity]
+          const uint32_t da0 = tmem_base + acc * TS_ACC_COLS;       // Da[k & 1] at +32 * (k & 1)
+          const uint32_t db0 = tmem_base + acc * TS_ACC_COLS + 64;  // Db[k & 1] at +16 * (k & 1)
           mbar_wait(smem_u32(op_full + op), op_phase);
           tcgen05_fence_after();
           const uint32_t a_hi = tmem_base + TS_OP_COL0 + op * 64;
@@ -159,9 +159,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < CC_BK / 8; ++k) {
             const uint64_t dwb = umma_desc_sw128(b_addr + k * 32);
-            const uint32_t first = ((kb >> 1) | k) != 0;   // first MMA of this parity's chains overwrites
-            umma_tf32_ts(da, a_hi + k * 8, dwb, TS_IDESC32, first);
-            umma_tf32_ts(db, a_lo + k * 8, dwb, CC_IDESC, first);
+            // chain set = k & 1: consecutive MMAs go Da0, Db0, Da1, Db1, ... so four chains are in flight at any time
+            const uint32_t first = (kb | (k >> 1)) != 0;   // the first MMA of each chain overwrites
+            umma_tf32_ts(da0 + (k & 1) * 32, a_hi + k * 8, dwb, TS_IDESC32, first);
+            umma_tf32_ts(db0 + (k & 1) * 16, a_lo + k * 8, dwb, CC_IDESC, first);
           }
           umma_commit(smem_u32(op_empty + op));
           if (++op == TS_OPS) { op = 0; op_phase ^= 1; }
