@@ -145,9 +145,13 @@ int scan_condconv_bwd(const scan_levels_t* lv, const float* rows, const float* w
  * chunks of M sub-tokens of 64 dims: chunk b owns sub-token rows [b*M,(b+1)*M) of the
  * row-major [4M,64] reinterpretation.  ctx [M,256] (same reinterpretation), lse [4M] (log-sum-exp of the
  * scaled scores, saved for backward).  scale = 0.25.  dropout_p > 0 applies a counter-based Bernoulli
- * mask keyed by (seed, chunk, i, j) to the probabilities (train-mode nn.Dropout of transformer.py:31). */
+ * mask keyed by (seed, chunk, i, j) to the probabilities (train-mode nn.Dropout of transformer.py:31).
+ * Forward: with a workspace of scan_attn_workspace_bytes(m) the tcgen05 kernel runs (3xTF32, fp32 accumulate in TMEM);
+ * workspace == NULL selects the fp32 FFMA kernel (verification path). */
+int64_t scan_attn_workspace_bytes(int32_t m);
 int scan_attn_fwd(const float* q, const float* k, const float* v, int32_t m, float scale,
-                  float dropout_p, uint64_t seed, float* ctx, float* lse, void* stream);
+                  float dropout_p, uint64_t seed, float* ctx, float* lse, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 int scan_attn_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* lse,
                   const float* d_ctx, int32_t m, float scale, float dropout_p, uint64_t seed,
                   float* dq, float* dk, float* dv, float* delta_ws, void* stream);

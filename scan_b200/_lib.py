@@ -48,7 +48,8 @@ SIGNATURES = {
     "scan_condconv_fwd": (c_int32, [_LV, _P, _P, _P, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
     "scan_condconv_bwd_workspace_bytes": (c_int64, [c_int32]),
     "scan_condconv_bwd": (c_int32, [_LV, _P, _P, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
-    "scan_attn_fwd": (c_int32, [_P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P]),
+    "scan_attn_workspace_bytes": (c_int64, [c_int32]),
+    "scan_attn_fwd": (c_int32, [_P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P, c_int64, _P]),
     "scan_attn_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P, _P, _P]),
     "scan_class_sums": (c_int32, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "scan_proto_update": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P]),

@@ -19,6 +19,10 @@ int launch_attn_fwd_tc(const float* q, const float* k, const float* v, int m, fl
                        float* lse, cudaStream_t st);
 int launch_attn_bwd_tc(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
                        float scale, float drop_p, uint64_t seed, float* dq, float* dk, float* dv, cudaStream_t st);
+// tcgen05 version (attention_t5.cu): used by scan_attn_fwd when the caller provides a workspace
+int64_t attn_t5_workspace_bytes(int m);
+int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
+                       float* lse, void* workspace, cudaStream_t st);
 static int attn_simt() {
   static const int v = getenv("SCAN_B200_ATTN_TC") ? !atoi(getenv("SCAN_B200_ATTN_TC")) : 1;
   return v;
@@ -315,11 +319,17 @@ static int set_attn_attrs() {
 
 }  // namespace scan
 
+extern "C" int64_t scan_attn_workspace_bytes(int32_t m) { return m > 0 ? scan::attn_t5_workspace_bytes(m) : 0; }
+
 extern "C" int scan_attn_fwd(const float* q, const float* k, const float* v, int32_t m, float scale, float dropout_p, uint64_t seed,
-                             float* ctx, float* lse, void* stream) {
+                             float* ctx, float* lse, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace scan;
   if (m == 0) return SCAN_OK;
   if (!q || !k || !v || !ctx || !lse || m < 0 || dropout_p < 0.f || dropout_p >= 1.f) return SCAN_EINVAL;
+  if (workspace) {  // tcgen05 path
+    if (workspace_bytes < attn_t5_workspace_bytes(m)) return SCAN_ECAPACITY;
+    return launch_attn_fwd_t5(q, k, v, m, scale, dropout_p, seed, ctx, lse, workspace, (cudaStream_t)stream);
+  }
   if (!attn_simt()) return launch_attn_fwd_tc(q, k, v, m, scale, dropout_p, seed, ctx, lse, (cudaStream_t)stream);
   int rc = set_attn_attrs();
   if (rc) return rc;

@@ -1,0 +1,441 @@
+// K3a on tcgen05: streaming attention over the 4 chunks of M 64-d sub-tokens (layers/transformer.py:5-34 under the
+// .view of :66-68) with the 128 x 64 score tiles and the P.V products on the 5th-gen tensor cores.
+//
+// Numerics: 3xTF32 (x = hi + lo): the scores feed an exponential, plain tf32 would break the 1e-3 contract.  The two
+// "hi x (hi | lo)" products are fused into ONE wide MMA by stacking [hi ; lo] of the B operand along N, so a tile needs
+// two short, independent accumulation chains instead of three dependent ones (dependent tcgen05.mma chains are bound by
+// the tensor-pipe latency, see condconv_ts.inl).
+//
+// Forward = two passes over the key tiles (no online rescaling of a TMEM-resident O):
+//   pass 1  S = Q K^T -> per-row running max / sum -> lse           (S double-buffered in TMEM)
+//   pass 2  S again, P = exp(S*scale - lse) (already normalised), dropout, split into hi / lo, stored to TENSOR MEMORY
+//           as the A operand of O += P V (tcgen05.mma with A from TMEM); O accumulates across all key tiles.
+// Operands come from a small pre-pass (attn_prep_kernel): q_hl / k_hl [4M, 128] = (hi | lo) per sub-token and the
+// transposed V^T planes [chunk][hi d 0..63 | lo d 0..63][Mp] (keys contiguous), all loaded by TMA (128-byte swizzle).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 softmax (lane quarter = warp % 4, key half = (warp-4)/4).
+#include "tc_common.cuh"
+
+namespace scan {
+
+constexpr int T5_BQ = 128;   // query rows per CTA (TMEM lanes)
+constexpr int T5_BK = 64;    // keys per tile
+constexpr int T5_D = 64;
+constexpr int T5_QBOX = T5_BQ * 32 * 4;   // 16 KB: [128 rows x 32 cols]
+constexpr int T5_KBOX = T5_BK * 32 * 4;   // 8 KB:  [64 rows x 32 cols]
+constexpr int T5_Q_BYTES = 4 * T5_QBOX;   // hi kb0, hi kb1, lo kb0, lo kb1
+constexpr int T5_STAGE = 4 * T5_KBOX;     // [kb0: hi | lo][kb1: hi | lo] = 32 KB
+constexpr int T5_SMEM = 1024 + T5_Q_BYTES + 2 * T5_STAGE + 2 * T5_STAGE + 4096;   // + barriers and the 2 KB row statistics
+constexpr int T5_THREADS = 384;
+constexpr int T5_S_COLS = 192;            // Sa (hi.hi | hi.lo) 128 + Sb (lo.hi) 64
+constexpr int T5_P_COL0 = 192;            // P operand slot: hi 64 | lo 64
+constexpr int T5_O_COL0 = 320;            // Oa 128 + Ob 64
+constexpr uint32_t T5_IDESC_N128 = umma_idesc_tf32(T5_BQ, 128);
+constexpr uint32_t T5_IDESC_N64 = umma_idesc_tf32(T5_BQ, 64);
+
+__device__ __forceinline__ uint32_t t5_drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
+  uint64_t x = seed ^ ((uint64_t)chunk << 60) ^ ((uint64_t)i << 30) ^ (uint64_t)j;
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 32);
+}
+
+__device__ __forceinline__ void t5_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void t5_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void t5_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void t5_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t5_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------- pre-pass
+// q_hl, k_hl: [4M, 128] = hi(64) | lo(64);  vt: [4][128][Mp], rows 0..63 hi of dim d, rows 64..127 lo, zero for keys >= M
+__global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                        int m, int mp, float* __restrict__ q_hl, float* __restrict__ k_hl,
+                                                        float* __restrict__ vt) {
+  __shared__ float th[64][33], tl[64][33];
+  const long long n_rows = 4ll * m;
+  // part 1: row-wise hi/lo of q and k (grid-stride over float4)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 16; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i >> 4;
+    const int c4 = (int)(i & 15);
+    for (int which = 0; which < 2; ++which) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>((which ? k : q) + row * 64) + c4);
+      float4 h, l;
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u); l.x = x.x - h.x;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u); l.y = x.y - h.y;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u); l.z = x.z - h.z;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u); l.w = x.w - h.w;
+      float* dst = (which ? k_hl : q_hl) + row * 128;
+      reinterpret_cast<float4*>(dst)[c4] = h;
+      reinterpret_cast<float4*>(dst + 64)[c4] = l;
+    }
+  }
+  // part 2: V^T planes, 32-key x 64-dim tiles through shared memory
+  const int tiles_per_chunk = mp / 32;
+  for (int tile = blockIdx.x; tile < 4 * tiles_per_chunk; tile += gridDim.x) {
+    const int chunk = tile / tiles_per_chunk, j0 = (tile % tiles_per_chunk) * 32;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+      const int key = i >> 6, d = i & 63;
+      float x = 0.f;
+      if (j0 + key < m) x = __ldg(v + ((long long)chunk * m + j0 + key) * 64 + d);
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+      th[d][key] = __uint_as_float(u);
+      tl[d][key] = x - __uint_as_float(u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+      const int d = i >> 5, key = i & 31;
+      vt[((long long)chunk * 128 + d) * mp + j0 + key] = th[d][key];
+      vt[((long long)chunk * 128 + 64 + d) * mp + j0 + key] = tl[d][key];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(T5_THREADS, 1)
+    attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                       const __grid_constant__ CUtensorMap map_v, int m, float scale, float drop_p, uint64_t seed,
+                       float* __restrict__ ctx, float* __restrict__ lse) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + T5_Q_BYTES;
+  uint8_t* v_s = k_s + 2 * T5_STAGE;
+  uint64_t* bars = (uint64_t*)(v_s + 2 * T5_STAGE);
+  uint64_t* k_full = bars;          // [2]
+  uint64_t* k_empty = bars + 2;     // [2]
+  uint64_t* v_full = bars + 4;      // [2]
+  uint64_t* v_empty = bars + 6;     // [2]
+  uint64_t* s_full = bars + 8;      // [2]
+  uint64_t* s_empty = bars + 10;    // [2] (256 arrivals)
+  uint64_t* p_full = bars + 12;     // (256 arrivals)
+  uint64_t* p_empty = bars + 13;
+  uint64_t* o_full = bars + 14;
+  uint64_t* q_full = bars + 15;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+  float* stat_m = (float*)(bars + 18);      // [2][128] per-half running max
+  float* stat_l = stat_m + 256;             // [2][128] per-half running sum
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.y;
+  const long long base = (long long)chunk * m;   // first sub-token row of the chunk
+  const int i0 = blockIdx.x * T5_BQ;
+  const int n_tiles = (m + T5_BK - 1) / T5_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(k_full + i), 1);
+      mbar_init(smem_u32(k_empty + i), 1);
+      mbar_init(smem_u32(v_full + i), 1);
+      mbar_init(smem_u32(v_empty + i), 1);
+      mbar_init(smem_u32(s_full + i), 1);
+      mbar_init(smem_u32(s_empty + i), 256);
+    }
+    mbar_init(smem_u32(p_full), 256);
+    mbar_init(smem_u32(p_empty), 1);
+    mbar_init(smem_u32(o_full), 1);
+    mbar_init(smem_u32(q_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(q_full), T5_Q_BYTES);
+      for (int part = 0; part < 2; ++part)      // hi, lo
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(smem_u32(q_s + (part * 2 + kb) * T5_QBOX), &map_q, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int t = 0; t < n_tiles; ++t) {
+          const int j0 = t * T5_BK;
+          mbar_wait(smem_u32(k_empty + ks), kph ^ 1);
+          mbar_expect_tx(smem_u32(k_full + ks), T5_STAGE);
+          for (int kb = 0; kb < 2; ++kb)
+            for (int part = 0; part < 2; ++part)
+              tma_load_2d(smem_u32(k_s + ks * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_k, smem_u32(k_full + ks), part * 64 + kb * 32,
+                          (int)(base + j0));
+          if (++ks == 2) { ks = 0; kph ^= 1; }
+          if (pass == 1) {
+            mbar_wait(smem_u32(v_empty + vs), vph ^ 1);
+            mbar_expect_tx(smem_u32(v_full + vs), T5_STAGE);
+            for (int kb = 0; kb < 2; ++kb)
+              for (int part = 0; part < 2; ++part)
+                tma_load_2d(smem_u32(v_s + vs * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_v, smem_u32(v_full + vs), j0 + kb * 32,
+                            chunk * 128 + part * 64);
+            if (++vs == 2) { vs = 0; vph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(smem_u32(q_full), 0);
+      tcgen05_fence_after();
+      const uint32_t q_addr = smem_u32(q_s);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      // S tile: Sa[128 x 128] = Qhi . [Khi ; Klo]^T, Sb[128 x 64] = Qlo . Khi^T
+      auto issue_s = [&](uint32_t s_col) {
+        mbar_wait(smem_u32(k_full + ks), kph);
+        tcgen05_fence_after();
+        const uint32_t kaddr = smem_u32(k_s + ks * T5_STAGE);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t b = umma_desc_sw128(kaddr + kb * 2 * T5_KBOX + k * 32);
+            t5_mma_ss(tmem_base + s_col, umma_desc_sw128(q_addr + kb * T5_QBOX + k * 32), b, T5_IDESC_N128, (kb | k) != 0);
+            t5_mma_ss(tmem_base + s_col + 128, umma_desc_sw128(q_addr + (2 + kb) * T5_QBOX + k * 32), b, T5_IDESC_N64, (kb | k) != 0);
+          }
+        umma_commit(smem_u32(k_empty + ks));
+        if (++ks == 2) { ks = 0; kph ^= 1; }
+      };
+      // ---- pass 1: S double-buffered at columns 0 / 192
+      {
+        uint32_t se_ph[2] = {0, 0};
+        for (int t = 0; t < n_tiles; ++t) {
+          const int buf = t & 1;
+          mbar_wait(smem_u32(s_empty + buf), se_ph[buf] ^ 1);
+          se_ph[buf] ^= 1;
+          tcgen05_fence_after();
+          issue_s(buf * T5_S_COLS);
+          umma_commit(smem_u32(s_full + buf));
+        }
+      }
+      // ---- pass 2: single S buffer (columns 0..191), P slot, O accumulators
+      {
+        // s_empty[0] phase bookkeeping continues from pass 1: count the completed phases so far
+        uint32_t se0 = (uint32_t)(((n_tiles + 1) / 2) & 1);   // parity of completions of s_empty[0] consumed in pass 1
+        uint32_t pf = 0;
+        // wait until the softmax warps have drained the last pass-1 tiles from BOTH buffers (buffer 1 overlaps P / O)
+        // -> handled by the s_empty waits below plus an explicit wait on buffer 1
+        uint32_t se1 = (uint32_t)((n_tiles / 2) & 1);
+        if (n_tiles >= 2) mbar_wait(smem_u32(s_empty + 1), se1 ^ 1);
+        tcgen05_fence_after();
+        for (int t = 0; t <= n_tiles; ++t) {
+          if (t < n_tiles) {
+            mbar_wait(smem_u32(s_empty + 0), se0 ^ 1);
+            se0 ^= 1;
+            tcgen05_fence_after();
+            issue_s(0);
+            umma_commit(smem_u32(s_full + 0));
+          }
+          if (t > 0) {  // O += P(t-1) . V(t-1)
+            mbar_wait(smem_u32(p_full), pf);
+            pf ^= 1;
+            mbar_wait(smem_u32(v_full + vs), vph);
+            tcgen05_fence_after();
+            const uint32_t vaddr = smem_u32(v_s + vs * T5_STAGE);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t b = umma_desc_sw128(vaddr + kb * 2 * T5_KBOX + k * 32);
+                const uint32_t acc = (t > 1 || kb || k) ? 1u : 0u;
+                t5_mma_ts(tmem_base + T5_O_COL0, tmem_base + T5_P_COL0 + kb * 32 + k * 8, b, T5_IDESC_N128, acc);
+                t5_mma_ts(tmem_base + T5_O_COL0 + 128, tmem_base + T5_P_COL0 + 64 + kb * 32 + k * 8, b, T5_IDESC_N64, acc);
+              }
+            umma_commit(smem_u32(v_empty + vs));
+            umma_commit(smem_u32(p_empty));
+            if (++vs == 2) { vs = 0; vph ^= 1; }
+          }
+        }
+        umma_commit(smem_u32(o_full));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== softmax / epilogue warps: thread = query row (TMEM lane), half h of the 64 key columns =====
+    const int w = warp - 4;
+    const int qd = w & 3, h = w >> 2;
+    const int row = qd * 32 + lane;                 // row inside the tile
+    const int grow = i0 + row;                      // row inside the chunk
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    float mrun = -INFINITY, lrun = 0.f;
+    uint32_t sf_ph[2] = {0, 0};
+    float a[32], b[32], c[32];
+    // ---- pass 1: statistics
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(smem_u32(s_full + buf), sf_ph[buf]);
+      sf_ph[buf] ^= 1;
+      tcgen05_fence_after();
+      const uint32_t sc = tmem_base + lane_base + buf * T5_S_COLS;
+      t5_ld32(sc + h * 32, a);
+      t5_ld32(sc + 64 + h * 32, b);
+      t5_ld32(sc + 128 + h * 32, c);
+      t5_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(s_empty + buf));
+      const int j0 = t * T5_BK + h * 32;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        a[e] = (j0 + e < m) ? (a[e] + b[e] + c[e]) * scale : -INFINITY;
+        mx = fmaxf(mx, a[e]);
+      }
+      const float mnew = fmaxf(mrun, mx);
+      if (mnew != -INFINITY) {
+        float sum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sum += (a[e] == -INFINITY) ? 0.f : __expf(a[e] - mnew);
+        lrun = lrun * ((mrun == -INFINITY) ? 0.f : __expf(mrun - mnew)) + sum;
+        mrun = mnew;
+      }
+    }
+    // combine the two column halves -> lse per row
+    stat_m[h * 128 + row] = mrun;
+    stat_l[h * 128 + row] = lrun;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float lse_row;
+    {
+      const float m0 = stat_m[row], m1 = stat_m[128 + row];
+      const float mm = fmaxf(m0, m1);
+      const float l0 = (m0 == -INFINITY) ? 0.f : stat_l[row] * expf(m0 - mm);
+      const float l1 = (m1 == -INFINITY) ? 0.f : stat_l[128 + row] * expf(m1 - mm);
+      lse_row = mm + logf(l0 + l1);
+    }
+    if (h == 0 && grow < m) lse[base + grow] = lse_row;
+    // ---- pass 2: P = exp(S*scale - lse), dropout, hi/lo -> TMEM operand slot
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    uint32_t sf0 = sf_ph[0], pe = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(smem_u32(s_full + 0), sf0);
+      sf0 ^= 1;
+      tcgen05_fence_after();
+      const uint32_t sc = tmem_base + lane_base;
+      t5_ld32(sc + h * 32, a);
+      t5_ld32(sc + 64 + h * 32, b);
+      t5_ld32(sc + 128 + h * 32, c);
+      t5_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(s_empty + 0));
+      const int j0 = t * T5_BK + h * 32;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float p = 0.f;
+        if (j0 + e < m) {
+          p = expf((a[e] + b[e] + c[e]) * scale - lse_row);
+          if (drop_p > 0.f) p = (t5_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? p * inv_keep : 0.f;
+        }
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(p));
+        hi[e] = u;
+        lo[e] = __float_as_uint(p - __uint_as_float(u));
+      }
+      if (t > 0) {   // the previous P must have been consumed by its P.V MMAs
+        mbar_wait(smem_u32(p_empty), pe);
+        pe ^= 1;
+      }
+      tcgen05_fence_after();
+      t5_st32(tmem_base + lane_base + T5_P_COL0 + h * 32, hi);
+      t5_st32(tmem_base + lane_base + T5_P_COL0 + 64 + h * 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(p_full));
+    }
+    // ---- epilogue: O = Oa[0..63] + Oa[64..127] + Ob
+    mbar_wait(smem_u32(o_full), 0);
+    tcgen05_fence_after();
+    const uint32_t oc = tmem_base + lane_base + T5_O_COL0;
+    t5_ld32(oc + h * 32, a);
+    t5_ld32(oc + 64 + h * 32, b);
+    t5_ld32(oc + 128 + h * 32, c);
+    t5_ld_wait();
+    if (grow < m) {
+      float4* dst = reinterpret_cast<float4*>(ctx + (base + grow) * T5_D + h * 32);
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4)
+        dst[e4] = make_float4(a[4 * e4] + b[4 * e4] + c[4 * e4], a[4 * e4 + 1] + b[4 * e4 + 1] + c[4 * e4 + 1],
+                              a[4 * e4 + 2] + b[4 * e4 + 2] + c[4 * e4 + 2], a[4 * e4 + 3] + b[4 * e4 + 3] + c[4 * e4 + 3]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+static int g_t5_attr = 0;
+
+int64_t attn_t5_workspace_bytes(int m) {
+  const long long mp = ((long long)m + 63) / 64 * 64;
+  return (4ll * m * 128 * 2 + 4ll * 128 * mp) * 4 + 1024;
+}
+
+int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
+                       float* lse, void* workspace, cudaStream_t st) {
+  const int mp = (m + 63) / 64 * 64;
+  float* q_hl = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* k_hl = q_hl + 4ll * m * 128;
+  float* vt = k_hl + 4ll * m * 128;
+  attn_prep_kernel<<<2 * sm_count(), 256, 0, st>>>(q, k, v, m, mp, q_hl, k_hl, vt);
+  SCAN_LAUNCH_CHECK("attn_prep_kernel");
+  CUtensorMap mq, mk, mv;
+  int rc = make_rowmajor_map(&mq, q_hl, 4ull * m, 128, T5_BQ);
+  if (rc) return rc;
+  rc = make_rowmajor_map(&mk, k_hl, 4ull * m, 128, T5_BK);
+  if (rc) return rc;
+  rc = make_rowmajor_map(&mv, vt, 4ull * 128, (uint64_t)mp, 64);
+  if (rc) return rc;
+  if (!g_t5_attr) {
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+    g_t5_attr = 1;
+  }
+  dim3 grid((m + T5_BQ - 1) / T5_BQ, 4);
+  attn_fwd_t5_kernel<<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse);
+  SCAN_LAUNCH_CHECK("attn_fwd_t5_kernel");
+  return SCAN_OK;
+}
+
+}  // namespace scan

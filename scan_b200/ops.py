@@ -270,6 +270,10 @@ def condconv(geo, rows, weight, bias, num_classes, act_mode, labels=None, loss_w
 # ----------------------------------------------------------------------------------------------------
 # K3a: attention
 # ----------------------------------------------------------------------------------------------------
+# forward implementation: "t5" = tcgen05 kernel (product), "ffma" = fp32 verification kernel (SCAN_B200_ATTN_FWD=ffma)
+ATTN_IMPL = {"fwd": __import__("os").environ.get("SCAN_B200_ATTN_FWD", "t5")}
+
+
 class _Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, scale, drop_p, seed):
@@ -277,7 +281,11 @@ class _Attention(torch.autograd.Function):
         m = q.shape[0]
         out = torch.empty_like(q)
         lse = torch.empty((4 * m,), device=q.device, dtype=torch.float32)
-        call("scan_attn_fwd", _ptr(q), _ptr(k), _ptr(v), m, scale, drop_p, seed, _ptr(out), _ptr(lse), _stream())
+        ws = None
+        if ATTN_IMPL["fwd"] == "t5":
+            ws = torch.empty((_lib.lib().scan_attn_workspace_bytes(m),), device=q.device, dtype=torch.uint8)
+        call("scan_attn_fwd", _ptr(q), _ptr(k), _ptr(v), m, scale, drop_p, seed, _ptr(out), _ptr(lse), _ptr(ws),
+             0 if ws is None else ws.numel(), _stream())
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.cfg = (scale, drop_p, seed)
         return out
