@@ -33,14 +33,6 @@ constexpr int AT_T = 64;   // tile edge
 constexpr int AT_LD = 68;  // padded leading dimension (floats): 272-byte rows, 16-byte aligned
 constexpr int AT_TILE = AT_T * AT_LD;
 
-__device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
-  uint64_t x = seed ^ ((uint64_t)chunk << 60) ^ ((uint64_t)i << 30) ^ (uint64_t)j;
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return (uint32_t)(x >> 32);
-}
 
 // tile loader: rows [r0, r0+64) of a [n_rows, 64] matrix -> smem [64][AT_LD], zero beyond n_rows
 __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ g, long long r0, long long n_rows) {
@@ -181,7 +173,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
         float p = (s[a][c] == -INFINITY) ? 0.f : expf(s[a][c] - mnew);
         sum += p;
         if (drop_p > 0.f) {
-          const uint32_t h = drop_hash(seed, chunk, i0 + ty * 4 + a, j0 + tx + 16 * c);
+          const uint32_t h = attn_drop_hash(seed, chunk, i0 + ty * 4 + a, j0 + tx + 16 * c);
           p = (h >= drop_thr) ? p * inv_keep : 0.f;
         }
         Ps[(ty * 4 + a) * AT_LD + tx + 16 * c] = p;
@@ -271,7 +263,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
         float p = 0.f, keep = 1.f;
         if (row < m && col < m) {
           p = expf(s[a][c] * scale - l);
-          if (drop_p > 0.f) keep = (drop_hash(seed, chunk, row, col) >= drop_thr) ? inv_keep : 0.f;
+          if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, row, col) >= drop_thr) ? inv_keep : 0.f;
         }
         const float pt = p * keep;
         Ps[(ty * 4 + a) * AT_LD + tx + 16 * c] = pt;

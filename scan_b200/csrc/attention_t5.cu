@@ -12,7 +12,8 @@
 //           as the A operand of O += P V (tcgen05.mma with A from TMEM); O accumulates across all key tiles.
 // Operands come from a small pre-pass (attn_prep_kernel): q_hl / k_hl [4M, 128] = (hi | lo) per sub-token and the
 // transposed V^T planes [chunk][hi d 0..63 | lo d 0..63][Mp] (keys contiguous), all loaded by TMA (128-byte swizzle).
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 softmax (lane quarter = warp % 4, key half = (warp-4)/4).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..19 softmax (lane quarter = w % 4, 16-key block = w / 4):
+// four softmax warps per scheduler hide the TMEM / MUFU / ALU latencies (one or two per scheduler run at IPC ~0.1).
 #include "tc_common.cuh"
 
 namespace scan {
@@ -24,22 +25,15 @@ constexpr int T5_QBOX = T5_BQ * 32 * 4;   // 16 KB: [128 rows x 32 cols]
 constexpr int T5_KBOX = T5_BK * 32 * 4;   // 8 KB:  [64 rows x 32 cols]
 constexpr int T5_Q_BYTES = 4 * T5_QBOX;   // hi kb0, hi kb1, lo kb0, lo kb1
 constexpr int T5_STAGE = 4 * T5_KBOX;     // [kb0: hi | lo][kb1: hi | lo] = 32 KB
-constexpr int T5_SMEM = 1024 + T5_Q_BYTES + 2 * T5_STAGE + 2 * T5_STAGE + 4096;   // + barriers and the 2 KB row statistics
-constexpr int T5_THREADS = 384;
+constexpr int T5_SMEM = 1024 + T5_Q_BYTES + 2 * T5_STAGE + 2 * T5_STAGE + 6144;   // + barriers and the 4 KB row statistics
+constexpr int T5_SM_WARPS = 16;           // softmax warps: lane quarter = w % 4, 16-column block = w / 4
+constexpr int T5_THREADS = 128 + 32 * T5_SM_WARPS;
 constexpr int T5_S_COLS = 192;            // Sa (hi.hi | hi.lo) 128 + Sb (lo.hi) 64
 constexpr int T5_P_COL0 = 192;            // P operand slot: hi 64 | lo 64
 constexpr int T5_O_COL0 = 320;            // Oa 128 + Ob 64
 constexpr uint32_t T5_IDESC_N128 = umma_idesc_tf32(T5_BQ, 128);
 constexpr uint32_t T5_IDESC_N64 = umma_idesc_tf32(T5_BQ, 64);
 
-__device__ __forceinline__ uint32_t t5_drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
-  uint64_t x = seed ^ ((uint64_t)chunk << 60) ^ ((uint64_t)i << 30) ^ (uint64_t)j;
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return (uint32_t)(x >> 32);
-}
 
 __device__ __forceinline__ void t5_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -66,6 +60,24 @@ __device__ __forceinline__ void t5_ld32(uint32_t taddr, float (&v)[32]) {
       : "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void t5_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void t5_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 __device__ __forceinline__ void t5_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void t5_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -148,8 +160,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
   uint64_t* o_full = bars + 14;
   uint64_t* q_full = bars + 15;
   uint32_t* tmem_slot = (uint32_t*)(bars + 16);
-  float* stat_m = (float*)(bars + 18);      // [2][128] per-half running max
-  float* stat_l = stat_m + 256;             // [2][128] per-half running sum
+  float* stat_m = (float*)(bars + 18);      // [4][128] per-column-block running max
+  float* stat_l = stat_m + 512;             // [4][128] per-column-block running sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
@@ -164,9 +176,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       mbar_init(smem_u32(v_full + i), 1);
       mbar_init(smem_u32(v_empty + i), 1);
       mbar_init(smem_u32(s_full + i), 1);
-      mbar_init(smem_u32(s_empty + i), 256);
+      mbar_init(smem_u32(s_empty + i), 32 * T5_SM_WARPS);
     }
-    mbar_init(smem_u32(p_full), 256);
+    mbar_init(smem_u32(p_full), 32 * T5_SM_WARPS);
     mbar_init(smem_u32(p_empty), 1);
     mbar_init(smem_u32(o_full), 1);
     mbar_init(smem_u32(q_full), 1);
@@ -291,15 +303,15 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===== softmax / epilogue warps: thread = query row (TMEM lane), half h of the 64 key columns =====
+    // ===== softmax / epilogue warps: thread = query row (TMEM lane), 16-column block cq of the 64 key columns =====
     const int w = warp - 4;
-    const int qd = w & 3, h = w >> 2;
+    const int qd = w & 3, cq = w >> 2;
     const int row = qd * 32 + lane;                 // row inside the tile
     const int grow = i0 + row;                      // row inside the chunk
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     float mrun = -INFINITY, lrun = 0.f;
     uint32_t sf_ph[2] = {0, 0};
-    float a[32], b[32], c[32];
+    float a[16], b[16], c[16];
     // ---- pass 1: statistics
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
@@ -307,16 +319,16 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       sf_ph[buf] ^= 1;
       tcgen05_fence_after();
       const uint32_t sc = tmem_base + lane_base + buf * T5_S_COLS;
-      t5_ld32(sc + h * 32, a);
-      t5_ld32(sc + 64 + h * 32, b);
-      t5_ld32(sc + 128 + h * 32, c);
+      t5_ld16(sc + cq * 16, a);
+      t5_ld16(sc + 64 + cq * 16, b);
+      t5_ld16(sc + 128 + cq * 16, c);
       t5_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(s_empty + buf));
-      const int j0 = t * T5_BK + h * 32;
+      const int j0 = t * T5_BK + cq * 16;
       float mx = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
+      for (int e = 0; e < 16; ++e) {
         a[e] = (j0 + e < m) ? (a[e] + b[e] + c[e]) * scale : -INFINITY;
         mx = fmaxf(mx, a[e]);
       }
@@ -324,24 +336,29 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       if (mnew != -INFINITY) {
         float sum = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sum += (a[e] == -INFINITY) ? 0.f : __expf(a[e] - mnew);
+        for (int e = 0; e < 16; ++e) sum += (a[e] == -INFINITY) ? 0.f : __expf(a[e] - mnew);
         lrun = lrun * ((mrun == -INFINITY) ? 0.f : __expf(mrun - mnew)) + sum;
         mrun = mnew;
       }
     }
-    // combine the two column halves -> lse per row
-    stat_m[h * 128 + row] = mrun;
-    stat_l[h * 128 + row] = lrun;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // combine the four column blocks -> lse per row
+    stat_m[cq * 128 + row] = mrun;
+    stat_l[cq * 128 + row] = lrun;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * T5_SM_WARPS) : "memory");
     float lse_row;
     {
-      const float m0 = stat_m[row], m1 = stat_m[128 + row];
-      const float mm = fmaxf(m0, m1);
-      const float l0 = (m0 == -INFINITY) ? 0.f : stat_l[row] * expf(m0 - mm);
-      const float l1 = (m1 == -INFINITY) ? 0.f : stat_l[128 + row] * expf(m1 - mm);
-      lse_row = mm + logf(l0 + l1);
+      float mm = -INFINITY;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) mm = fmaxf(mm, stat_m[x * 128 + row]);
+      float ll = 0.f;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const float mx_ = stat_m[x * 128 + row];
+        if (mx_ != -INFINITY) ll += stat_l[x * 128 + row] * expf(mx_ - mm);
+      }
+      lse_row = mm + logf(ll);
     }
-    if (h == 0 && grow < m) lse[base + grow] = lse_row;
+    if (cq == 0 && grow < m) lse[base + grow] = lse_row;
     // ---- pass 2: P = exp(S*scale - lse), dropout, hi/lo -> TMEM operand slot
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
@@ -351,20 +368,20 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       sf0 ^= 1;
       tcgen05_fence_after();
       const uint32_t sc = tmem_base + lane_base;
-      t5_ld32(sc + h * 32, a);
-      t5_ld32(sc + 64 + h * 32, b);
-      t5_ld32(sc + 128 + h * 32, c);
+      t5_ld16(sc + cq * 16, a);
+      t5_ld16(sc + 64 + cq * 16, b);
+      t5_ld16(sc + 128 + cq * 16, c);
       t5_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(s_empty + 0));
-      const int j0 = t * T5_BK + h * 32;
-      uint32_t hi[32], lo[32];
+      const int j0 = t * T5_BK + cq * 16;
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
+      for (int e = 0; e < 16; ++e) {
         float p = 0.f;
         if (j0 + e < m) {
           p = expf((a[e] + b[e] + c[e]) * scale - lse_row);
-          if (drop_p > 0.f) p = (t5_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? p * inv_keep : 0.f;
+          if (drop_p > 0.f) p = (attn_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? p * inv_keep : 0.f;
         }
         uint32_t u;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(p));
@@ -376,24 +393,24 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
         pe ^= 1;
       }
       tcgen05_fence_after();
-      t5_st32(tmem_base + lane_base + T5_P_COL0 + h * 32, hi);
-      t5_st32(tmem_base + lane_base + T5_P_COL0 + 64 + h * 32, lo);
+      t5_st16(tmem_base + lane_base + T5_P_COL0 + cq * 16, hi);
+      t5_st16(tmem_base + lane_base + T5_P_COL0 + 64 + cq * 16, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       mbar_arrive(smem_u32(p_full));
     }
-    // ---- epilogue: O = Oa[0..63] + Oa[64..127] + Ob
+    // ---- epilogue: O = Oa[0..63] + Oa[64..127] + Ob, 16 of the 64 d columns per warp
     mbar_wait(smem_u32(o_full), 0);
     tcgen05_fence_after();
     const uint32_t oc = tmem_base + lane_base + T5_O_COL0;
-    t5_ld32(oc + h * 32, a);
-    t5_ld32(oc + 64 + h * 32, b);
-    t5_ld32(oc + 128 + h * 32, c);
+    t5_ld16(oc + cq * 16, a);
+    t5_ld16(oc + 64 + cq * 16, b);
+    t5_ld16(oc + 128 + cq * 16, c);
     t5_ld_wait();
     if (grow < m) {
-      float4* dst = reinterpret_cast<float4*>(ctx + (base + grow) * T5_D + h * 32);
+      float4* dst = reinterpret_cast<float4*>(ctx + (base + grow) * T5_D + cq * 16);
 #pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4)
+      for (int e4 = 0; e4 < 4; ++e4)
         dst[e4] = make_float4(a[4 * e4] + b[4 * e4] + c[4 * e4], a[4 * e4 + 1] + b[4 * e4 + 1] + c[4 * e4 + 1],
                               a[4 * e4 + 2] + b[4 * e4 + 2] + c[4 * e4 + 2], a[4 * e4 + 3] + b[4 * e4 + 3] + c[4 * e4 + 3]);
     }

@@ -22,14 +22,6 @@ constexpr int TA_T = 64;
 constexpr int LDT = 72;                 // leading dimension of every tile (floats)
 constexpr int TILE_F = TA_T * LDT;      // floats per tile plane
 
-__device__ __forceinline__ uint32_t ta_drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
-  uint64_t x = seed ^ ((uint64_t)chunk << 60) ^ ((uint64_t)i << 30) ^ (uint64_t)j;
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return (uint32_t)(x >> 32);
-}
 
 __device__ __forceinline__ int perm8(int k) { return (k & ~7) | (((k & 3) << 1) | ((k >> 2) & 1)); }
 
@@ -218,7 +210,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const float* __restric
         float pv = (s[nt][i] == -INFINITY) ? 0.f : expf(s[nt][i] - mnew[r]);
         sum[r] += pv;
         if (drop_p > 0.f) {
-          const uint32_t h = ta_drop_hash(seed, chunk, r ? row_b : row_a, j0 + nt * 8 + 2 * t + (i & 1));
+          const uint32_t h = attn_drop_hash(seed, chunk, r ? row_b : row_a, j0 + nt * 8 + 2 * t + (i & 1));
           pv = (h >= drop_thr) ? pv * inv_keep : 0.f;
         }
         // P[row][key] is the A operand of P.V: key index permuted
@@ -330,7 +322,7 @@ __global__ void __launch_bounds__(256) attn_bwd_tc_kernel(const float* __restric
           float p = 0.f, keep = 1.f;
           if (row < m && col < m) {
             p = expf(s[nt][i] * scale - l[r]);
-            if (drop_p > 0.f) keep = (ta_drop_hash(seed, chunk, row, col) >= drop_thr) ? inv_keep : 0.f;
+            if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, row, col) >= drop_thr) ? inv_keep : 0.f;
           }
           PT[lk * LDT + perm8(lq)] = p * keep;                        // P~^T  [key][query]
           ST[lk * LDT + perm8(lq)] = p * (dp[nt][i] * keep - dl[r]);  // dS^T  [key][query]

@@ -89,4 +89,18 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
+// Counter-based Bernoulli source of the attention dropout mask: 32-bit hash of (seed, chunk, query, key).  All attention
+// kernels (forward and backward, every implementation) must use THIS function so that masks agree.  ~9 integer ops; the
+// row part is loop-invariant in every caller.
+__device__ __forceinline__ uint32_t attn_drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
+  uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (chunk * 0x85EBCA6Bu) ^ (i * 0xC2B2AE35u);
+  h ^= j * 0x27D4EB2Fu;
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
+
 }  // namespace scan
