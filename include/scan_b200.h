@@ -152,9 +152,13 @@ int64_t scan_attn_workspace_bytes(int32_t m);
 int scan_attn_fwd(const float* q, const float* k, const float* v, int32_t m, float scale,
                   float dropout_p, uint64_t seed, float* ctx, float* lse, void* workspace,
                   int64_t workspace_bytes, void* stream);
+/* Backward: delta_ws [4M] floats of scratch.  With a workspace of scan_attn_bwd_workspace_bytes(m) the two tcgen05
+ * kernels run (dQ per 128-query CTA, dK/dV per 128-key CTA, no atomics); workspace == NULL selects the FFMA kernel. */
+int64_t scan_attn_bwd_workspace_bytes(int32_t m);
 int scan_attn_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* lse,
                   const float* d_ctx, int32_t m, float scale, float dropout_p, uint64_t seed,
-                  float* dq, float* dk, float* dv, float* delta_ws, void* stream);
+                  float* dq, float* dk, float* dv, float* delta_ws, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 
 /* ---- K3b: per-class prototype sums + paradigm EMA (condgraph.py:395-398 class means;
  *      :558-617 update_prototype / _nx1 / _nx1_rnn) -------------------------------

@@ -23,6 +23,9 @@ int launch_attn_bwd_tc(const float* q, const float* k, const float* v, const flo
 int64_t attn_t5_workspace_bytes(int m);
 int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
                        float* lse, void* workspace, cudaStream_t st);
+int64_t attn_t5_bwd_workspace_bytes(int m);
+int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
+                       float scale, float drop_p, uint64_t seed, float* dq, float* dk, float* dv, void* workspace, cudaStream_t st);
 static int attn_simt() {
   static const int v = getenv("SCAN_B200_ATTN_TC") ? !atoi(getenv("SCAN_B200_ATTN_TC")) : 1;
   return v;
@@ -313,6 +316,8 @@ static int set_attn_attrs() {
 
 extern "C" int64_t scan_attn_workspace_bytes(int32_t m) { return m > 0 ? scan::attn_t5_workspace_bytes(m) : 0; }
 
+extern "C" int64_t scan_attn_bwd_workspace_bytes(int32_t m) { return m > 0 ? scan::attn_t5_bwd_workspace_bytes(m) : 0; }
+
 extern "C" int scan_attn_fwd(const float* q, const float* k, const float* v, int32_t m, float scale, float dropout_p, uint64_t seed,
                              float* ctx, float* lse, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace scan;
@@ -333,7 +338,7 @@ extern "C" int scan_attn_fwd(const float* q, const float* k, const float* v, int
 
 extern "C" int scan_attn_bwd(const float* q, const float* k, const float* v, const float* ctx, const float* lse, const float* d_ctx,
                              int32_t m, float scale, float dropout_p, uint64_t seed, float* dq, float* dk, float* dv,
-                             float* delta_ws, void* stream) {
+                             float* delta_ws, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace scan;
   if (m == 0) return SCAN_OK;
   if (!q || !k || !v || !ctx || !lse || !d_ctx || !dq || !dk || !dv || !delta_ws || m < 0) return SCAN_EINVAL;
@@ -341,9 +346,13 @@ extern "C" int scan_attn_bwd(const float* q, const float* k, const float* v, con
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long n_rows = 4ll * m;
-  SCAN_CUDA_CHECK(cudaMemsetAsync(dq, 0, sizeof(float) * n_rows * AT_D, st));
   attn_delta_kernel<<<(unsigned)ceil_div(n_rows * 16, 256), 256, 0, st>>>(ctx, d_ctx, n_rows, delta_ws);
   SCAN_LAUNCH_CHECK("attn_delta_kernel");
+  if (workspace) {  // tcgen05 path: every gradient row is written exactly once, no zero-fill needed
+    if (workspace_bytes < attn_t5_bwd_workspace_bytes(m)) return SCAN_ECAPACITY;
+    return launch_attn_bwd_t5(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv, workspace, st);
+  }
+  SCAN_CUDA_CHECK(cudaMemsetAsync(dq, 0, sizeof(float) * n_rows * AT_D, st));
   if (!attn_simt()) return launch_attn_bwd_tc(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv, st);
   dim3 grid((m + AT_T - 1) / AT_T, 4);
   attn_bwd_kernel<<<grid, 256, 6 * AT_TILE * 4, st>>>(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv);

@@ -1,0 +1,567 @@
+// K3a backward on tcgen05 (see attention_t5.cu for the forward and the numerics).  Two kernels, both recompute the
+// probabilities from the saved log-sum-exp and keep their accumulators in tensor memory across the whole loop:
+//   attn_bwd_dq_t5_kernel   CTA = 128 queries (TMEM lanes), loops over 64-key tiles:
+//        S = Q K^T, dP = dO V^T -> dS = P (dP*keep - D) -> hi/lo to TMEM -> dQ += dS K          (B = K^T planes)
+//   attn_bwd_dkv_t5_kernel  CTA = 128 keys (TMEM lanes), loops over 32-query tiles:
+//        S^T = K Q^T, dP^T = V dO^T -> P~^T, dS^T -> hi/lo to TMEM -> dV += P~^T dO, dK += dS^T Q (B = dO^T / Q^T planes)
+// Every product is 3xTF32 with the "hi x (hi | lo)" pair fused into one wide-N MMA.  No atomics: dQ, dK, dV are each
+// written once.  Operand planes come from attn_bwd_prep_kernel.
+#include "tc_common.cuh"
+
+namespace scan {
+
+constexpr int B5_THREADS = 640;           // warps 0-3 control, 4..19 elementwise (lane quarter = w % 4, column block = w / 4)
+constexpr int B5_EW = 512;
+constexpr int B5_BOX128 = 128 * 32 * 4;   // 16 KB  [128 rows x 32 cols]
+constexpr int B5_BOX64 = 64 * 32 * 4;     // 8 KB
+constexpr int B5_BOX32 = 32 * 32 * 4;     // 4 KB
+constexpr uint32_t B5_ID128 = umma_idesc_tf32(128, 128);
+constexpr uint32_t B5_ID64 = umma_idesc_tf32(128, 64);
+constexpr uint32_t B5_ID32 = umma_idesc_tf32(128, 32);
+
+__device__ __forceinline__ void b5_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void b5_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void b5_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void b5_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void b5_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void b5_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void b5_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void b5_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void b5_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// ---------------------------------------------------------------------------- pre-pass
+// rows:   dst_hl[r] = hi(src[r]) | lo(src[r])                       ([4M, 64] -> [4M, 128])
+// planes: dst_t[chunk][d | 64 + d][key] = hi | lo of src[chunk*M + key][d], zero for key >= M   ([4][128][Mp])
+struct PrepArgs {
+  const float* rows_src[4];
+  float* rows_dst[4];
+  const float* t_src[3];
+  float* t_dst[3];
+  int n_rows, n_t;
+};
+
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(PrepArgs a, int m, int mp) {
+  __shared__ float th[64][33], tl[64][33];
+  const long long n_rows = 4ll * m;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 16; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i >> 4;
+    const int c4 = (int)(i & 15);
+    for (int which = 0; which < a.n_rows; ++which) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a.rows_src[which] + row * 64) + c4);
+      float4 h, l;
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u); l.x = x.x - h.x;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u); l.y = x.y - h.y;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u); l.z = x.z - h.z;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u); l.w = x.w - h.w;
+      float* dst = a.rows_dst[which] + row * 128;
+      reinterpret_cast<float4*>(dst)[c4] = h;
+      reinterpret_cast<float4*>(dst + 64)[c4] = l;
+    }
+  }
+  const int tiles_per_chunk = mp / 32;
+  for (int tile = blockIdx.x; tile < a.n_t * 4 * tiles_per_chunk; tile += gridDim.x) {
+    const int which = tile / (4 * tiles_per_chunk);
+    const int rem = tile % (4 * tiles_per_chunk);
+    const int chunk = rem / tiles_per_chunk, j0 = (rem % tiles_per_chunk) * 32;
+    const float* src = a.t_src[which];
+    float* dst = a.t_dst[which];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+      const int key = i >> 6, d = i & 63;
+      float x = 0.f;
+      if (j0 + key < m) x = __ldg(src + ((long long)chunk * m + j0 + key) * 64 + d);
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+      th[d][key] = __uint_as_float(u);
+      tl[d][key] = x - __uint_as_float(u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+      const int d = i >> 5, key = i & 31;
+      dst[((long long)chunk * 128 + d) * mp + j0 + key] = th[d][key];
+      dst[((long long)chunk * 128 + 64 + d) * mp + j0 + key] = tl[d][key];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- dQ
+// smem: Q hi/lo (4 x 16 KB) | dO hi/lo (4 x 16 KB) | K stage 32 KB | V stage 32 KB | K^T stage 32 KB
+// TMEM: S [0,192)  dP [192,384)  dS operand slot hi|lo aliases [0,128)  dQ accumulator [384,512)
+constexpr int DQ_SMEM = 1024 + 8 * B5_BOX128 + 3 * 4 * B5_BOX64 + 1024;
+
+__global__ void __launch_bounds__(B5_THREADS, 1)
+    attn_bwd_dq_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                          const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                          const __grid_constant__ CUtensorMap map_kt, const float* __restrict__ lse, const float* __restrict__ delta,
+                          int m, float scale, float drop_p, uint64_t seed, float* __restrict__ dq) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;
+  uint8_t* do_s = q_s + 4 * B5_BOX128;
+  uint8_t* k_s = do_s + 4 * B5_BOX128;
+  uint8_t* v_s = k_s + 4 * B5_BOX64;
+  uint8_t* kt_s = v_s + 4 * B5_BOX64;
+  uint64_t* bars = (uint64_t*)(kt_s + 4 * B5_BOX64);
+  uint64_t* r_full = bars;        // resident Q, dO
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;
+  uint64_t* v_empty = bars + 4;
+  uint64_t* kt_full = bars + 5;
+  uint64_t* kt_empty = bars + 6;
+  uint64_t* sp_full = bars + 7;   // S and dP ready
+  uint64_t* ds_full = bars + 8;   // dS operand written (512 arrivals)
+  uint64_t* dq_done = bars + 9;   // dQ MMAs of the tile retired: S region / dS slot may be overwritten
+  uint64_t* acc_full = bars + 10;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.y;
+  const long long base = (long long)chunk * m;
+  const int i0 = blockIdx.x * 128;
+  const int n_tiles = (m + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 11; ++i) mbar_init(smem_u32(bars + i), i == 8 ? B5_EW : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(r_full), 8 * B5_BOX128);
+      for (int part = 0; part < 2; ++part)
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(smem_u32(q_s + (part * 2 + kb) * B5_BOX128), &map_q, smem_u32(r_full), part * 64 + kb * 32, (int)(base + i0));
+          tma_load_2d(smem_u32(do_s + (part * 2 + kb) * B5_BOX128), &map_do, smem_u32(r_full), part * 64 + kb * 32, (int)(base + i0));
+        }
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * 64;
+        const uint32_t ph = (uint32_t)(t & 1);
+        mbar_wait(smem_u32(k_empty), ph ^ 1);
+        mbar_expect_tx(smem_u32(k_full), 4 * B5_BOX64);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part)
+            tma_load_2d(smem_u32(k_s + (kb * 2 + part) * B5_BOX64), &map_k, smem_u32(k_full), part * 64 + kb * 32, (int)(base + j0));
+        mbar_wait(smem_u32(v_empty), ph ^ 1);
+        mbar_expect_tx(smem_u32(v_full), 4 * B5_BOX64);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part)
+            tma_load_2d(smem_u32(v_s + (kb * 2 + part) * B5_BOX64), &map_v, smem_u32(v_full), part * 64 + kb * 32, (int)(base + j0));
+        mbar_wait(smem_u32(kt_empty), ph ^ 1);
+        mbar_expect_tx(smem_u32(kt_full), 4 * B5_BOX64);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part)
+            tma_load_2d(smem_u32(kt_s + (kb * 2 + part) * B5_BOX64), &map_kt, smem_u32(kt_full), j0 + kb * 32, chunk * 128 + part * 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(r_full), 0);
+      tcgen05_fence_after();
+      const uint32_t qa = smem_u32(q_s), da = smem_u32(do_s), ka = smem_u32(k_s), va = smem_u32(v_s), kta = smem_u32(kt_s);
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t ph = (uint32_t)(t & 1);
+        if (t > 0) mbar_wait(smem_u32(dq_done), ph ^ 1);   // dQ MMAs of tile t-1 retired (they read the aliased dS slot)
+        mbar_wait(smem_u32(k_full), ph);
+        mbar_wait(smem_u32(v_full), ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb | k) != 0;
+            const uint64_t bk = umma_desc_sw128(ka + kb * 2 * B5_BOX64 + k * 32);
+            const uint64_t bv = umma_desc_sw128(va + kb * 2 * B5_BOX64 + k * 32);
+            b5_mma_ss(tmem_base + 0, umma_desc_sw128(qa + kb * B5_BOX128 + k * 32), bk, B5_ID128, acc);           // Sa
+            b5_mma_ss(tmem_base + 192, umma_desc_sw128(da + kb * B5_BOX128 + k * 32), bv, B5_ID128, acc);        // dPa
+            b5_mma_ss(tmem_base + 128, umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32), bk, B5_ID64, acc);   // Sb
+            b5_mma_ss(tmem_base + 320, umma_desc_sw128(da + (2 + kb) * B5_BOX128 + k * 32), bv, B5_ID64, acc);   // dPb
+          }
+        umma_commit(smem_u32(k_empty));
+        umma_commit(smem_u32(v_empty));
+        umma_commit(smem_u32(sp_full));
+        mbar_wait(smem_u32(ds_full), ph);
+        mbar_wait(smem_u32(kt_full), ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (t | kb | k) != 0;
+            const uint64_t b = umma_desc_sw128(kta + kb * 2 * B5_BOX64 + k * 32);
+            b5_mma_ts(tmem_base + 384, tmem_base + kb * 32 + k * 8, b, B5_ID128, acc);        // dS_hi . [Kt_hi ; Kt_lo]
+            b5_mma_ts(tmem_base + 384, tmem_base + 64 + kb * 32 + k * 8, b, B5_ID64, 1);      // dS_lo . Kt_hi
+          }
+        umma_commit(smem_u32(kt_empty));
+        umma_commit(smem_u32(dq_done));
+      }
+      umma_commit(smem_u32(acc_full));
+    }
+  } else if (warp >= 4) {
+    const int w = warp - 4;
+    const int qd = w & 3, cq = w >> 2;
+    const int row = qd * 32 + lane, grow = i0 + row;
+    const uint32_t lb = (uint32_t)(qd * 32) << 16;
+    const float lse_r = grow < m ? __ldg(lse + base + grow) : 0.f;
+    const float dl_r = grow < m ? __ldg(delta + base + grow) : 0.f;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    float a[16], b[16], c[16], x[16], y[16], z[16];
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
+      tcgen05_fence_after();
+      const uint32_t tb = tmem_base + lb;
+      b5_ld16(tb + cq * 16, a);
+      b5_ld16(tb + 64 + cq * 16, b);
+      b5_ld16(tb + 128 + cq * 16, c);
+      b5_ld16(tb + 192 + cq * 16, x);
+      b5_ld16(tb + 256 + cq * 16, y);
+      b5_ld16(tb + 320 + cq * 16, z);
+      b5_ld_wait();
+      // the dS slot columns this warp writes below (cq*16.. and 64+cq*16..) are exactly the ones it just read
+      const int j0 = t * 64 + cq * 16;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float ds = 0.f;
+        if (grow < m && j0 + e < m) {
+          const float p = expf((a[e] + b[e] + c[e]) * scale - lse_r);
+          float keep = 1.f;
+          if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? inv_keep : 0.f;
+          ds = p * ((x[e] + y[e] + z[e]) * keep - dl_r);
+        }
+        b5_split(ds, hi[e], lo[e]);
+      }
+      b5_st16(tb + cq * 16, hi);
+      b5_st16(tb + 64 + cq * 16, lo);
+      b5_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(ds_full));
+    }
+    mbar_wait(smem_u32(acc_full), 0);
+    tcgen05_fence_after();
+    b5_ld16(tmem_base + lb + 384 + cq * 16, a);
+    b5_ld16(tmem_base + lb + 448 + cq * 16, b);
+    b5_ld_wait();
+    if (grow < m) {
+      float4* dst = reinterpret_cast<float4*>(dq + (base + grow) * 64 + cq * 16);
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4)
+        dst[e4] = make_float4((a[4 * e4] + b[4 * e4]) * scale, (a[4 * e4 + 1] + b[4 * e4 + 1]) * scale,
+                              (a[4 * e4 + 2] + b[4 * e4 + 2]) * scale, (a[4 * e4 + 3] + b[4 * e4 + 3]) * scale);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------- dK, dV
+// smem: K hi/lo (4 x 16 KB) | V hi/lo (4 x 16 KB) | Q stage 16 KB | dO stage 16 KB | dO^T stage 16 KB | Q^T stage 16 KB
+// TMEM: S^T [0,96)  dP^T [96,192)  operand slots alias [0,128): P~^T hi [0,32) lo [32,64), dS^T hi [64,96) lo [96,128)
+//       dV accumulator [256,384)  dK accumulator [384,512)
+constexpr int DKV_SMEM = 1024 + 8 * B5_BOX128 + 4 * 4 * B5_BOX32 + 1024;
+
+__global__ void __launch_bounds__(B5_THREADS, 1)
+    attn_bwd_dkv_t5_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                           const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                           const __grid_constant__ CUtensorMap map_dot, const __grid_constant__ CUtensorMap map_qt,
+                           const float* __restrict__ lse, const float* __restrict__ delta, int m, float scale, float drop_p,
+                           uint64_t seed, float* __restrict__ dk, float* __restrict__ dv) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* k_s = smem;
+  uint8_t* v_s = k_s + 4 * B5_BOX128;
+  uint8_t* q_s = v_s + 4 * B5_BOX128;      // [kb][hi 4 KB | lo 4 KB]
+  uint8_t* do_s = q_s + 4 * B5_BOX32;
+  uint8_t* dot_s = do_s + 4 * B5_BOX32;    // [hi d 0..63 (8 KB) | lo (8 KB)] x 32 queries
+  uint8_t* qt_s = dot_s + 4 * B5_BOX32;
+  uint64_t* bars = (uint64_t*)(qt_s + 4 * B5_BOX32);
+  uint64_t* r_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = bars + 2;    // Q and dO row tiles (S-type operands)
+  uint64_t* t_full = bars + 3;
+  uint64_t* t_empty = bars + 4;    // dO^T and Q^T planes (accumulation operands)
+  uint64_t* sp_full = bars + 5;
+  uint64_t* op_full = bars + 6;    // 512 arrivals
+  uint64_t* acc_done = bars + 7;
+  uint64_t* acc_full = bars + 8;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.y;
+  const long long base = (long long)chunk * m;
+  const int j0 = blockIdx.x * 128;            // first key of this CTA
+  const int n_tiles = (m + 31) / 32;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(smem_u32(bars + i), i == 6 ? B5_EW : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(r_full), 8 * B5_BOX128);
+      for (int part = 0; part < 2; ++part)
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(smem_u32(k_s + (part * 2 + kb) * B5_BOX128), &map_k, smem_u32(r_full), part * 64 + kb * 32, (int)(base + j0));
+          tma_load_2d(smem_u32(v_s + (part * 2 + kb) * B5_BOX128), &map_v, smem_u32(r_full), part * 64 + kb * 32, (int)(base + j0));
+        }
+      for (int t = 0; t < n_tiles; ++t) {
+        const int i0 = t * 32;
+        const uint32_t ph = (uint32_t)(t & 1);
+        mbar_wait(smem_u32(q_empty), ph ^ 1);
+        mbar_expect_tx(smem_u32(q_full), 8 * B5_BOX32);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part) {
+            tma_load_2d(smem_u32(q_s + (kb * 2 + part) * B5_BOX32), &map_q, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
+            tma_load_2d(smem_u32(do_s + (kb * 2 + part) * B5_BOX32), &map_do, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
+          }
+        mbar_wait(smem_u32(t_empty), ph ^ 1);
+        mbar_expect_tx(smem_u32(t_full), 4 * B5_BOX64);
+        for (int part = 0; part < 2; ++part) {
+          tma_load_2d(smem_u32(dot_s + part * B5_BOX64), &map_dot, smem_u32(t_full), i0, chunk * 128 + part * 64);
+          tma_load_2d(smem_u32(qt_s + part * B5_BOX64), &map_qt, smem_u32(t_full), i0, chunk * 128 + part * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(r_full), 0);
+      tcgen05_fence_after();
+      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s), qa = smem_u32(q_s), da = smem_u32(do_s);
+      const uint32_t dota = smem_u32(dot_s), qta = smem_u32(qt_s);
+      for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t ph = (uint32_t)(t & 1);
+        if (t > 0) mbar_wait(smem_u32(acc_done), ph ^ 1);
+        mbar_wait(smem_u32(q_full), ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb | k) != 0;
+            const uint64_t bq = umma_desc_sw128(qa + kb * 2 * B5_BOX32 + k * 32);
+            const uint64_t bd = umma_desc_sw128(da + kb * 2 * B5_BOX32 + k * 32);
+            b5_mma_ss(tmem_base + 0, umma_desc_sw128(ka + kb * B5_BOX128 + k * 32), bq, B5_ID64, acc);           // S^T a: K_hi . [Q_hi;Q_lo]
+            b5_mma_ss(tmem_base + 96, umma_desc_sw128(va + kb * B5_BOX128 + k * 32), bd, B5_ID64, acc);          // dP^T a
+            b5_mma_ss(tmem_base + 64, umma_desc_sw128(ka + (2 + kb) * B5_BOX128 + k * 32), bq, B5_ID32, acc);    // S^T b: K_lo . Q_hi
+            b5_mma_ss(tmem_base + 160, umma_desc_sw128(va + (2 + kb) * B5_BOX128 + k * 32), bd, B5_ID32, acc);   // dP^T b
+          }
+        umma_commit(smem_u32(q_empty));
+        umma_commit(smem_u32(sp_full));
+        mbar_wait(smem_u32(op_full), ph);
+        mbar_wait(smem_u32(t_full), ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (t | k) != 0;
+          const uint64_t bdo = umma_desc_sw128(dota + k * 32);
+          const uint64_t bq = umma_desc_sw128(qta + k * 32);
+          b5_mma_ts(tmem_base + 256, tmem_base + 0 + k * 8, bdo, B5_ID128, acc);    // dV  += P~^T_hi . [dO^T_hi ; dO^T_lo]
+          b5_mma_ts(tmem_base + 384, tmem_base + 64 + k * 8, bq, B5_ID128, acc);    // dK  += dS^T_hi . [Q^T_hi ; Q^T_lo]
+          b5_mma_ts(tmem_base + 256, tmem_base + 32 + k * 8, bdo, B5_ID64, 1);      // dV  += P~^T_lo . dO^T_hi
+          b5_mma_ts(tmem_base + 384, tmem_base + 96 + k * 8, bq, B5_ID64, 1);       // dK  += dS^T_lo . Q^T_hi
+        }
+        umma_commit(smem_u32(t_empty));
+        umma_commit(smem_u32(acc_done));
+      }
+      umma_commit(smem_u32(acc_full));
+    }
+  } else if (warp >= 4) {
+    const int w = warp - 4;
+    const int qd = w & 3, cq = w >> 2;             // 8 query columns per warp
+    const int row = qd * 32 + lane, gkey = j0 + row;
+    const uint32_t lb = (uint32_t)(qd * 32) << 16;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    float a[8], b[8], c[8], x[8], y[8], z[8];
+    for (int t = 0; t < n_tiles; ++t) {
+      const int i0 = t * 32 + cq * 8;
+      float lse_c[8], dl_c[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        lse_c[e] = (i0 + e < m) ? __ldg(lse + base + i0 + e) : 0.f;
+        dl_c[e] = (i0 + e < m) ? __ldg(delta + base + i0 + e) : 0.f;
+      }
+      mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
+      tcgen05_fence_after();
+      const uint32_t tb = tmem_base + lb;
+      b5_ld8(tb + cq * 8, a);
+      b5_ld8(tb + 32 + cq * 8, b);
+      b5_ld8(tb + 64 + cq * 8, c);
+      b5_ld8(tb + 96 + cq * 8, x);
+      b5_ld8(tb + 128 + cq * 8, y);
+      b5_ld8(tb + 160 + cq * 8, z);
+      b5_ld_wait();
+      // the operand-slot columns written below are columns this same warp just read (no cross-warp hazard)
+      uint32_t ph_[8], pl_[8], sh_[8], sl_[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float pt = 0.f, ds = 0.f;
+        if (gkey < m && i0 + e < m) {
+          const float p = expf((a[e] + b[e] + c[e]) * scale - lse_c[e]);
+          float keep = 1.f;
+          if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, i0 + e, gkey) >= drop_thr) ? inv_keep : 0.f;
+          pt = p * keep;
+          ds = p * ((x[e] + y[e] + z[e]) * keep - dl_c[e]);
+        }
+        b5_split(pt, ph_[e], pl_[e]);
+        b5_split(ds, sh_[e], sl_[e]);
+      }
+      b5_st8(tb + 0 + cq * 8, ph_);
+      b5_st8(tb + 32 + cq * 8, pl_);
+      b5_st8(tb + 64 + cq * 8, sh_);
+      b5_st8(tb + 96 + cq * 8, sl_);
+      b5_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(op_full));
+    }
+    mbar_wait(smem_u32(acc_full), 0);
+    tcgen05_fence_after();
+    float o0[16], o1[16];
+    b5_ld16(tmem_base + lb + 256 + cq * 16, o0);
+    b5_ld16(tmem_base + lb + 320 + cq * 16, o1);
+    b5_ld_wait();
+    if (gkey < m) {
+      float4* dst = reinterpret_cast<float4*>(dv + (base + gkey) * 64 + cq * 16);
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4)
+        dst[e4] = make_float4(o0[4 * e4] + o1[4 * e4], o0[4 * e4 + 1] + o1[4 * e4 + 1], o0[4 * e4 + 2] + o1[4 * e4 + 2],
+                              o0[4 * e4 + 3] + o1[4 * e4 + 3]);
+    }
+    b5_ld16(tmem_base + lb + 384 + cq * 16, o0);
+    b5_ld16(tmem_base + lb + 448 + cq * 16, o1);
+    b5_ld_wait();
+    if (gkey < m) {
+      float4* dst = reinterpret_cast<float4*>(dk + (base + gkey) * 64 + cq * 16);
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4)
+        dst[e4] = make_float4((o0[4 * e4] + o1[4 * e4]) * scale, (o0[4 * e4 + 1] + o1[4 * e4 + 1]) * scale,
+                              (o0[4 * e4 + 2] + o1[4 * e4 + 2]) * scale, (o0[4 * e4 + 3] + o1[4 * e4 + 3]) * scale);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+static int g_b5_attr = 0;
+
+int64_t attn_t5_bwd_workspace_bytes(int m) {
+  const long long mp = ((long long)m + 63) / 64 * 64;
+  return (4ll * (4ll * m * 128) + 3ll * (4ll * 128 * mp)) * 4 + 1024;
+}
+
+int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
+                       float scale, float drop_p, uint64_t seed, float* dq, float* dk, float* dv, void* workspace, cudaStream_t st) {
+  const int mp = (m + 63) / 64 * 64;
+  const long long hl = 4ll * m * 128, pl = 4ll * 128 * mp;
+  float* w0 = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float *q_hl = w0, *k_hl = w0 + hl, *v_hl = w0 + 2 * hl, *do_hl = w0 + 3 * hl;
+  float *kt = w0 + 4 * hl, *dot = kt + pl, *qt = dot + pl;
+  PrepArgs pa;
+  pa.n_rows = 4;
+  pa.rows_src[0] = q; pa.rows_src[1] = k; pa.rows_src[2] = v; pa.rows_src[3] = d_ctx;
+  pa.rows_dst[0] = q_hl; pa.rows_dst[1] = k_hl; pa.rows_dst[2] = v_hl; pa.rows_dst[3] = do_hl;
+  pa.n_t = 3;
+  pa.t_src[0] = k; pa.t_src[1] = d_ctx; pa.t_src[2] = q;
+  pa.t_dst[0] = kt; pa.t_dst[1] = dot; pa.t_dst[2] = qt;
+  attn_bwd_prep_kernel<<<4 * sm_count(), 256, 0, st>>>(pa, m, mp);
+  SCAN_LAUNCH_CHECK("attn_bwd_prep_kernel");
+  CUtensorMap mq128, mdo128, mk128, mv128, mk64, mv64, mq32, mdo32, mkt, mdot, mqt;
+  int rc = 0;
+  rc |= make_rowmajor_map(&mq128, q_hl, 4ull * m, 128, 128);
+  rc |= make_rowmajor_map(&mdo128, do_hl, 4ull * m, 128, 128);
+  rc |= make_rowmajor_map(&mk128, k_hl, 4ull * m, 128, 128);
+  rc |= make_rowmajor_map(&mv128, v_hl, 4ull * m, 128, 128);
+  rc |= make_rowmajor_map(&mk64, k_hl, 4ull * m, 128, 64);
+  rc |= make_rowmajor_map(&mv64, v_hl, 4ull * m, 128, 64);
+  rc |= make_rowmajor_map(&mq32, q_hl, 4ull * m, 128, 32);
+  rc |= make_rowmajor_map(&mdo32, do_hl, 4ull * m, 128, 32);
+  rc |= make_rowmajor_map(&mkt, kt, 4ull * 128, (uint64_t)mp, 64);
+  rc |= make_rowmajor_map(&mdot, dot, 4ull * 128, (uint64_t)mp, 64);
+  rc |= make_rowmajor_map(&mqt, qt, 4ull * 128, (uint64_t)mp, 64);
+  if (rc) return SCAN_ECUDA;
+  if (!g_b5_attr) {
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    g_b5_attr = 1;
+  }
+  dim3 grid((m + 127) / 128, 4);
+  attn_bwd_dq_t5_kernel<<<grid, B5_THREADS, DQ_SMEM, st>>>(mq128, mdo128, mk64, mv64, mkt, lse, delta, m, scale, drop_p, seed, dq);
+  SCAN_LAUNCH_CHECK("attn_bwd_dq_t5_kernel");
+  attn_bwd_dkv_t5_kernel<<<grid, B5_THREADS, DKV_SMEM, st>>>(mk128, mv128, mq32, mdo32, mdot, mqt, lse, delta, m, scale, drop_p, seed,
+                                                            dk, dv);
+  SCAN_LAUNCH_CHECK("attn_bwd_dkv_t5_kernel");
+  return SCAN_OK;
+}
+
+}  // namespace scan

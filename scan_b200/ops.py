@@ -270,8 +270,9 @@ def condconv(geo, rows, weight, bias, num_classes, act_mode, labels=None, loss_w
 # ----------------------------------------------------------------------------------------------------
 # K3a: attention
 # ----------------------------------------------------------------------------------------------------
-# forward implementation: "t5" = tcgen05 kernel (product), "ffma" = fp32 verification kernel (SCAN_B200_ATTN_FWD=ffma)
-ATTN_IMPL = {"fwd": __import__("os").environ.get("SCAN_B200_ATTN_FWD", "t5")}
+# implementations: "t5" = tcgen05 kernels (product), "ffma" = fp32 verification kernels (SCAN_B200_ATTN_FWD/BWD=ffma)
+ATTN_IMPL = {"fwd": __import__("os").environ.get("SCAN_B200_ATTN_FWD", "t5"),
+             "bwd": __import__("os").environ.get("SCAN_B200_ATTN_BWD", "t5")}
 
 
 class _Attention(torch.autograd.Function):
@@ -299,8 +300,11 @@ class _Attention(torch.autograd.Function):
         m = q.shape[0]
         dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         delta = torch.empty((4 * m,), device=q.device, dtype=torch.float32)
+        ws = None
+        if ATTN_IMPL["bwd"] == "t5":
+            ws = torch.empty((_lib.lib().scan_attn_bwd_workspace_bytes(m),), device=q.device, dtype=torch.uint8)
         call("scan_attn_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), _ptr(d_out), m, scale, drop_p, seed,
-             _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta), _stream())
+             _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta), _ptr(ws), 0 if ws is None else ws.numel(), _stream())
         return dq, dk, dv, None, None, None
 
 

@@ -228,6 +228,26 @@ def test_attention_dropout_is_consistent_between_forward_and_backward():
     assert abs(float(dropped.mean()) - float(base.mean())) < 0.02
 
 
+@pytest.mark.parametrize("m,drop", [(300, 0.1), (1, 0.0), (129, 0.3), (1000, 0.0)])
+def test_attention_tcgen05_and_ffma_kernels_agree(m, drop):
+    """The tcgen05 forward/backward (product) against the fp32 FFMA kernels, same dropout mask (shared counter hash)."""
+    g = torch.Generator().manual_seed(m + 17)
+    q, k, v, cot = [torch.randn(m, 256, generator=g).to(DEV) for _ in range(4)]
+    res = {}
+    saved = dict(ops.ATTN_IMPL)
+    try:
+        for impl in ("ffma", "t5"):
+            ops.ATTN_IMPL.update(fwd=impl, bwd=impl)
+            qd, kd, vd = [t.clone().requires_grad_(True) for t in (q, k, v)]
+            out = ops.chunked_attention(qd, kd, vd, 0.25, drop, 4321)
+            (out * cot).sum().backward()
+            res[impl] = (out.detach(), qd.grad, kd.grad, vd.grad)
+    finally:
+        ops.ATTN_IMPL.update(saved)
+    for name, a, b in zip(("ctx", "dq", "dk", "dv"), res["t5"], res["ffma"]):
+        _close(a, b, 5e-5, name)
+
+
 def test_class_sums_and_proto_update():
     g = torch.Generator().manual_seed(4)
     m, k = 3000, 9
