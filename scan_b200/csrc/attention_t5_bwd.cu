@@ -128,8 +128,18 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(PrepArgs a, int m, i
 
 // ---------------------------------------------------------------------------- dQ
 // smem: Q hi/lo (4 x 16 KB) | dO hi/lo (4 x 16 KB) | K stage 32 KB | V stage 32 KB | K^T stage 32 KB
-// TMEM: S [0,192)  dP [192,384)  dS operand slot hi|lo aliases [0,128)  dQ accumulator [384,512)
+// TMEM: S [0,192) (wide: hi.hi | hi.lo | lo.hi)   dP [192,256) (three MMAs into one accumulator)
+//       dS operand slot hi [256,320) lo [320,384)   dQ accumulator [384,512)
+// Pipeline: the elementwise warps pull S/dP of tile t into registers and release the TMEM region at once, so the tensor
+// pipe computes S/dP of tile t+1 while they work; dQ MMAs of tile t follow as soon as dS(t) is in the operand slot.
 constexpr int DQ_SMEM = 1024 + 8 * B5_BOX128 + 3 * 4 * B5_BOX64 + 1024;
+constexpr float B5_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float b5_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(B5_THREADS, 1)
     attn_bwd_dq_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
@@ -151,11 +161,12 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint64_t* v_empty = bars + 4;
   uint64_t* kt_full = bars + 5;
   uint64_t* kt_empty = bars + 6;
-  uint64_t* sp_full = bars + 7;   // S and dP ready
-  uint64_t* ds_full = bars + 8;   // dS operand written (512 arrivals)
-  uint64_t* dq_done = bars + 9;   // dQ MMAs of the tile retired: S region / dS slot may be overwritten
-  uint64_t* acc_full = bars + 10;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 11);
+  uint64_t* sp_full = bars + 7;   // S and dP of a tile are in TMEM
+  uint64_t* sp_free = bars + 8;   // ... and have been pulled into registers (512 arrivals)
+  uint64_t* ds_full = bars + 9;   // dS operand written (512 arrivals)
+  uint64_t* dq_done = bars + 10;  // dQ MMAs of the tile retired: the dS slot may be overwritten
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const int n_tiles = (m + 63) / 64;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 11; ++i) mbar_init(smem_u32(bars + i), i == 8 ? B5_EW : 1);
+    for (int i = 0; i < 12; ++i) mbar_init(smem_u32(bars + i), (i == 8 || i == 9) ? B5_EW : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -210,9 +221,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       mbar_wait(smem_u32(r_full), 0);
       tcgen05_fence_after();
       const uint32_t qa = smem_u32(q_s), da = smem_u32(do_s), ka = smem_u32(k_s), va = smem_u32(v_s), kta = smem_u32(kt_s);
-      for (int t = 0; t < n_tiles; ++t) {
+      auto issue_sdp = [&](int t) {
         const uint32_t ph = (uint32_t)(t & 1);
-        if (t > 0) mbar_wait(smem_u32(dq_done), ph ^ 1);   // dQ MMAs of tile t-1 retired (they read the aliased dS slot)
         mbar_wait(smem_u32(k_full), ph);
         mbar_wait(smem_u32(v_full), ph);
         tcgen05_fence_after();
@@ -222,15 +232,30 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0;
             const uint64_t bk = umma_desc_sw128(ka + kb * 2 * B5_BOX64 + k * 32);
-            const uint64_t bv = umma_desc_sw128(va + kb * 2 * B5_BOX64 + k * 32);
-            b5_mma_ss(tmem_base + 0, umma_desc_sw128(qa + kb * B5_BOX128 + k * 32), bk, B5_ID128, acc);           // Sa
-            b5_mma_ss(tmem_base + 192, umma_desc_sw128(da + kb * B5_BOX128 + k * 32), bv, B5_ID128, acc);        // dPa
-            b5_mma_ss(tmem_base + 128, umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32), bk, B5_ID64, acc);   // Sb
-            b5_mma_ss(tmem_base + 320, umma_desc_sw128(da + (2 + kb) * B5_BOX128 + k * 32), bv, B5_ID64, acc);   // dPb
+            const uint64_t bvh = umma_desc_sw128(va + kb * 2 * B5_BOX64 + k * 32);
+            const uint64_t bvl = umma_desc_sw128(va + (kb * 2 + 1) * B5_BOX64 + k * 32);
+            const uint64_t aqh = umma_desc_sw128(qa + kb * B5_BOX128 + k * 32);
+            const uint64_t aql = umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32);
+            const uint64_t adh = umma_desc_sw128(da + kb * B5_BOX128 + k * 32);
+            const uint64_t adl = umma_desc_sw128(da + (2 + kb) * B5_BOX128 + k * 32);
+            b5_mma_ss(tmem_base + 0, aqh, bk, B5_ID128, acc);     // S: Q_hi . [K_hi ; K_lo]
+            b5_mma_ss(tmem_base + 192, adh, bvh, B5_ID64, acc);   // dP: dO_hi . V_hi
+            b5_mma_ss(tmem_base + 128, aql, bk, B5_ID64, acc);    // S: Q_lo . K_hi
+            b5_mma_ss(tmem_base + 192, adh, bvl, B5_ID64, 1);     // dP: dO_hi . V_lo
+            b5_mma_ss(tmem_base + 192, adl, bvh, B5_ID64, 1);     // dP: dO_lo . V_hi
           }
         umma_commit(smem_u32(k_empty));
         umma_commit(smem_u32(v_empty));
         umma_commit(smem_u32(sp_full));
+      };
+      for (int tt = 0; tt <= n_tiles; ++tt) {
+        if (tt < n_tiles) {
+          if (tt > 0) mbar_wait(smem_u32(sp_free), (uint32_t)((tt - 1) & 1));   // S/dP of tile tt-1 now live in registers
+          issue_sdp(tt);
+        }
+        if (tt == 0) continue;
+        const int t = tt - 1;
+        const uint32_t ph = (uint32_t)(t & 1);
         mbar_wait(smem_u32(ds_full), ph);
         mbar_wait(smem_u32(kt_full), ph);
         tcgen05_fence_after();
@@ -240,8 +265,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (t | kb | k) != 0;
             const uint64_t b = umma_desc_sw128(kta + kb * 2 * B5_BOX64 + k * 32);
-            b5_mma_ts(tmem_base + 384, tmem_base + kb * 32 + k * 8, b, B5_ID128, acc);        // dS_hi . [Kt_hi ; Kt_lo]
-            b5_mma_ts(tmem_base + 384, tmem_base + 64 + kb * 32 + k * 8, b, B5_ID64, 1);      // dS_lo . Kt_hi
+            b5_mma_ts(tmem_base + 384, tmem_base + 256 + kb * 32 + k * 8, b, B5_ID128, acc);   // dS_hi . [Kt_hi ; Kt_lo]
+            b5_mma_ts(tmem_base + 384, tmem_base + 320 + kb * 32 + k * 8, b, B5_ID64, 1);      // dS_lo . Kt_hi
           }
         umma_commit(smem_u32(kt_empty));
         umma_commit(smem_u32(dq_done));
@@ -253,46 +278,48 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const int qd = w & 3, cq = w >> 2;
     const int row = qd * 32 + lane, grow = i0 + row;
     const uint32_t lb = (uint32_t)(qd * 32) << 16;
-    const float lse_r = grow < m ? __ldg(lse + base + grow) : 0.f;
+    // rows past the chunk: lse = +huge makes every probability (and dS) exactly zero
+    const float lse2 = grow < m ? __ldg(lse + base + grow) * B5_LOG2E : 1e30f;
     const float dl_r = grow < m ? __ldg(delta + base + grow) : 0.f;
+    const float sl2 = scale * B5_LOG2E;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
-    float a[16], b[16], c[16], x[16], y[16], z[16];
+    const uint32_t tb = tmem_base + lb;
+    float a[16], b[16], c[16], x[16];
     for (int t = 0; t < n_tiles; ++t) {
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
-      const uint32_t tb = tmem_base + lb;
       b5_ld16(tb + cq * 16, a);
       b5_ld16(tb + 64 + cq * 16, b);
       b5_ld16(tb + 128 + cq * 16, c);
       b5_ld16(tb + 192 + cq * 16, x);
-      b5_ld16(tb + 256 + cq * 16, y);
-      b5_ld16(tb + 320 + cq * 16, z);
       b5_ld_wait();
-      // the dS slot columns this warp writes below (cq*16.. and 64+cq*16..) are exactly the ones it just read
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(sp_free));
       const int j0 = t * 64 + cq * 16;
+      const int lim = m - j0;          // keys j0+e with e >= lim are past the chunk
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        float ds = 0.f;
-        if (grow < m && j0 + e < m) {
-          const float p = expf((a[e] + b[e] + c[e]) * scale - lse_r);
-          float keep = 1.f;
-          if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? inv_keep : 0.f;
-          ds = p * ((x[e] + y[e] + z[e]) * keep - dl_r);
-        }
+        const float p = b5_ex2((a[e] + b[e] + c[e]) * sl2 - lse2);
+        float dp = x[e];
+        if (drop_p > 0.f) dp = (attn_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? dp * inv_keep : 0.f;
+        float ds = p * (dp - dl_r);
+        ds = e < lim ? ds : 0.f;
         b5_split(ds, hi[e], lo[e]);
       }
-      b5_st16(tb + cq * 16, hi);
-      b5_st16(tb + 64 + cq * 16, lo);
+      if (t > 0) mbar_wait(smem_u32(dq_done), (uint32_t)((t - 1) & 1));
+      tcgen05_fence_after();
+      b5_st16(tb + 256 + cq * 16, hi);
+      b5_st16(tb + 320 + cq * 16, lo);
       b5_st_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(ds_full));
     }
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
-    b5_ld16(tmem_base + lb + 384 + cq * 16, a);
-    b5_ld16(tmem_base + lb + 448 + cq * 16, b);
+    b5_ld16(tb + 384 + cq * 16, a);
+    b5_ld16(tb + 448 + cq * 16, b);
     b5_ld_wait();
     if (grow < m) {
       float4* dst = reinterpret_cast<float4*>(dq + (base + grow) * 64 + cq * 16);
@@ -312,8 +339,9 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 
 // ---------------------------------------------------------------------------- dK, dV
 // smem: K hi/lo (4 x 16 KB) | V hi/lo (4 x 16 KB) | Q stage 16 KB | dO stage 16 KB | dO^T stage 16 KB | Q^T stage 16 KB
-// TMEM: S^T [0,96)  dP^T [96,192)  operand slots alias [0,128): P~^T hi [0,32) lo [32,64), dS^T hi [64,96) lo [96,128)
-//       dV accumulator [256,384)  dK accumulator [384,512)
+// TMEM: S^T [0,96) (wide)   dP^T [96,128) (three MMAs)   operand slots P~^T hi [128,160) lo [160,192), dS^T hi [192,224)
+//       lo [224,256)   dV accumulator [256,384)   dK accumulator [384,512)
+// Same register-buffered pipeline as the dQ kernel.
 constexpr int DKV_SMEM = 1024 + 8 * B5_BOX128 + 4 * 4 * B5_BOX32 + 1024;
 
 __global__ void __launch_bounds__(B5_THREADS, 1)
@@ -337,10 +365,11 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint64_t* t_full = bars + 3;
   uint64_t* t_empty = bars + 4;    // dO^T and Q^T planes (accumulation operands)
   uint64_t* sp_full = bars + 5;
-  uint64_t* op_full = bars + 6;    // 512 arrivals
-  uint64_t* acc_done = bars + 7;
-  uint64_t* acc_full = bars + 8;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  uint64_t* sp_free = bars + 6;    // 512 arrivals
+  uint64_t* op_full = bars + 7;    // 512 arrivals
+  uint64_t* acc_done = bars + 8;
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
@@ -349,7 +378,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const int n_tiles = (m + 31) / 32;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(smem_u32(bars + i), i == 6 ? B5_EW : 1);
+    for (int i = 0; i < 10; ++i) mbar_init(smem_u32(bars + i), (i == 6 || i == 7) ? B5_EW : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -394,10 +423,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       tcgen05_fence_after();
       const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s), qa = smem_u32(q_s), da = smem_u32(do_s);
       const uint32_t dota = smem_u32(dot_s), qta = smem_u32(qt_s);
-      for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t ph = (uint32_t)(t & 1);
-        if (t > 0) mbar_wait(smem_u32(acc_done), ph ^ 1);
-        mbar_wait(smem_u32(q_full), ph);
+      auto issue_sdp = [&](int t) {
+        mbar_wait(smem_u32(q_full), (uint32_t)(t & 1));
         tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
@@ -405,14 +432,29 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0;
             const uint64_t bq = umma_desc_sw128(qa + kb * 2 * B5_BOX32 + k * 32);
-            const uint64_t bd = umma_desc_sw128(da + kb * 2 * B5_BOX32 + k * 32);
-            b5_mma_ss(tmem_base + 0, umma_desc_sw128(ka + kb * B5_BOX128 + k * 32), bq, B5_ID64, acc);           // S^T a: K_hi . [Q_hi;Q_lo]
-            b5_mma_ss(tmem_base + 96, umma_desc_sw128(va + kb * B5_BOX128 + k * 32), bd, B5_ID64, acc);          // dP^T a
-            b5_mma_ss(tmem_base + 64, umma_desc_sw128(ka + (2 + kb) * B5_BOX128 + k * 32), bq, B5_ID32, acc);    // S^T b: K_lo . Q_hi
-            b5_mma_ss(tmem_base + 160, umma_desc_sw128(va + (2 + kb) * B5_BOX128 + k * 32), bd, B5_ID32, acc);   // dP^T b
+            const uint64_t bdh = umma_desc_sw128(da + kb * 2 * B5_BOX32 + k * 32);
+            const uint64_t bdl = umma_desc_sw128(da + (kb * 2 + 1) * B5_BOX32 + k * 32);
+            const uint64_t akh = umma_desc_sw128(ka + kb * B5_BOX128 + k * 32);
+            const uint64_t akl = umma_desc_sw128(ka + (2 + kb) * B5_BOX128 + k * 32);
+            const uint64_t avh = umma_desc_sw128(va + kb * B5_BOX128 + k * 32);
+            const uint64_t avl = umma_desc_sw128(va + (2 + kb) * B5_BOX128 + k * 32);
+            b5_mma_ss(tmem_base + 0, akh, bq, B5_ID64, acc);      // S^T: K_hi . [Q_hi ; Q_lo]
+            b5_mma_ss(tmem_base + 96, avh, bdh, B5_ID32, acc);    // dP^T: V_hi . dO_hi
+            b5_mma_ss(tmem_base + 64, akl, bq, B5_ID32, acc);     // S^T: K_lo . Q_hi
+            b5_mma_ss(tmem_base + 96, avh, bdl, B5_ID32, 1);      // dP^T: V_hi . dO_lo
+            b5_mma_ss(tmem_base + 96, avl, bdh, B5_ID32, 1);      // dP^T: V_lo . dO_hi
           }
         umma_commit(smem_u32(q_empty));
         umma_commit(smem_u32(sp_full));
+      };
+      for (int tt = 0; tt <= n_tiles; ++tt) {
+        if (tt < n_tiles) {
+          if (tt > 0) mbar_wait(smem_u32(sp_free), (uint32_t)((tt - 1) & 1));
+          issue_sdp(tt);
+        }
+        if (tt == 0) continue;
+        const int t = tt - 1;
+        const uint32_t ph = (uint32_t)(t & 1);
         mbar_wait(smem_u32(op_full), ph);
         mbar_wait(smem_u32(t_full), ph);
         tcgen05_fence_after();
@@ -421,10 +463,10 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           const uint32_t acc = (t | k) != 0;
           const uint64_t bdo = umma_desc_sw128(dota + k * 32);
           const uint64_t bq = umma_desc_sw128(qta + k * 32);
-          b5_mma_ts(tmem_base + 256, tmem_base + 0 + k * 8, bdo, B5_ID128, acc);    // dV  += P~^T_hi . [dO^T_hi ; dO^T_lo]
-          b5_mma_ts(tmem_base + 384, tmem_base + 64 + k * 8, bq, B5_ID128, acc);    // dK  += dS^T_hi . [Q^T_hi ; Q^T_lo]
-          b5_mma_ts(tmem_base + 256, tmem_base + 32 + k * 8, bdo, B5_ID64, 1);      // dV  += P~^T_lo . dO^T_hi
-          b5_mma_ts(tmem_base + 384, tmem_base + 96 + k * 8, bq, B5_ID64, 1);       // dK  += dS^T_lo . Q^T_hi
+          b5_mma_ts(tmem_base + 256, tmem_base + 128 + k * 8, bdo, B5_ID128, acc);   // dV += P~^T_hi . [dO^T_hi ; dO^T_lo]
+          b5_mma_ts(tmem_base + 384, tmem_base + 192 + k * 8, bq, B5_ID128, acc);    // dK += dS^T_hi . [Q^T_hi ; Q^T_lo]
+          b5_mma_ts(tmem_base + 256, tmem_base + 160 + k * 8, bdo, B5_ID64, 1);      // dV += P~^T_lo . dO^T_hi
+          b5_mma_ts(tmem_base + 384, tmem_base + 224 + k * 8, bq, B5_ID64, 1);       // dK += dS^T_lo . Q^T_hi
         }
         umma_commit(smem_u32(t_empty));
         umma_commit(smem_u32(acc_done));
@@ -436,46 +478,44 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const int qd = w & 3, cq = w >> 2;             // 8 query columns per warp
     const int row = qd * 32 + lane, gkey = j0 + row;
     const uint32_t lb = (uint32_t)(qd * 32) << 16;
+    const float sl2 = scale * B5_LOG2E;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
-    float a[8], b[8], c[8], x[8], y[8], z[8];
+    const uint32_t tb = tmem_base + lb;
+    float a[8], b[8], c[8], x[8];
     for (int t = 0; t < n_tiles; ++t) {
       const int i0 = t * 32 + cq * 8;
       float lse_c[8], dl_c[8];
+      // queries past the chunk: lse = +huge makes the probability (hence P~ and dS) exactly zero
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        lse_c[e] = (i0 + e < m) ? __ldg(lse + base + i0 + e) : 0.f;
+        lse_c[e] = (i0 + e < m) ? __ldg(lse + base + i0 + e) * B5_LOG2E : 1e30f;
         dl_c[e] = (i0 + e < m) ? __ldg(delta + base + i0 + e) : 0.f;
       }
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
-      const uint32_t tb = tmem_base + lb;
       b5_ld8(tb + cq * 8, a);
       b5_ld8(tb + 32 + cq * 8, b);
       b5_ld8(tb + 64 + cq * 8, c);
       b5_ld8(tb + 96 + cq * 8, x);
-      b5_ld8(tb + 128 + cq * 8, y);
-      b5_ld8(tb + 160 + cq * 8, z);
       b5_ld_wait();
-      // the operand-slot columns written below are columns this same warp just read (no cross-warp hazard)
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(sp_free));
       uint32_t ph_[8], pl_[8], sh_[8], sl_[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float pt = 0.f, ds = 0.f;
-        if (gkey < m && i0 + e < m) {
-          const float p = expf((a[e] + b[e] + c[e]) * scale - lse_c[e]);
-          float keep = 1.f;
-          if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, i0 + e, gkey) >= drop_thr) ? inv_keep : 0.f;
-          pt = p * keep;
-          ds = p * ((x[e] + y[e] + z[e]) * keep - dl_c[e]);
-        }
-        b5_split(pt, ph_[e], pl_[e]);
-        b5_split(ds, sh_[e], sl_[e]);
+        const float p = b5_ex2((a[e] + b[e] + c[e]) * sl2 - lse_c[e]);
+        float keep = 1.f;
+        if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, i0 + e, gkey) >= drop_thr) ? inv_keep : 0.f;
+        b5_split(p * keep, ph_[e], pl_[e]);
+        b5_split(p * (x[e] * keep - dl_c[e]), sh_[e], sl_[e]);
       }
-      b5_st8(tb + 0 + cq * 8, ph_);
-      b5_st8(tb + 32 + cq * 8, pl_);
-      b5_st8(tb + 64 + cq * 8, sh_);
-      b5_st8(tb + 96 + cq * 8, sl_);
+      if (t > 0) mbar_wait(smem_u32(acc_done), (uint32_t)((t - 1) & 1));
+      tcgen05_fence_after();
+      b5_st8(tb + 128 + cq * 8, ph_);
+      b5_st8(tb + 160 + cq * 8, pl_);
+      b5_st8(tb + 192 + cq * 8, sh_);
+      b5_st8(tb + 224 + cq * 8, sl_);
       b5_st_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(op_full));
@@ -483,8 +523,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
     float o0[16], o1[16];
-    b5_ld16(tmem_base + lb + 256 + cq * 16, o0);
-    b5_ld16(tmem_base + lb + 320 + cq * 16, o1);
+    b5_ld16(tb + 256 + cq * 16, o0);
+    b5_ld16(tb + 320 + cq * 16, o1);
     b5_ld_wait();
     if (gkey < m) {
       float4* dst = reinterpret_cast<float4*>(dv + (base + gkey) * 64 + cq * 16);
@@ -493,8 +533,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         dst[e4] = make_float4(o0[4 * e4] + o1[4 * e4], o0[4 * e4 + 1] + o1[4 * e4 + 1], o0[4 * e4 + 2] + o1[4 * e4 + 2],
                               o0[4 * e4 + 3] + o1[4 * e4 + 3]);
     }
-    b5_ld16(tmem_base + lb + 384 + cq * 16, o0);
-    b5_ld16(tmem_base + lb + 448 + cq * 16, o1);
+    b5_ld16(tb + 384 + cq * 16, o0);
+    b5_ld16(tb + 448 + cq * 16, o1);
     b5_ld_wait();
     if (gkey < m) {
       float4* dst = reinterpret_cast<float4*>(dk + (base + gkey) * 64 + cq * 16);
