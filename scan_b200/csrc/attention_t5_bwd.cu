@@ -209,7 +209,15 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         for (int kb = 0; kb < 2; ++kb)
           for (int part = 0; part < 2; ++part)
             tma_load_2d(smem_u32(v_s + (kb * 2 + part) * B5_BOX64), &map_v, smem_u32(v_full), part * 64 + kb * 32, (int)(base + j0));
-        mbar_wait(smem_u32(kt_empty), ph ^ 1);
+      }
+    }
+  } else if (warp == 3) {
+    // K^T planes have their own producer: their slot frees only when the dQ MMAs retire, which must not hold back the
+    // K/V prefetch for the next S/dP
+    if (lane == 0) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * 64;
+        mbar_wait(smem_u32(kt_empty), (uint32_t)(t & 1) ^ 1);
         mbar_expect_tx(smem_u32(kt_full), 4 * B5_BOX64);
         for (int kb = 0; kb < 2; ++kb)
           for (int part = 0; part < 2; ++part)
@@ -338,11 +346,12 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------- dK, dV
-// smem: K hi/lo (4 x 16 KB) | V hi/lo (4 x 16 KB) | Q stage 16 KB | dO stage 16 KB | dO^T stage 16 KB | Q^T stage 16 KB
+// smem: K hi/lo (4 x 16 KB) | V hi/lo (4 x 16 KB) | 2 stages of (Q 16 KB + dO 16 KB) | dO^T stage 16 KB | Q^T stage 16 KB
 // TMEM: S^T [0,96) (wide)   dP^T [96,128) (three MMAs)   operand slots P~^T hi [128,160) lo [160,192), dS^T hi [192,224)
 //       lo [224,256)   dV accumulator [256,384)   dK accumulator [384,512)
 // Same register-buffered pipeline as the dQ kernel.
-constexpr int DKV_SMEM = 1024 + 8 * B5_BOX128 + 4 * 4 * B5_BOX32 + 1024;
+constexpr int DKV_QSTAGE = 8 * B5_BOX32;   // Q tile (16 KB) + dO tile (16 KB); two stages
+constexpr int DKV_SMEM = 1024 + 8 * B5_BOX128 + 2 * DKV_QSTAGE + 8 * B5_BOX32 + 1024;
 
 __global__ void __launch_bounds__(B5_THREADS, 1)
     attn_bwd_dkv_t5_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -354,22 +363,21 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* k_s = smem;
   uint8_t* v_s = k_s + 4 * B5_BOX128;
-  uint8_t* q_s = v_s + 4 * B5_BOX128;      // [kb][hi 4 KB | lo 4 KB]
-  uint8_t* do_s = q_s + 4 * B5_BOX32;
-  uint8_t* dot_s = do_s + 4 * B5_BOX32;    // [hi d 0..63 (8 KB) | lo (8 KB)] x 32 queries
+  uint8_t* q_s = v_s + 4 * B5_BOX128;      // stage s at q_s + s*DKV_QSTAGE: Q [kb][hi 4 KB | lo 4 KB], then dO likewise
+  uint8_t* dot_s = q_s + 2 * DKV_QSTAGE;   // [hi d 0..63 (8 KB) | lo (8 KB)] x 32 queries
   uint8_t* qt_s = dot_s + 4 * B5_BOX32;
   uint64_t* bars = (uint64_t*)(qt_s + 4 * B5_BOX32);
   uint64_t* r_full = bars;
-  uint64_t* q_full = bars + 1;
-  uint64_t* q_empty = bars + 2;    // Q and dO row tiles (S-type operands)
-  uint64_t* t_full = bars + 3;
-  uint64_t* t_empty = bars + 4;    // dO^T and Q^T planes (accumulation operands)
-  uint64_t* sp_full = bars + 5;
-  uint64_t* sp_free = bars + 6;    // 512 arrivals
-  uint64_t* op_full = bars + 7;    // 512 arrivals
-  uint64_t* acc_done = bars + 8;
-  uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+  uint64_t* q_full = bars + 1;     // [2]  Q and dO row tiles (S-type operands)
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* t_full = bars + 5;
+  uint64_t* t_empty = bars + 6;    // dO^T and Q^T planes (accumulation operands)
+  uint64_t* sp_full = bars + 7;
+  uint64_t* sp_free = bars + 8;    // 512 arrivals
+  uint64_t* op_full = bars + 9;    // 512 arrivals
+  uint64_t* acc_done = bars + 10;
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const int n_tiles = (m + 31) / 32;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 10; ++i) mbar_init(smem_u32(bars + i), (i == 6 || i == 7) ? B5_EW : 1);
+    for (int i = 0; i < 12; ++i) mbar_init(smem_u32(bars + i), (i == 8 || i == 9) ? B5_EW : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -400,16 +408,23 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           tma_load_2d(smem_u32(v_s + (part * 2 + kb) * B5_BOX128), &map_v, smem_u32(r_full), part * 64 + kb * 32, (int)(base + j0));
         }
       for (int t = 0; t < n_tiles; ++t) {
-        const int i0 = t * 32;
-        const uint32_t ph = (uint32_t)(t & 1);
-        mbar_wait(smem_u32(q_empty), ph ^ 1);
-        mbar_expect_tx(smem_u32(q_full), 8 * B5_BOX32);
+        const int i0 = t * 32, st = t & 1;
+        uint8_t* qs = q_s + st * DKV_QSTAGE;
+        mbar_wait(smem_u32(q_empty + st), (uint32_t)((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(smem_u32(q_full + st), 8 * B5_BOX32);
         for (int kb = 0; kb < 2; ++kb)
           for (int part = 0; part < 2; ++part) {
-            tma_load_2d(smem_u32(q_s + (kb * 2 + part) * B5_BOX32), &map_q, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
-            tma_load_2d(smem_u32(do_s + (kb * 2 + part) * B5_BOX32), &map_do, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
+            tma_load_2d(smem_u32(qs + (kb * 2 + part) * B5_BOX32), &map_q, smem_u32(q_full + st), part * 64 + kb * 32, (int)(base + i0));
+            tma_load_2d(smem_u32(qs + (4 + kb * 2 + part) * B5_BOX32), &map_do, smem_u32(q_full + st), part * 64 + kb * 32,
+                        (int)(base + i0));
           }
-        mbar_wait(smem_u32(t_empty), ph ^ 1);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const int i0 = t * 32;
+        mbar_wait(smem_u32(t_empty), (uint32_t)(t & 1) ^ 1);
         mbar_expect_tx(smem_u32(t_full), 4 * B5_BOX64);
         for (int part = 0; part < 2; ++part) {
           tma_load_2d(smem_u32(dot_s + part * B5_BOX64), &map_dot, smem_u32(t_full), i0, chunk * 128 + part * 64);
@@ -421,10 +436,12 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     if (lane == 0) {
       mbar_wait(smem_u32(r_full), 0);
       tcgen05_fence_after();
-      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s), qa = smem_u32(q_s), da = smem_u32(do_s);
+      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
       const uint32_t dota = smem_u32(dot_s), qta = smem_u32(qt_s);
       auto issue_sdp = [&](int t) {
-        mbar_wait(smem_u32(q_full), (uint32_t)(t & 1));
+        const int st = t & 1;
+        const uint32_t qa = smem_u32(q_s + st * DKV_QSTAGE), da = qa + 4 * B5_BOX32;
+        mbar_wait(smem_u32(q_full + st), (uint32_t)((t >> 1) & 1));
         tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
@@ -444,7 +461,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
             b5_mma_ss(tmem_base + 96, avh, bdl, B5_ID32, 1);      // dP^T: V_hi . dO_lo
             b5_mma_ss(tmem_base + 96, avl, bdh, B5_ID32, 1);      // dP^T: V_lo . dO_hi
           }
-        umma_commit(smem_u32(q_empty));
+        umma_commit(smem_u32(q_empty + st));
         umma_commit(smem_u32(sp_full));
       };
       for (int tt = 0; tt <= n_tiles; ++tt) {
