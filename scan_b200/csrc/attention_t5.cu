@@ -14,6 +14,8 @@
 // transposed V^T planes [chunk][hi d 0..63 | lo d 0..63][Mp] (keys contiguous), all loaded by TMA (128-byte swizzle).
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..19 softmax (lane quarter = w % 4, 16-key block = w / 4):
 // four softmax warps per scheduler hide the TMEM / MUFU / ALU latencies (one or two per scheduler run at IPC ~0.1).
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace scan {
@@ -36,13 +38,13 @@ constexpr uint32_t T5_IDESC_N64 = umma_idesc_tf32(T5_BQ, 64);
 
 
 __device__ __forceinline__ void t5_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
+  if (elect_one_sync()) asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void t5_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
+  if (elect_one_sync()) asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
@@ -79,7 +81,15 @@ __device__ __forceinline__ void t5_st16(uint32_t taddr, const uint32_t (&r)[16])
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void t5_commit(uint32_t bar) {
+  if (elect_one_sync()) umma_commit(bar);
+}
 __device__ __forceinline__ void t5_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float t5_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void t5_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------- forward
+template <bool DROP>
 __global__ void __launch_bounds__(T5_THREADS, 1)
     attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, int m, float scale, float drop_p, uint64_t seed,
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
   float* stat_m = (float*)(bars + 18);      // [4][128] per-column-block running max
   float* stat_l = stat_m + 512;             // [4][128] per-column-block running sum
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
   const long long base = (long long)chunk * m;   // first sub-token row of the chunk
   const int i0 = blockIdx.x * T5_BQ;
@@ -201,8 +212,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       for (int part = 0; part < 2; ++part)      // hi, lo
         for (int kb = 0; kb < 2; ++kb)
           tma_load_2d(smem_u32(q_s + (part * 2 + kb) * T5_QBOX), &map_q, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
+      int ks = 0;
+      uint32_t kph = 0;
       for (int pass = 0; pass < 2; ++pass) {
         for (int t = 0; t < n_tiles; ++t) {
           const int j0 = t * T5_BK;
@@ -213,21 +224,28 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
               tma_load_2d(smem_u32(k_s + ks * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_k, smem_u32(k_full + ks), part * 64 + kb * 32,
                           (int)(base + j0));
           if (++ks == 2) { ks = 0; kph ^= 1; }
-          if (pass == 1) {
-            mbar_wait(smem_u32(v_empty + vs), vph ^ 1);
-            mbar_expect_tx(smem_u32(v_full + vs), T5_STAGE);
-            for (int kb = 0; kb < 2; ++kb)
-              for (int part = 0; part < 2; ++part)
-                tma_load_2d(smem_u32(v_s + vs * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_v, smem_u32(v_full + vs), j0 + kb * 32,
-                            chunk * 128 + part * 64);
-            if (++vs == 2) { vs = 0; vph ^= 1; }
-          }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 3) {
+    // ===== second TMA producer: V^T planes (pass 2 only), independent of the K ring =====
     if (lane == 0) {
+      int vs = 0;
+      uint32_t vph = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * T5_BK;
+        mbar_wait(smem_u32(v_empty + vs), vph ^ 1);
+        mbar_expect_tx(smem_u32(v_full + vs), T5_STAGE);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part)
+            tma_load_2d(smem_u32(v_s + vs * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_v, smem_u32(v_full + vs), j0 + kb * 32,
+                        chunk * 128 + part * 64);
+        if (++vs == 2) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: all 32 lanes run the loop, each tcgen05 instruction is issued by one elected lane =====
+    {
       mbar_wait(smem_u32(q_full), 0);
       tcgen05_fence_after();
       const uint32_t q_addr = smem_u32(q_s);
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
             t5_mma_ss(tmem_base + s_col, umma_desc_sw128(q_addr + kb * T5_QBOX + k * 32), b, T5_IDESC_N128, (kb | k) != 0);
             t5_mma_ss(tmem_base + s_col + 128, umma_desc_sw128(q_addr + (2 + kb) * T5_QBOX + k * 32), b, T5_IDESC_N64, (kb | k) != 0);
           }
-        umma_commit(smem_u32(k_empty + ks));
+        t5_commit(smem_u32(k_empty + ks));
         if (++ks == 2) { ks = 0; kph ^= 1; }
       };
       // ---- pass 1: S double-buffered at columns 0 / 192
@@ -258,7 +276,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
           se_ph[buf] ^= 1;
           tcgen05_fence_after();
           issue_s(buf * T5_S_COLS);
-          umma_commit(smem_u32(s_full + buf));
+          t5_commit(smem_u32(s_full + buf));
         }
       }
       // ---- pass 2: single S buffer (columns 0..191), P slot, O accumulators
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
             se0 ^= 1;
             tcgen05_fence_after();
             issue_s(0);
-            umma_commit(smem_u32(s_full + 0));
+            t5_commit(smem_u32(s_full + 0));
           }
           if (t > 0) {  // O += P(t-1) . V(t-1)
             mbar_wait(smem_u32(p_full), pf);
@@ -294,14 +312,15 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
                 t5_mma_ts(tmem_base + T5_O_COL0, tmem_base + T5_P_COL0 + kb * 32 + k * 8, b, T5_IDESC_N128, acc);
                 t5_mma_ts(tmem_base + T5_O_COL0 + 128, tmem_base + T5_P_COL0 + 64 + kb * 32 + k * 8, b, T5_IDESC_N64, acc);
               }
-            umma_commit(smem_u32(v_empty + vs));
-            umma_commit(smem_u32(p_empty));
+            t5_commit(smem_u32(v_empty + vs));
+            t5_commit(smem_u32(p_empty));
             if (++vs == 2) { vs = 0; vph ^= 1; }
           }
         }
-        umma_commit(smem_u32(o_full));
+        t5_commit(smem_u32(o_full));
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===== softmax / epilogue warps: thread = query row (TMEM lane), 16-column block cq of the 64 key columns =====
     const int w = warp - 4;
@@ -309,11 +328,14 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
     const int row = qd * 32 + lane;                 // row inside the tile
     const int grow = i0 + row;                      // row inside the chunk
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    // everything in the log2 domain: s2 = S * scale * log2(e), p = 2^(s2 - lse2)
+    const float sl2 = scale * 1.4426950408889634f;
     float mrun = -INFINITY, lrun = 0.f;
     uint32_t sf_ph[2] = {0, 0};
     float a[16], b[16], c[16];
-    // ---- pass 1: statistics
-    for (int t = 0; t < n_tiles; ++t) {
+    // ---- pass 1: statistics.  LAST: only the final key tile can hold keys past the chunk.
+    auto stat_tile = [&](int t, auto last_c) {
+      constexpr bool LAST = decltype(last_c)::value;
       const int buf = t & 1;
       mbar_wait(smem_u32(s_full + buf), sf_ph[buf]);
       sf_ph[buf] ^= 1;
@@ -325,27 +347,30 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       t5_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(s_empty + buf));
-      const int j0 = t * T5_BK + cq * 16;
+      const int lim = m - (t * T5_BK + cq * 16);
       float mx = -INFINITY;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        a[e] = (j0 + e < m) ? (a[e] + b[e] + c[e]) * scale : -INFINITY;
+        a[e] = (a[e] + b[e] + c[e]) * sl2;
+        if (LAST) a[e] = e < lim ? a[e] : -INFINITY;
         mx = fmaxf(mx, a[e]);
       }
       const float mnew = fmaxf(mrun, mx);
-      if (mnew != -INFINITY) {
+      if (mnew != -INFINITY) {   // ex2(-inf) = 0 takes care of masked entries and of the first tile (mrun = -inf)
         float sum = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) sum += (a[e] == -INFINITY) ? 0.f : __expf(a[e] - mnew);
-        lrun = lrun * ((mrun == -INFINITY) ? 0.f : __expf(mrun - mnew)) + sum;
+        for (int e = 0; e < 16; ++e) sum += t5_ex2(a[e] - mnew);
+        lrun = lrun * t5_ex2(mrun - mnew) + sum;
         mrun = mnew;
       }
-    }
-    // combine the four column blocks -> lse per row
+    };
+    for (int t = 0; t + 1 < n_tiles; ++t) stat_tile(t, std::false_type{});
+    stat_tile(n_tiles - 1, std::true_type{});
+    // combine the four column blocks -> log-sum-exp per row
     stat_m[cq * 128 + row] = mrun;
     stat_l[cq * 128 + row] = lrun;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * T5_SM_WARPS) : "memory");
-    float lse_row;
+    float lse2_row;
     {
       float mm = -INFINITY;
 #pragma unroll
@@ -354,16 +379,18 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const float mx_ = stat_m[x * 128 + row];
-        if (mx_ != -INFINITY) ll += stat_l[x * 128 + row] * expf(mx_ - mm);
+        if (mx_ != -INFINITY) ll += stat_l[x * 128 + row] * exp2f(mx_ - mm);
       }
-      lse_row = mm + logf(ll);
+      lse2_row = mm + log2f(ll);
     }
-    if (cq == 0 && grow < m) lse[base + grow] = lse_row;
-    // ---- pass 2: P = exp(S*scale - lse), dropout, hi/lo -> TMEM operand slot
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    if (cq == 0 && grow < m) lse[base + grow] = lse2_row * 0.6931471805599453f;
+    // ---- pass 2: P = 2^(s2 - lse2), dropout, hi/lo -> TMEM operand slot
+    const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = DROP ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const uint32_t hrow = attn_drop_pre(seed, chunk) ^ ((uint32_t)grow * ATTN_DROP_CI);
     uint32_t sf0 = sf_ph[0], pe = 0;
-    for (int t = 0; t < n_tiles; ++t) {
+    auto prob_tile = [&](int t, auto last_c) {
+      constexpr bool LAST = decltype(last_c)::value;
       mbar_wait(smem_u32(s_full + 0), sf0);
       sf0 ^= 1;
       tcgen05_fence_after();
@@ -375,14 +402,14 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       tcgen05_fence_before();
       mbar_arrive(smem_u32(s_empty + 0));
       const int j0 = t * T5_BK + cq * 16;
+      const int lim = m - j0;
+      const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        float p = 0.f;
-        if (j0 + e < m) {
-          p = expf((a[e] + b[e] + c[e]) * scale - lse_row);
-          if (drop_p > 0.f) p = (attn_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? p * inv_keep : 0.f;
-        }
+        float p = t5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse2_row));
+        if (DROP) p = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? p * inv_keep : 0.f;
+        if (LAST) p = e < lim ? p : 0.f;
         uint32_t u;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(p));
         hi[e] = u;
@@ -398,7 +425,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       mbar_arrive(smem_u32(p_full));
-    }
+    };
+    for (int t = 0; t + 1 < n_tiles; ++t) prob_tile(t, std::false_type{});
+    prob_tile(n_tiles - 1, std::true_type{});
     // ---- epilogue: O = Oa[0..63] + Oa[64..127] + Ob, 16 of the 64 d columns per warp
     mbar_wait(smem_u32(o_full), 0);
     tcgen05_fence_after();
@@ -446,11 +475,15 @@ int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, fl
   rc = make_rowmajor_map(&mv, vt, 4ull * 128, (uint64_t)mp, 64);
   if (rc) return rc;
   if (!g_t5_attr) {
-    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
     g_t5_attr = 1;
   }
   dim3 grid((m + T5_BQ - 1) / T5_BQ, 4);
-  attn_fwd_t5_kernel<<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse);
+  if (drop_p > 0.f)
+    attn_fwd_t5_kernel<true><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse);
+  else
+    attn_fwd_t5_kernel<false><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse);
   SCAN_LAUNCH_CHECK("attn_fwd_t5_kernel");
   return SCAN_OK;
 }

@@ -6,6 +6,8 @@
 //        S^T = K Q^T, dP^T = V dO^T -> P~^T, dS^T -> hi/lo to TMEM -> dV += P~^T dO, dK += dS^T Q (B = dO^T / Q^T planes)
 // Every product is 3xTF32 with the "hi x (hi | lo)" pair fused into one wide-N MMA.  No atomics: dQ, dK, dV are each
 // written once.  Operand planes come from attn_bwd_prep_kernel.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace scan {
@@ -20,13 +22,13 @@ constexpr uint32_t B5_ID64 = umma_idesc_tf32(128, 64);
 constexpr uint32_t B5_ID32 = umma_idesc_tf32(128, 32);
 
 __device__ __forceinline__ void b5_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
+  if (elect_one_sync()) asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void b5_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
+  if (elect_one_sync()) asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
@@ -63,6 +65,9 @@ __device__ __forceinline__ void b5_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void b5_commit(uint32_t bar) {
+  if (elect_one_sync()) umma_commit(bar);
+}
 __device__ __forceinline__ void b5_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void b5_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void b5_split(float x, uint32_t& hi, uint32_t& lo) {
@@ -79,6 +84,8 @@ struct PrepArgs {
   const float* t_src[3];
   float* t_dst[3];
   int n_rows, n_t;
+  const float *lse, *delta;   // [4M]
+  float *lse2p, *dlp;         // [4][Mp]: lse * log2(e) padded with +huge (probability 0), delta padded with 0
 };
 
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(PrepArgs a, int m, int mp) {
@@ -99,6 +106,11 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(PrepArgs a, int m, i
       reinterpret_cast<float4*>(dst)[c4] = h;
       reinterpret_cast<float4*>(dst + 64)[c4] = l;
     }
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 4ll * mp; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i / mp), r = (int)(i % mp);
+    a.lse2p[i] = r < m ? __ldg(a.lse + (long long)chunk * m + r) * 1.4426950408889634f : 1e30f;
+    a.dlp[i] = r < m ? __ldg(a.delta + (long long)chunk * m + r) : 0.f;
   }
   const int tiles_per_chunk = mp / 32;
   for (int tile = blockIdx.x; tile < a.n_t * 4 * tiles_per_chunk; tile += gridDim.x) {
@@ -141,6 +153,7 @@ __device__ __forceinline__ float b5_ex2(float x) {
   return y;
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(B5_THREADS, 1)
     attn_bwd_dq_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                           const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint64_t* acc_full = bars + 11;
   uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
   const long long base = (long long)chunk * m;
   const int i0 = blockIdx.x * 128;
@@ -204,7 +217,13 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         for (int kb = 0; kb < 2; ++kb)
           for (int part = 0; part < 2; ++part)
             tma_load_2d(smem_u32(k_s + (kb * 2 + part) * B5_BOX64), &map_k, smem_u32(k_full), part * 64 + kb * 32, (int)(base + j0));
-        mbar_wait(smem_u32(v_empty), ph ^ 1);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * 64;
+        mbar_wait(smem_u32(v_empty), (uint32_t)(t & 1) ^ 1);
         mbar_expect_tx(smem_u32(v_full), 4 * B5_BOX64);
         for (int kb = 0; kb < 2; ++kb)
           for (int part = 0; part < 2; ++part)
@@ -225,14 +244,15 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes run the issue loop; each tcgen05 instruction is issued by one elected lane
       mbar_wait(smem_u32(r_full), 0);
       tcgen05_fence_after();
       const uint32_t qa = smem_u32(q_s), da = smem_u32(do_s), ka = smem_u32(k_s), va = smem_u32(v_s), kta = smem_u32(kt_s);
+      // S first, then dP: the K stage frees a whole dP-phase earlier, so the (single-stage) K and V loads of the next tile
+      // hide behind the dP MMAs and the dQ MMAs respectively
       auto issue_sdp = [&](int t) {
         const uint32_t ph = (uint32_t)(t & 1);
         mbar_wait(smem_u32(k_full), ph);
-        mbar_wait(smem_u32(v_full), ph);
         tcgen05_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
@@ -240,21 +260,27 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0;
             const uint64_t bk = umma_desc_sw128(ka + kb * 2 * B5_BOX64 + k * 32);
+            b5_mma_ss(tmem_base + 0, umma_desc_sw128(qa + kb * B5_BOX128 + k * 32), bk, B5_ID128, acc);         // Q_hi . [K_hi ; K_lo]
+            b5_mma_ss(tmem_base + 128, umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32), bk, B5_ID64, acc);   // Q_lo . K_hi
+          }
+        b5_commit(smem_u32(k_empty));
+        mbar_wait(smem_u32(v_full), ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb | k) != 0;
             const uint64_t bvh = umma_desc_sw128(va + kb * 2 * B5_BOX64 + k * 32);
             const uint64_t bvl = umma_desc_sw128(va + (kb * 2 + 1) * B5_BOX64 + k * 32);
-            const uint64_t aqh = umma_desc_sw128(qa + kb * B5_BOX128 + k * 32);
-            const uint64_t aql = umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32);
             const uint64_t adh = umma_desc_sw128(da + kb * B5_BOX128 + k * 32);
             const uint64_t adl = umma_desc_sw128(da + (2 + kb) * B5_BOX128 + k * 32);
-            b5_mma_ss(tmem_base + 0, aqh, bk, B5_ID128, acc);     // S: Q_hi . [K_hi ; K_lo]
-            b5_mma_ss(tmem_base + 192, adh, bvh, B5_ID64, acc);   // dP: dO_hi . V_hi
-            b5_mma_ss(tmem_base + 128, aql, bk, B5_ID64, acc);    // S: Q_lo . K_hi
-            b5_mma_ss(tmem_base + 192, adh, bvl, B5_ID64, 1);     // dP: dO_hi . V_lo
-            b5_mma_ss(tmem_base + 192, adl, bvh, B5_ID64, 1);     // dP: dO_lo . V_hi
+            b5_mma_ss(tmem_base + 192, adh, bvh, B5_ID64, acc);   // dO_hi . V_hi
+            b5_mma_ss(tmem_base + 192, adh, bvl, B5_ID64, 1);     // dO_hi . V_lo
+            b5_mma_ss(tmem_base + 192, adl, bvh, B5_ID64, 1);     // dO_lo . V_hi
           }
-        umma_commit(smem_u32(k_empty));
-        umma_commit(smem_u32(v_empty));
-        umma_commit(smem_u32(sp_full));
+        b5_commit(smem_u32(v_empty));
+        b5_commit(smem_u32(sp_full));
       };
       for (int tt = 0; tt <= n_tiles; ++tt) {
         if (tt < n_tiles) {
@@ -276,11 +302,12 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
             b5_mma_ts(tmem_base + 384, tmem_base + 256 + kb * 32 + k * 8, b, B5_ID128, acc);   // dS_hi . [Kt_hi ; Kt_lo]
             b5_mma_ts(tmem_base + 384, tmem_base + 320 + kb * 32 + k * 8, b, B5_ID64, 1);      // dS_lo . Kt_hi
           }
-        umma_commit(smem_u32(kt_empty));
-        umma_commit(smem_u32(dq_done));
+        b5_commit(smem_u32(kt_empty));
+        b5_commit(smem_u32(dq_done));
       }
-      umma_commit(smem_u32(acc_full));
+      b5_commit(smem_u32(acc_full));
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int w = warp - 4;
     const int qd = w & 3, cq = w >> 2;
@@ -290,11 +317,14 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const float lse2 = grow < m ? __ldg(lse + base + grow) * B5_LOG2E : 1e30f;
     const float dl_r = grow < m ? __ldg(delta + base + grow) : 0.f;
     const float sl2 = scale * B5_LOG2E;
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = DROP ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const uint32_t hrow = attn_drop_pre(seed, chunk) ^ ((uint32_t)grow * ATTN_DROP_CI);
     const uint32_t tb = tmem_base + lb;
     float a[16], b[16], c[16], x[16];
-    for (int t = 0; t < n_tiles; ++t) {
+    // LAST: only the final key tile can hold keys past the chunk
+    auto ew_tile = [&](int t, auto last_c) {
+      constexpr bool LAST = decltype(last_c)::value;
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
       b5_ld16(tb + cq * 16, a);
@@ -305,15 +335,16 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       tcgen05_fence_before();
       mbar_arrive(smem_u32(sp_free));
       const int j0 = t * 64 + cq * 16;
-      const int lim = m - j0;          // keys j0+e with e >= lim are past the chunk
+      const int lim = m - j0;
+      const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float p = b5_ex2((a[e] + b[e] + c[e]) * sl2 - lse2);
+        const float p = b5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse2));
         float dp = x[e];
-        if (drop_p > 0.f) dp = (attn_drop_hash(seed, chunk, grow, j0 + e) >= drop_thr) ? dp * inv_keep : 0.f;
+        if (DROP) dp = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? dp * inv_keep : 0.f;
         float ds = p * (dp - dl_r);
-        ds = e < lim ? ds : 0.f;
+        if (LAST) ds = e < lim ? ds : 0.f;
         b5_split(ds, hi[e], lo[e]);
       }
       if (t > 0) mbar_wait(smem_u32(dq_done), (uint32_t)((t - 1) & 1));
@@ -323,7 +354,9 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       b5_st_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(ds_full));
-    }
+    };
+    for (int t = 0; t + 1 < n_tiles; ++t) ew_tile(t, std::false_type{});
+    ew_tile(n_tiles - 1, std::true_type{});
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
     b5_ld16(tb + 384 + cq * 16, a);
@@ -353,12 +386,13 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 constexpr int DKV_QSTAGE = 8 * B5_BOX32;   // Q tile (16 KB) + dO tile (16 KB); two stages
 constexpr int DKV_SMEM = 1024 + 8 * B5_BOX128 + 2 * DKV_QSTAGE + 8 * B5_BOX32 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(B5_THREADS, 1)
     attn_bwd_dkv_t5_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                            const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                            const __grid_constant__ CUtensorMap map_dot, const __grid_constant__ CUtensorMap map_qt,
-                           const float* __restrict__ lse, const float* __restrict__ delta, int m, float scale, float drop_p,
-                           uint64_t seed, float* __restrict__ dk, float* __restrict__ dv) {
+                           const float* __restrict__ lse2p, const float* __restrict__ dlp, int m, int mp, float scale,
+                           float drop_p, uint64_t seed, float* __restrict__ dk, float* __restrict__ dv) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* k_s = smem;
@@ -379,7 +413,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint64_t* acc_full = bars + 11;
   uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
   const long long base = (long long)chunk * m;
   const int j0 = blockIdx.x * 128;            // first key of this CTA
@@ -433,7 +467,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes run the issue loop; each tcgen05 instruction is issued by one elected lane
       mbar_wait(smem_u32(r_full), 0);
       tcgen05_fence_after();
       const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
@@ -461,8 +495,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
             b5_mma_ss(tmem_base + 96, avh, bdl, B5_ID32, 1);      // dP^T: V_hi . dO_lo
             b5_mma_ss(tmem_base + 96, avl, bdh, B5_ID32, 1);      // dP^T: V_lo . dO_hi
           }
-        umma_commit(smem_u32(q_empty + st));
-        umma_commit(smem_u32(sp_full));
+        b5_commit(smem_u32(q_empty + st));
+        b5_commit(smem_u32(sp_full));
       };
       for (int tt = 0; tt <= n_tiles; ++tt) {
         if (tt < n_tiles) {
@@ -485,30 +519,31 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           b5_mma_ts(tmem_base + 256, tmem_base + 160 + k * 8, bdo, B5_ID64, 1);      // dV += P~^T_lo . dO^T_hi
           b5_mma_ts(tmem_base + 384, tmem_base + 224 + k * 8, bq, B5_ID64, 1);       // dK += dS^T_lo . Q^T_hi
         }
-        umma_commit(smem_u32(t_empty));
-        umma_commit(smem_u32(acc_done));
+        b5_commit(smem_u32(t_empty));
+        b5_commit(smem_u32(acc_done));
       }
-      umma_commit(smem_u32(acc_full));
+      b5_commit(smem_u32(acc_full));
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int w = warp - 4;
     const int qd = w & 3, cq = w >> 2;             // 8 query columns per warp
     const int row = qd * 32 + lane, gkey = j0 + row;
     const uint32_t lb = (uint32_t)(qd * 32) << 16;
     const float sl2 = scale * B5_LOG2E;
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t drop_thr = drop_p > 0.f ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = DROP ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const uint32_t hkey = attn_drop_pre(seed, chunk) ^ ((uint32_t)gkey * ATTN_DROP_CJ);
     const uint32_t tb = tmem_base + lb;
+    const float4* lse4 = reinterpret_cast<const float4*>(lse2p + (long long)chunk * mp) + cq * 2;
+    const float4* dl4 = reinterpret_cast<const float4*>(dlp + (long long)chunk * mp) + cq * 2;
     float a[8], b[8], c[8], x[8];
     for (int t = 0; t < n_tiles; ++t) {
-      const int i0 = t * 32 + cq * 8;
-      float lse_c[8], dl_c[8];
-      // queries past the chunk: lse = +huge makes the probability (hence P~ and dS) exactly zero
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        lse_c[e] = (i0 + e < m) ? __ldg(lse + base + i0 + e) * B5_LOG2E : 1e30f;
-        dl_c[e] = (i0 + e < m) ? __ldg(delta + base + i0 + e) : 0.f;
-      }
+      // per-query statistics of the 8 columns of this warp (padded rows: lse = +huge -> probability exactly 0)
+      const float4 l0 = __ldg(lse4 + t * 8), l1 = __ldg(lse4 + t * 8 + 1);
+      const float4 d0 = __ldg(dl4 + t * 8), d1 = __ldg(dl4 + t * 8 + 1);
+      const float lse_c[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+      const float dl_c[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
       b5_ld8(tb + cq * 8, a);
@@ -518,14 +553,19 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       b5_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(sp_free));
+      const uint32_t hq = (uint32_t)(t * 32 + cq * 8) * ATTN_DROP_CI;
       uint32_t ph_[8], pl_[8], sh_[8], sl_[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float p = b5_ex2((a[e] + b[e] + c[e]) * sl2 - lse_c[e]);
-        float keep = 1.f;
-        if (drop_p > 0.f) keep = (attn_drop_hash(seed, chunk, i0 + e, gkey) >= drop_thr) ? inv_keep : 0.f;
-        b5_split(p * keep, ph_[e], pl_[e]);
-        b5_split(p * (x[e] * keep - dl_c[e]), sh_[e], sl_[e]);
+        const float p = b5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse_c[e]));
+        float pt = p, dp = x[e];
+        if (DROP) {
+          const bool keep = attn_drop_mix(hkey ^ (hq + (uint32_t)e * ATTN_DROP_CI)) >= drop_thr;
+          pt = keep ? p * inv_keep : 0.f;
+          dp = keep ? dp * inv_keep : 0.f;
+        }
+        b5_split(pt, ph_[e], pl_[e]);
+        b5_split(p * (dp - dl_c[e]), sh_[e], sl_[e]);
       }
       if (t > 0) mbar_wait(smem_u32(acc_done), (uint32_t)((t - 1) & 1));
       tcgen05_fence_after();
@@ -574,7 +614,7 @@ static int g_b5_attr = 0;
 
 int64_t attn_t5_bwd_workspace_bytes(int m) {
   const long long mp = ((long long)m + 63) / 64 * 64;
-  return (4ll * (4ll * m * 128) + 3ll * (4ll * 128 * mp)) * 4 + 1024;
+  return (4ll * (4ll * m * 128) + 3ll * (4ll * 128 * mp) + 2ll * 4 * mp) * 4 + 1024;
 }
 
 int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
@@ -584,6 +624,7 @@ int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const flo
   float* w0 = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   float *q_hl = w0, *k_hl = w0 + hl, *v_hl = w0 + 2 * hl, *do_hl = w0 + 3 * hl;
   float *kt = w0 + 4 * hl, *dot = kt + pl, *qt = dot + pl;
+  float *lse2p = qt + pl, *dlp = lse2p + 4ll * mp;
   PrepArgs pa;
   pa.n_rows = 4;
   pa.rows_src[0] = q; pa.rows_src[1] = k; pa.rows_src[2] = v; pa.rows_src[3] = d_ctx;
@@ -591,6 +632,7 @@ int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const flo
   pa.n_t = 3;
   pa.t_src[0] = k; pa.t_src[1] = d_ctx; pa.t_src[2] = q;
   pa.t_dst[0] = kt; pa.t_dst[1] = dot; pa.t_dst[2] = qt;
+  pa.lse = lse; pa.delta = delta; pa.lse2p = lse2p; pa.dlp = dlp;
   attn_bwd_prep_kernel<<<4 * sm_count(), 256, 0, st>>>(pa, m, mp);
   SCAN_LAUNCH_CHECK("attn_bwd_prep_kernel");
   CUtensorMap mq128, mdo128, mk128, mv128, mk64, mv64, mq32, mdo32, mkt, mdot, mqt;
@@ -608,15 +650,24 @@ int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const flo
   rc |= make_rowmajor_map(&mqt, qt, 4ull * 128, (uint64_t)mp, 64);
   if (rc) return SCAN_ECUDA;
   if (!g_b5_attr) {
-    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     g_b5_attr = 1;
   }
   dim3 grid((m + 127) / 128, 4);
-  attn_bwd_dq_t5_kernel<<<grid, B5_THREADS, DQ_SMEM, st>>>(mq128, mdo128, mk64, mv64, mkt, lse, delta, m, scale, drop_p, seed, dq);
-  SCAN_LAUNCH_CHECK("attn_bwd_dq_t5_kernel");
-  attn_bwd_dkv_t5_kernel<<<grid, B5_THREADS, DKV_SMEM, st>>>(mk128, mv128, mq32, mdo32, mdot, mqt, lse, delta, m, scale, drop_p, seed,
-                                                            dk, dv);
+  if (drop_p > 0.f) {
+    attn_bwd_dq_t5_kernel<true><<<grid, B5_THREADS, DQ_SMEM, st>>>(mq128, mdo128, mk64, mv64, mkt, lse, delta, m, scale, drop_p, seed, dq);
+    SCAN_LAUNCH_CHECK("attn_bwd_dq_t5_kernel");
+    attn_bwd_dkv_t5_kernel<true><<<grid, B5_THREADS, DKV_SMEM, st>>>(mk128, mv128, mq32, mdo32, mdot, mqt, lse2p, dlp, m, mp, scale,
+                                                                    drop_p, seed, dk, dv);
+  } else {
+    attn_bwd_dq_t5_kernel<false><<<grid, B5_THREADS, DQ_SMEM, st>>>(mq128, mdo128, mk64, mv64, mkt, lse, delta, m, scale, drop_p, seed, dq);
+    SCAN_LAUNCH_CHECK("attn_bwd_dq_t5_kernel");
+    attn_bwd_dkv_t5_kernel<false><<<grid, B5_THREADS, DKV_SMEM, st>>>(mk128, mv128, mq32, mdo32, mdot, mqt, lse2p, dlp, m, mp, scale,
+                                                                     drop_p, seed, dk, dv);
+  }
   SCAN_LAUNCH_CHECK("attn_bwd_dkv_t5_kernel");
   return SCAN_OK;
 }

@@ -90,17 +90,25 @@ __device__ __forceinline__ float warp_max(float v) {
 static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
 // Counter-based Bernoulli source of the attention dropout mask: 32-bit hash of (seed, chunk, query, key).  All attention
-// kernels (forward and backward, every implementation) must use THIS function so that masks agree.  ~9 integer ops; the
-// row part is loop-invariant in every caller.
-__device__ __forceinline__ uint32_t attn_drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
-  uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (chunk * 0x85EBCA6Bu) ^ (i * 0xC2B2AE35u);
-  h ^= j * 0x27D4EB2Fu;
-  h ^= h >> 16;
+// kernels (forward and backward, every implementation) must produce THIS value so that masks agree.  Callers compare it
+// with a threshold, i.e. they consume the HIGH bits: multiply - xorshift - multiply leaves those depending on every
+// input bit, and a trailing xorshift (which only touches low bits) is omitted on purpose.
+//   h = mix(pre(seed, chunk) ^ i * ATTN_DROP_CI ^ j * ATTN_DROP_CJ)
+// The tensor-core kernels keep the loop-invariant part in a register and step the other by a constant add, which leaves
+// 6 integer ops per element.
+constexpr uint32_t ATTN_DROP_CI = 0xC2B2AE35u;
+constexpr uint32_t ATTN_DROP_CJ = 0x27D4EB2Fu;
+__device__ __forceinline__ uint32_t attn_drop_pre(uint64_t seed, uint32_t chunk) {
+  return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (chunk * 0x85EBCA6Bu);
+}
+__device__ __forceinline__ uint32_t attn_drop_mix(uint32_t h) {
   h *= 0x7FEB352Du;
   h ^= h >> 15;
   h *= 0x846CA68Bu;
-  h ^= h >> 16;
   return h;
+}
+__device__ __forceinline__ uint32_t attn_drop_hash(uint64_t seed, uint32_t chunk, uint32_t i, uint32_t j) {
+  return attn_drop_mix(attn_drop_pre(seed, chunk) ^ (i * ATTN_DROP_CI) ^ (j * ATTN_DROP_CJ));
 }
 
 }  // namespace scan

@@ -49,6 +49,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// one lane of a converged warp (CUTLASS' elect_one_sync): tcgen05.mma / commit issued under this predicate from
+// warp-uniform code compile to a single predicated UTCxMMA instead of the compiler's generic one-thread-at-a-time loop
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+// warp index the compiler can prove uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // K-major operand tile with 128-byte rows and the 128B swizzle: 8-row groups are 1024 B apart (SBO),
 // LBO unused for swizzled K-major layouts, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
