@@ -33,6 +33,10 @@ constexpr int T5_THREADS = 128 + 32 * T5_SM_WARPS;
 constexpr int T5_S_COLS = 192;            // Sa (hi.hi | hi.lo) 128 + Sb (lo.hi) 64
 constexpr int T5_P_COL0 = 192;            // P operand slot: hi 64 | lo 64
 constexpr int T5_O_COL0 = 320;            // Oa 128 + Ob 64
+// The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest: over the ~1100 accumulation steps
+// of a full-size O row that is a coherent 5e-5 relative error (measured, tools/diag_attn_precision.py).  O is therefore
+// drained every T5_FLUSH key tiles (64 steps) into the fp32 output row with ordinary round-to-nearest adds.
+constexpr int T5_FLUSH = 8;
 constexpr uint32_t T5_IDESC_N128 = umma_idesc_tf32(T5_BQ, 128);
 constexpr uint32_t T5_IDESC_N64 = umma_idesc_tf32(T5_BQ, 64);
 
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t b = umma_desc_sw128(vaddr + kb * 2 * T5_KBOX + k * 32);
-                const uint32_t acc = (t > 1 || kb || k) ? 1u : 0u;
+                const uint32_t acc = (((t - 1) % T5_FLUSH) | kb | k) != 0;   // restart after every drain
                 t5_mma_ts(tmem_base + T5_O_COL0, tmem_base + T5_P_COL0 + kb * 32 + k * 8, b, T5_IDESC_N128, acc);
                 t5_mma_ts(tmem_base + T5_O_COL0 + 128, tmem_base + T5_P_COL0 + 64 + kb * 32 + k * 8, b, T5_IDESC_N64, acc);
               }
@@ -383,14 +387,34 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       }
       lse2_row = mm + log2f(ll);
     }
-    if (cq == 0 && grow < m) lse[base + grow] = lse2_row * 0.6931471805599453f;
+    // The backward recomputes P from the STORED natural-log value: use exactly that value (same two roundings) here as well,
+    // otherwise every probability of a row differs from the backward's by a common factor ~1e-6, which the dP - D
+    // cancellation of the softmax gradient amplifies a thousandfold.
+    const float lse_nat = lse2_row * 0.6931471805599453f;
+    lse2_row = lse_nat * 1.4426950408889634f;
+    if (cq == 0 && grow < m) lse[base + grow] = lse_nat;
     // ---- pass 2: P = 2^(s2 - lse2), dropout, hi/lo -> TMEM operand slot
     const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
     const uint32_t drop_thr = DROP ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
     const uint32_t hrow = attn_drop_pre(seed, chunk) ^ ((uint32_t)grow * ATTN_DROP_CI);
     uint32_t sf0 = sf_ph[0], pe = 0;
+    // drain the O accumulator (Oa[0..63] + Oa[64..127] + Ob, 16 of the 64 d columns per warp) into the output row
+    auto drain_o = [&](bool first) {
+      tmem_drain16<3>(tmem_base + lane_base + T5_O_COL0 + cq * 16, ctx + (base + grow) * T5_D + cq * 16, 1.f, first, grow < m);
+    };
     auto prob_tile = [&](int t, auto last_c) {
       constexpr bool LAST = decltype(last_c)::value;
+      // Every T5_FLUSH tiles: tiles [t - T5_FLUSH, t) are complete in O once the P.V MMAs of tile t-1 have retired -> drain
+      // them now, while few registers are live.  The P.V MMAs of tile t restart the accumulator and are issued only after
+      // every softmax thread has arrived on p_full at the end of this tile, i.e. after this read.
+      const bool drain = t > 0 && t % T5_FLUSH == 0;
+      if (drain) {
+        mbar_wait(smem_u32(p_empty), pe);
+        pe ^= 1;
+        tcgen05_fence_after();
+        drain_o(t == T5_FLUSH);
+        tcgen05_fence_before();
+      }
       mbar_wait(smem_u32(s_full + 0), sf0);
       sf0 ^= 1;
       tcgen05_fence_after();
@@ -415,7 +439,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
         hi[e] = u;
         lo[e] = __float_as_uint(p - __uint_as_float(u));
       }
-      if (t > 0) {   // the previous P must have been consumed by its P.V MMAs
+      if (t > 0 && !drain) {   // the previous P must have been consumed by its P.V MMAs
         mbar_wait(smem_u32(p_empty), pe);
         pe ^= 1;
       }
@@ -428,21 +452,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
     };
     for (int t = 0; t + 1 < n_tiles; ++t) prob_tile(t, std::false_type{});
     prob_tile(n_tiles - 1, std::true_type{});
-    // ---- epilogue: O = Oa[0..63] + Oa[64..127] + Ob, 16 of the 64 d columns per warp
+    // ---- epilogue: the tiles since the last drain
     mbar_wait(smem_u32(o_full), 0);
     tcgen05_fence_after();
-    const uint32_t oc = tmem_base + lane_base + T5_O_COL0;
-    t5_ld16(oc + cq * 16, a);
-    t5_ld16(oc + 64 + cq * 16, b);
-    t5_ld16(oc + 128 + cq * 16, c);
-    t5_ld_wait();
-    if (grow < m) {
-      float4* dst = reinterpret_cast<float4*>(ctx + (base + grow) * T5_D + cq * 16);
-#pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4)
-        dst[e4] = make_float4(a[4 * e4] + b[4 * e4] + c[4 * e4], a[4 * e4 + 1] + b[4 * e4 + 1] + c[4 * e4 + 1],
-                              a[4 * e4 + 2] + b[4 * e4 + 2] + c[4 * e4 + 2], a[4 * e4 + 3] + b[4 * e4 + 3] + c[4 * e4 + 3]);
-    }
+    drain_o(n_tiles <= T5_FLUSH);
   }
   tcgen05_fence_before();
   __syncthreads();

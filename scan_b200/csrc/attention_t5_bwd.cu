@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(PrepArgs a, int m, i
 // pipe computes S/dP of tile t+1 while they work; dQ MMAs of tile t follow as soon as dS(t) is in the operand slot.
 constexpr int DQ_SMEM = 1024 + 8 * B5_BOX128 + 3 * 4 * B5_BOX64 + 1024;
 constexpr float B5_LOG2E = 1.4426950408889634f;
+// The tensor core adds into its fp32 accumulator with truncation: the gradient accumulators are drained into the fp32
+// output rows every 64 accumulation steps (see T5_FLUSH in attention_t5.cu).
+constexpr int DQ_FLUSH = 8;     // key tiles of 64 (8 steps each)
+constexpr int DKV_FLUSH = 16;   // query tiles of 32 (4 steps each)
 
 __device__ __forceinline__ float b5_ex2(float x) {
   float y;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (t | kb | k) != 0;
+            const uint32_t acc = ((t % DQ_FLUSH) | kb | k) != 0;   // restart after every drain
             const uint64_t b = umma_desc_sw128(kta + kb * 2 * B5_BOX64 + k * 32);
             b5_mma_ts(tmem_base + 384, tmem_base + 256 + kb * 32 + k * 8, b, B5_ID128, acc);   // dS_hi . [Kt_hi ; Kt_lo]
             b5_mma_ts(tmem_base + 384, tmem_base + 320 + kb * 32 + k * 8, b, B5_ID64, 1);      // dS_lo . Kt_hi
@@ -322,9 +326,22 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const uint32_t hrow = attn_drop_pre(seed, chunk) ^ ((uint32_t)grow * ATTN_DROP_CI);
     const uint32_t tb = tmem_base + lb;
     float a[16], b[16], c[16], x[16];
+    auto drain_dq = [&](bool first) {
+      tmem_drain16<2>(tb + 384 + cq * 16, dq + (base + grow) * 64 + cq * 16, scale, first, grow < m);
+    };
     // LAST: only the final key tile can hold keys past the chunk
     auto ew_tile = [&](int t, auto last_c) {
       constexpr bool LAST = decltype(last_c)::value;
+      // Every DQ_FLUSH tiles: tiles [t - DQ_FLUSH, t) are complete in the accumulator once the dQ MMAs of tile t-1 have
+      // retired -> drain them now, while few registers are live.  The dQ MMAs of tile t (which restart the accumulator) are
+      // issued only after every elementwise thread has arrived on ds_full at the end of this tile, i.e. after this read.
+      const bool drain = t > 0 && t % DQ_FLUSH == 0;
+      if (drain) {
+        mbar_wait(smem_u32(dq_done), (uint32_t)((t - 1) & 1));
+        tcgen05_fence_after();
+        drain_dq(t == DQ_FLUSH);
+        tcgen05_fence_before();
+      }
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
       b5_ld16(tb + cq * 16, a);
@@ -347,7 +364,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         if (LAST) ds = e < lim ? ds : 0.f;
         b5_split(ds, hi[e], lo[e]);
       }
-      if (t > 0) mbar_wait(smem_u32(dq_done), (uint32_t)((t - 1) & 1));
+      if (t > 0 && !drain) mbar_wait(smem_u32(dq_done), (uint32_t)((t - 1) & 1));
       tcgen05_fence_after();
       b5_st16(tb + 256 + cq * 16, hi);
       b5_st16(tb + 320 + cq * 16, lo);
@@ -359,16 +376,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     ew_tile(n_tiles - 1, std::true_type{});
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
-    b5_ld16(tb + 384 + cq * 16, a);
-    b5_ld16(tb + 448 + cq * 16, b);
-    b5_ld_wait();
-    if (grow < m) {
-      float4* dst = reinterpret_cast<float4*>(dq + (base + grow) * 64 + cq * 16);
-#pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4)
-        dst[e4] = make_float4((a[4 * e4] + b[4 * e4]) * scale, (a[4 * e4 + 1] + b[4 * e4 + 1]) * scale,
-                              (a[4 * e4 + 2] + b[4 * e4 + 2]) * scale, (a[4 * e4 + 3] + b[4 * e4 + 3]) * scale);
-    }
+    drain_dq(n_tiles <= DQ_FLUSH);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         tcgen05_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t acc = (t | k) != 0;
+          const uint32_t acc = ((t % DKV_FLUSH) | k) != 0;   // restart after every drain
           const uint64_t bdo = umma_desc_sw128(dota + k * 32);
           const uint64_t bq = umma_desc_sw128(qta + k * 32);
           b5_mma_ts(tmem_base + 256, tmem_base + 128 + k * 8, bdo, B5_ID128, acc);   // dV += P~^T_hi . [dO^T_hi ; dO^T_lo]
@@ -538,7 +546,18 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const float4* lse4 = reinterpret_cast<const float4*>(lse2p + (long long)chunk * mp) + cq * 2;
     const float4* dl4 = reinterpret_cast<const float4*>(dlp + (long long)chunk * mp) + cq * 2;
     float a[8], b[8], c[8], x[8];
+    auto drain_one = [&](uint32_t col, float* out, float mul, bool first) {
+      tmem_drain16<2>(tb + col + cq * 16, out + (base + gkey) * 64 + cq * 16, mul, first, gkey < m);
+    };
     for (int t = 0; t < n_tiles; ++t) {
+      const bool drain = t > 0 && t % DKV_FLUSH == 0;   // see the dQ kernel
+      if (drain) {
+        mbar_wait(smem_u32(acc_done), (uint32_t)((t - 1) & 1));
+        tcgen05_fence_after();
+        drain_one(256, dv, 1.f, t == DKV_FLUSH);
+        drain_one(384, dk, scale, t == DKV_FLUSH);
+        tcgen05_fence_before();
+      }
       // per-query statistics of the 8 columns of this warp (padded rows: lse = +huge -> probability exactly 0)
       const float4 l0 = __ldg(lse4 + t * 8), l1 = __ldg(lse4 + t * 8 + 1);
       const float4 d0 = __ldg(dl4 + t * 8), d1 = __ldg(dl4 + t * 8 + 1);
@@ -567,7 +586,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         b5_split(pt, ph_[e], pl_[e]);
         b5_split(p * (dp - dl_c[e]), sh_[e], sl_[e]);
       }
-      if (t > 0) mbar_wait(smem_u32(acc_done), (uint32_t)((t - 1) & 1));
+      if (t > 0 && !drain) mbar_wait(smem_u32(acc_done), (uint32_t)((t - 1) & 1));
       tcgen05_fence_after();
       b5_st8(tb + 128 + cq * 8, ph_);
       b5_st8(tb + 160 + cq * 8, pl_);
@@ -579,27 +598,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     }
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
-    float o0[16], o1[16];
-    b5_ld16(tb + 256 + cq * 16, o0);
-    b5_ld16(tb + 320 + cq * 16, o1);
-    b5_ld_wait();
-    if (gkey < m) {
-      float4* dst = reinterpret_cast<float4*>(dv + (base + gkey) * 64 + cq * 16);
-#pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4)
-        dst[e4] = make_float4(o0[4 * e4] + o1[4 * e4], o0[4 * e4 + 1] + o1[4 * e4 + 1], o0[4 * e4 + 2] + o1[4 * e4 + 2],
-                              o0[4 * e4 + 3] + o1[4 * e4 + 3]);
-    }
-    b5_ld16(tb + 384 + cq * 16, o0);
-    b5_ld16(tb + 448 + cq * 16, o1);
-    b5_ld_wait();
-    if (gkey < m) {
-      float4* dst = reinterpret_cast<float4*>(dk + (base + gkey) * 64 + cq * 16);
-#pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4)
-        dst[e4] = make_float4((o0[4 * e4] + o1[4 * e4]) * scale, (o0[4 * e4 + 1] + o1[4 * e4 + 1]) * scale,
-                              (o0[4 * e4 + 2] + o1[4 * e4 + 2]) * scale, (o0[4 * e4 + 3] + o1[4 * e4 + 3]) * scale);
-    }
+    drain_one(256, dv, 1.f, n_tiles <= DKV_FLUSH);
+    drain_one(384, dk, scale, n_tiles <= DKV_FLUSH);
   }
   tcgen05_fence_before();
   __syncthreads();

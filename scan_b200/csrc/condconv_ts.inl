@@ -23,8 +23,9 @@ constexpr uint32_t TS_IDESC32 = umma_idesc_tf32(CC_BM, 32);
 constexpr int TS_SMEM = 1024 + 2 * CC_W_BYTES + TS_STAGES * CC_STAGE_BYTES + 1024;
 constexpr int TS_THREADS = 512;  // warps 0-3 TMA / MMA / alloc / idle, 4-7 epilogue, 8-11 and 12-15 converters (alternate k-blocks)
 
+// issued by one elected lane of the (converged) MMA warp
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
+  if (elect_one_sync()) asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   __shared__ double red[4];
   __shared__ int flag_s;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const long long R = lv.row_off[SCAN_MAX_LEVELS];
 
   if (threadIdx.x == 0) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes run the issue loop; every tcgen05.mma / commit goes out from one elected lane
       int op = 0, acc = 0;
       uint32_t op_phase = 0, acc_phase = 0;
       mbar_wait(smem_u32(w_ready), 0);
@@ -164,13 +165,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
             umma_tf32_ts(da0 + (k & 1) * 32, a_hi + k * 8, dwb, TS_IDESC32, first);
             umma_tf32_ts(db0 + (k & 1) * 16, a_lo + k * 8, dwb, CC_IDESC, first);
           }
-          umma_commit(smem_u32(op_empty + op));
+          if (elect_one_sync()) umma_commit(smem_u32(op_empty + op));
           if (++op == TS_OPS) { op = 0; op_phase ^= 1; }
         }
-        umma_commit(smem_u32(acc_full + acc));
+        if (elect_one_sync()) umma_commit(smem_u32(acc_full + acc));
         if (++acc == TS_ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 8) {
     // ===== converter: smem row -> registers -> hi/lo -> TMEM operand slot =====
     const int group = (warp - 8) >> 2;           // 0 or 1: alternate k-blocks

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   uint64_t* a_free = bars + 2 * G_STAGES + 5;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * G_STAGES + 6);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
   const int nt = (n + GT - 1) / GT;
 
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: all 32 lanes run the loop, every tcgen05 instruction goes out from one elected lane =====
+    {
       UnitIter it(nt);
       int row, j0, j1, stage = 0, acc = 0, units = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -180,17 +180,19 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             const uint32_t b_addr = smem_u32(stages + stage * G_BOX_BYTES);
 #pragma unroll
             for (int k = 0; k < GK / 8; ++k)
-              umma_tf32(d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), G_IDESC, (kb | k) != 0);
-            umma_commit(smem_u32(b_empty + stage));
+              if (elect_one_sync())
+                umma_tf32(d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), G_IDESC, (kb | k) != 0);
+            if (elect_one_sync()) umma_commit(smem_u32(b_empty + stage));
             if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(smem_u32(acc_full + acc));
+          if (elect_one_sync()) umma_commit(smem_u32(acc_full + acc));
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(smem_u32(a_free));  // arrives when every MMA reading this A tile has retired
+        if (elect_one_sync()) umma_commit(smem_u32(a_free));  // arrives when every MMA reading this A tile has retired
         ++units;
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue: 16 warps; warp e owns TMEM lanes [32q, 32q+32) (q = e % 4: rows of the tile) and the 32-column
     // block c0 = 32 * (e / 4).  One warp per scheduler is latency-bound (IPC ~0.1, ncu round-1 run 9): four per

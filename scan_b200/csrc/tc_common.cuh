@@ -63,6 +63,44 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 // warp index the compiler can prove uniform
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
+// Drain 16 accumulator columns of this thread's TMEM lane into an fp32 row in global memory:
+//   dst[0..15] (+)= mul * sum_{p < PARTS} tmem[taddr + 64 p + 0..15]        (plain store when first, else reduction)
+// The tensor core adds into its accumulator with TRUNCATION (measured: a 1100-step chain is off by a coherent 5e-5), so long
+// reductions are cut into <= 64-step pieces that are combined here with round-to-nearest adds.  The add is a fire-and-
+// forget vector reduction performed by the L2 (red.global.add.v4.f32): no load latency on the SM, and deterministic because
+// each address belongs to exactly one thread, which issues its pieces in order.  Warp-collective.
+template <int PARTS>
+__device__ __forceinline__ void tmem_drain16(uint32_t taddr, float* dst, float mul, bool first, bool valid) {
+  uint32_t r[PARTS][16];
+#pragma unroll
+  for (int p = 0; p < PARTS; ++p)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[p][0]), "=r"(r[p][1]), "=r"(r[p][2]), "=r"(r[p][3]), "=r"(r[p][4]), "=r"(r[p][5]), "=r"(r[p][6]), "=r"(r[p][7]),
+          "=r"(r[p][8]), "=r"(r[p][9]), "=r"(r[p][10]), "=r"(r[p][11]), "=r"(r[p][12]), "=r"(r[p][13]), "=r"(r[p][14]), "=r"(r[p][15])
+        : "r"(taddr + 64 * p)
+        : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (valid) {
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float sum = __uint_as_float(r[0][4 * e4 + i]);
+#pragma unroll
+        for (int p = 1; p < PARTS; ++p) sum += __uint_as_float(r[p][4 * e4 + i]);
+        v[i] = sum * mul;
+      }
+      if (first)
+        reinterpret_cast<float4*>(dst)[e4] = make_float4(v[0], v[1], v[2], v[3]);
+      else
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * e4), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                     : "memory");
+    }
+  }
+}
+
 // K-major operand tile with 128-byte rows and the 128B swizzle: 8-row groups are 1024 B apart (SBO),
 // LBO unused for swizzled K-major layouts, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {

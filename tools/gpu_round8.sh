@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout -k 10 "$TMO" "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?"; tail -n "${TAILN:-12}" gpurun_out/$name.log; }
+TMO=900 TAILN=3 run gpu_tests python -m pytest tests -m gpu -q --tb=short -x
+TMO=300 TAILN=3 run smoke python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
+TMO=900 TAILN=2 run bench python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+export SCAN_PROFILE=1
+TMO=900 TAILN=2 run ncu_step ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline
