@@ -66,6 +66,22 @@ int scan_pack_rows(const scan_levels_t* lv, const void* const* nchw_host, int32_
 int scan_unpack_rows(const scan_levels_t* lv, const float* rows, int32_t channels,
                      void* const* nchw_host, int32_t accumulate, void* stream);
 
+/* ---- f1: GroupNorm(32) + ReLU of the head_in towers on the rows layout (condgraph.py:68-119: the
+ *      nn.GroupNorm(32, C) + nn.ReLU that follow every tower convolution) ---------
+ * x_levels_host: host array of n_levels device pointers, level l = that level's convolution output as
+ * NHWC-dense [N*H_l*W_l, 256] fp32 (a torch channels_last tensor).  y_rows [R,256] receives
+ * relu(group_norm(x)) of all levels in the rows order; stats [n_levels*N*32*2] receives (mean, rstd).
+ * Backward: dy_levels_host like x_levels_host; dx_rows [R,256] in rows order; dgamma, dbeta [256].
+ * Workspace: scan_gn_workspace_bytes(lv) bytes.  Deterministic (per-block partials combined in fp64). */
+int64_t scan_gn_workspace_bytes(const scan_levels_t* lv);
+int scan_gn_relu_fwd(const scan_levels_t* lv, const void* const* x_levels_host, const float* gamma,
+                     const float* beta, float eps, float* y_rows, float* stats, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+int scan_gn_relu_bwd(const scan_levels_t* lv, const void* const* x_levels_host,
+                     const void* const* dy_levels_host, const float* y_rows, const float* gamma,
+                     const float* stats, float* dx_rows, float* dgamma, float* dbeta, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
 /* ---- K1a: FCOS ground-truth assignment (loss.py:262-343, PrototypeComputation.prepare_targets +
  *      compute_targets_for_locations; locations of condgraph.py:631-655 are computed from the index) --
  * boxes      [N, g_max, 4] fp32 xyxy, box_labels [N, g_max] int64, box_count [N] int32 (1..g_max)

@@ -79,6 +79,29 @@ class GRAPHHead(nn.Module):
     def forward(self, x):
         return [self.middle_tower(f) for f in x]
 
+    def forward_levels(self, geo, levels):
+        """The same tower on channels-last tensors: cuDNN runs its NHWC kernels without layout conversions and every
+        GroupNorm + ReLU pair is the scan_gn_relu kernel over all levels at once.  Returns per-level
+        [N,C,H,W] tensors; after a GroupNorm they are adjacent views of one rows buffer (ops.join_rows is then free)."""
+        layers = list(self.middle_tower)
+        h, i = list(levels), 0
+        while i < len(layers):
+            conv = layers[i]
+            i += 1
+            w = conv.weight.contiguous(memory_format=torch.channels_last)
+            outs = [F.conv2d(ops.nhwc_dense(x), w, conv.bias, padding=1) for x in h]
+            if i + 1 < len(layers) and isinstance(layers[i], nn.GroupNorm) and isinstance(layers[i + 1], nn.ReLU) \
+                    and layers[i].num_groups == 32:
+                gn = layers[i]
+                i += 2
+                h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs)
+            else:   # IN / BN variants and the norm-free head_out: torch modules (not used by the shipped configs' head_in)
+                while i < len(layers) and not isinstance(layers[i], nn.Conv2d):
+                    outs = [layers[i](o) for o in outs]
+                    i += 1
+                h = outs
+        return h
+
 
 class MultiHeadAttention(nn.Module):
     """Parameters of layers/transformer.py:36-90; the attention itself runs in scan_attn_fwd/bwd."""
@@ -287,15 +310,28 @@ class GRAPHModule(nn.Module):
 
     # ------------------------------------------------------------------ head_out (condgraph.py:379-384)
     def features_post_processing(self, features, act_maps):
-        if self.with_concated_maps:
-            return self.head_out([torch.cat([f, a], dim=1) for f, a in zip(features, act_maps)])
-        return features
+        """head_out(cat([features, act_maps], 1)) without materialising the concatenation: the first
+        convolution is split into its 256 feature columns (channels-last, NHWC kernels) and its K map columns."""
+        if not self.with_concated_maps:
+            return features
+        layers = list(self.head_out.middle_tower)
+        conv = layers[0]
+        wf = conv.weight[:, :ops.C].contiguous(memory_format=torch.channels_last)
+        wa = conv.weight[:, ops.C:].contiguous(memory_format=torch.channels_last)
+        outs = []
+        for f, a in zip(features, act_maps):
+            y = F.conv2d(ops.nhwc_dense(f), wf, conv.bias, padding=1)
+            y = y + F.conv2d(a.contiguous(memory_format=torch.channels_last), wa, None, padding=1)
+            for layer in layers[1:]:
+                y = layer(y)
+            outs.append(y)
+        return outs
 
     # ------------------------------------------------------------------ branches
     def _forward_train_source(self, images, features, targets=None, return_maps=False):
         geo = ops.Geometry.of(features, self.fpn_strides)
         dev = features[0].device
-        rows = ops.pack_rows(geo, features)
+        rows = ops.join_rows(geo, features)
         boxes, box_labels, box_count, g_max = ops.pad_targets(targets, dev)
         labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
         smp = ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels)
@@ -371,7 +407,7 @@ class GRAPHModule(nn.Module):
 
     def _forward_train_target(self, images, features, targets=None, return_maps=False):
         geo = ops.Geometry.of(features, self.fpn_strides)
-        rows = ops.pack_rows(geo, features)
+        rows = ops.join_rows(geo, features)
         weight, bias = self._split_kernel(self.get_conded_weight())   # identical at every level (condgraph.py:507)
         acts, _, _ = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode())
         smp = self._sample_target(geo, rows, acts)
@@ -406,15 +442,17 @@ class GRAPHModule(nn.Module):
 
     def _forward_inference(self, images, features, targets=None, return_maps=False):
         geo = ops.Geometry.of(features, self.fpn_strides)
-        rows = ops.pack_rows(geo, features)
+        rows = ops.join_rows(geo, features)
         weight, bias = self._split_kernel(self.get_conded_weight())
         acts, _, _ = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode())
         return self.features_post_processing(features, acts), None, None, acts
 
     def forward(self, images, features, targets=None, return_maps=False, mode="source", forward_target=False):
-        features = self.head_in(list(features))
+        features = list(features)
         if not features[0].is_cuda:
             raise RuntimeError("scan_b200.GRAPHModule runs on CUDA only (no CPU fallback)")
+        geo = ops.Geometry.of(features, self.fpn_strides)
+        features = self.head_in.forward_levels(geo, ops.pack_levels(geo, features))
         self.last = {"features_in": features}
         if self.training and targets and mode == "source":
             return self._forward_train_source(images, features, targets, return_maps)

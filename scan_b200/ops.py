@@ -120,6 +120,132 @@ def pack_rows(geo, feats):
 
 
 # ----------------------------------------------------------------------------------------------------
+# rows <-> per-level channels-last tensors (zero-copy), towers on the rows layout (SURVEY 8f rank 1)
+# ----------------------------------------------------------------------------------------------------
+def level_views(geo, rows):
+    """[R,256] rows -> list of [N,256,H_l,W_l] tensors that are channels_last VIEWS of `rows` (no copy)."""
+    return [rows[geo.row_off[l]:geo.row_off[l + 1]].view(geo.n_images, h, w, C).permute(0, 3, 1, 2)
+            for l, (h, w) in enumerate(geo.shapes)]
+
+
+def nhwc_dense(t):
+    """[N,C,H,W] tensor whose memory is NHWC-dense (torch channels_last); copies only if it is not already."""
+    if t.permute(0, 2, 3, 1).is_contiguous():
+        return t
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _level_rows(t):
+    """[N,C,H,W] NHWC-dense tensor -> its [N*H*W, C] rows view."""
+    return t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])
+
+
+class _PackLevels(torch.autograd.Function):
+    """NCHW features -> the rows matrix, handed out as per-level channels_last views (what cuDNN's NHWC kernels want)."""
+
+    @staticmethod
+    def forward(ctx, geo, *feats):
+        feats = [f.contiguous() for f in feats]
+        rows = torch.empty((geo.R, C), device=feats[0].device, dtype=torch.float32)
+        call("scan_pack_rows", geo.ref(), _ptr_array(feats), C, _ptr(rows), _stream())
+        ctx.geo = geo
+        ctx.shapes = [f.shape for f in feats]
+        return tuple(level_views(geo, rows))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *d_levels):
+        geo = ctx.geo
+        grads = []
+        for l, (g, shape) in enumerate(zip(d_levels, ctx.shapes)):
+            if g is None:
+                grads.append(None)
+                continue
+            g_rows = _level_rows(nhwc_dense(g))
+            out = torch.empty(shape, device=g.device, dtype=torch.float32)
+            one = Geometry([geo.shapes[l]], [geo.strides[l]], geo.n_images)
+            call("scan_unpack_rows", one.ref(), _ptr(g_rows), C, _ptr_array([out]), 0, _stream())
+            grads.append(out)
+        return (None,) + tuple(grads)
+
+
+def pack_levels(geo, feats):
+    for f in feats:
+        if f.dtype != torch.float32 or f.shape[1] != C:
+            raise RuntimeError("features must be fp32 with %d channels" % C)
+    return list(_PackLevels.apply(geo, *feats))
+
+
+class _JoinRows(torch.autograd.Function):
+    """Per-level tensors -> [R,256] rows.  Zero-copy when the levels are adjacent channels_last views of one buffer (what
+    gn_relu_levels / pack_levels hand out); otherwise one concatenating copy."""
+
+    @staticmethod
+    def forward(ctx, geo, *levels):
+        ctx.geo = geo
+        base = levels[0]
+        adjacent = True
+        for l, t in enumerate(levels):
+            if (not t.permute(0, 2, 3, 1).is_contiguous() or t.untyped_storage().data_ptr() != base.untyped_storage().data_ptr()
+                    or t.data_ptr() != base.data_ptr() + geo.row_off[l] * C * 4):
+                adjacent = False
+        if adjacent:
+            return torch.as_strided(base.detach(), (geo.R, C), (C, 1), base.storage_offset())
+        return torch.cat([_level_rows(nhwc_dense(t)) for t in levels])
+
+    @staticmethod
+    def backward(ctx, d_rows):
+        return (None,) + tuple(level_views(ctx.geo, d_rows.contiguous()))
+
+
+def join_rows(geo, levels):
+    return _JoinRows.apply(geo, *levels)
+
+
+class _GnReluLevels(torch.autograd.Function):
+    """relu(group_norm(x, 32)) of the five per-level convolution outputs in one launch sequence; the result is ONE rows
+    buffer handed out as per-level channels_last views."""
+
+    @staticmethod
+    def forward(ctx, geo, gamma, beta, eps, *xs):
+        xs = [nhwc_dense(x) for x in xs]
+        dev = xs[0].device
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        y_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
+        stats = torch.empty((len(xs) * geo.n_images * 32 * 2,), device=dev, dtype=torch.float32)
+        ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
+        call("scan_gn_relu_fwd", geo.ref(), _ptr_array(xs), _ptr(gamma), _ptr(beta), float(eps), _ptr(y_rows), _ptr(stats),
+             _ptr(ws), ws.numel(), _stream())
+        ctx.geo = geo
+        ctx.save_for_backward(gamma, stats, y_rows, *xs)
+        return tuple(level_views(geo, y_rows))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *d_levels):
+        geo = ctx.geo
+        gamma, stats, y_rows = ctx.saved_tensors[:3]
+        xs = ctx.saved_tensors[3:]
+        dev = y_rows.device
+        dys = [nhwc_dense(g) if g is not None else torch.zeros_like(x) for g, x in zip(d_levels, xs)]
+        dx_rows = torch.empty_like(y_rows)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
+        call("scan_gn_relu_bwd", geo.ref(), _ptr_array(xs), _ptr_array(dys), _ptr(y_rows), _ptr(gamma), _ptr(stats),
+             _ptr(dx_rows), _ptr(dgamma), _ptr(dbeta), _ptr(ws), ws.numel(), _stream())
+        return (None, dgamma, dbeta, None) + tuple(level_views(geo, dx_rows))
+
+
+def gn_relu_levels(geo, gamma, beta, eps, xs):
+    if gamma.numel() != C:
+        raise RuntimeError("the GroupNorm kernel is built for %d channels in 32 groups" % C)
+    for x in xs:
+        if not x.is_cuda or x.dtype != torch.float32 or x.shape[1] != C:
+            raise RuntimeError("gn_relu_levels expects CUDA fp32 [N,%d,H,W] tensors (no CPU fallback)" % C)
+    return list(_GnReluLevels.apply(geo, gamma, beta, eps, *xs))
+
+
+# ----------------------------------------------------------------------------------------------------
 # K1: assignment, sampling, gather
 # ----------------------------------------------------------------------------------------------------
 def pad_targets(targets, device):

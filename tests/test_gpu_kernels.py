@@ -130,6 +130,52 @@ def test_gather_scatter_rows():
     _close(r.grad, want, 1e-6, "scatter_add")
 
 
+@pytest.mark.parametrize("shapes,n", [(SHAPES, 3), (FULL, 2), ([(1, 1), (5, 3)], 1)])
+def test_gn_relu_levels_matches_torch_group_norm(shapes, n):
+    """f1: GroupNorm(32)+ReLU over all levels in the rows layout vs torch's group_norm + relu, forward and backward."""
+    g = torch.Generator().manual_seed(11)
+    geo = ops.Geometry(shapes, STRIDES[:len(shapes)], n)
+    xs = [(torch.randn(n, 256, h, w, generator=g) * 2 + 0.3) for h, w in shapes]
+    gamma, beta = torch.randn(256, generator=g), torch.randn(256, generator=g) * 0.1
+    cots = [torch.randn(n, 256, h, w, generator=g) for h, w in shapes]
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = [torch.relu(torch.nn.functional.group_norm(x, 32, gr, br, 1e-5)) for x in xr]
+    sum((y * c).sum() for y, c in zip(yr, cots)).backward()
+    xd = [x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for x in xs]
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    yd = ops.gn_relu_levels(geo, gd, bd, 1e-5, xd)
+    rows = ops.join_rows(geo, yd)                       # zero-copy: the levels are adjacent views of one buffer
+    assert rows.data_ptr() == yd[0].data_ptr() and rows.shape == (geo.R, 256)
+    (sum((y * c.to(DEV)).sum() for y, c in zip(yd, cots)) + 0.0 * rows.sum()).backward()
+    for l in range(len(shapes)):
+        _close(yd[l], yr[l], 2e-5, "y_l%d" % l)
+        _close(xd[l].grad, xr[l].grad, 5e-5, "dx_l%d" % l)
+        want_rows = yr[l].permute(0, 2, 3, 1).reshape(-1, 256)
+        assert torch.allclose(rows[geo.row_off[l]:geo.row_off[l + 1]].cpu(), want_rows.detach(), rtol=1e-4, atol=1e-5)
+    _close(gd.grad, gr.grad, 5e-5, "dgamma")
+    _close(bd.grad, br.grad, 5e-5, "dbeta")
+
+
+def test_pack_levels_roundtrip_and_gradient():
+    g = torch.Generator().manual_seed(12)
+    geo = ops.Geometry(SHAPES, STRIDES, 2)
+    feats = [torch.randn(2, 256, h, w, generator=g) for h, w in SHAPES]
+    fd = [f.to(DEV).requires_grad_(True) for f in feats]
+    levels = ops.pack_levels(geo, fd)
+    for l, f in enumerate(feats):
+        assert levels[l].shape == f.shape and levels[l].permute(0, 2, 3, 1).is_contiguous()
+        assert torch.equal(levels[l].cpu(), f)
+    rows = ops.join_rows(geo, levels)
+    assert rows.data_ptr() == levels[0].data_ptr()
+    cot = torch.randn(rows.shape, generator=g)
+    (rows * cot.to(DEV)).sum().backward()
+    for l, f in enumerate(fd):
+        h, w = SHAPES[l]
+        want = cot[geo.row_off[l]:geo.row_off[l + 1]].view(2, h, w, 256).permute(0, 3, 1, 2)
+        assert torch.equal(f.grad.cpu(), want)
+
+
 def _condconv_reference(feats, weight, bias, labels, mode, lam):
     k = weight.shape[0]
     logits = [torch.nn.functional.conv2d(f, weight.reshape(k, -1, 1, 1), bias) for f in feats]
