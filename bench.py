@@ -12,7 +12,8 @@ a trained model, so that the target-domain DBSCAN sees a realistic number of poi
 
   value      whole-job images/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same through the public module call with HOST (pinned) inputs: H2D of the step's FPN features and
-             D2H of its losses inside the timed region
+             D2H of its losses inside the timed region; the batch of step i+1 is copied on a side stream while step i
+             computes (a double-buffered input pipeline), the first copy is exposed
   roofline   conditional-convolution forward kernel: algorithmic bytes / its CUDA-event duration,
              against MEASURED_PEAKS.json
   cpu_baseline / --impl reference
@@ -248,11 +249,30 @@ def main():
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d2h = 0
+    # Input pipeline of a training loop: the pinned host batch of step i+1 is copied on a side stream while step i computes
+    # (double buffering).  Every step's H2D copy and result read-back happen inside the timed region; the first copy is
+    # fully exposed.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    def stage():
+        with torch.cuda.stream(copy_stream):
+            s_ = [f.to(dev, non_blocking=True) for f in src_h]
+            t_ = [f.to(dev, non_blocking=True) for f in tgt_h]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return s_, t_, ev
+
     f0.record()
-    for _ in range(args.steps):
-        s = [f.to(dev, non_blocking=True) for f in src_h]
-        t = [f.to(dev, non_blocking=True) for f in tgt_h]
+    nxt = stage()
+    for i in range(args.steps):
+        s, t, ev = nxt
+        main_stream.wait_event(ev)
+        if i + 1 < args.steps:
+            nxt = stage()
         res = one_step(module, s, src_t, t, cots)
+        for x in s + t:
+            x.record_stream(main_stream)
         host = [r.cpu() for r in res if r is not None]
         d2h = sum(h.numel() * 4 for h in host)
     f1.record()
@@ -291,6 +311,7 @@ def main():
                                        "synthetic images per GPU per step, 800x1344 FPN features, 8 classes + bg" % (n, n),
                            "parallelism": "dp%d (image shards, prototype all-reduce)" % world, "settle_steps": args.settle,
                            "attention_dropout": args.dropout,
+                           "e2e_input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i",
                            "l2_note": "inputs 2x%d MB per step exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
