@@ -254,25 +254,30 @@ def main():
     # fully exposed.
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
+    bufs = [([torch.empty(f.shape, device=dev) for f in src_h], [torch.empty(f.shape, device=dev) for f in tgt_h]) for _ in range(2)]
+    consumed = [None, None]   # event: the step that read buffer set b has finished
 
-    def stage():
+    def stage(b):
         with torch.cuda.stream(copy_stream):
-            s_ = [f.to(dev, non_blocking=True) for f in src_h]
-            t_ = [f.to(dev, non_blocking=True) for f in tgt_h]
+            if consumed[b] is not None:
+                copy_stream.wait_event(consumed[b])
+            for d_, h_ in zip(bufs[b][0] + bufs[b][1], src_h + tgt_h):
+                d_.copy_(h_, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return s_, t_, ev
+        return ev
 
+    barrier()
     f0.record()
-    nxt = stage()
+    ready = stage(0)
     for i in range(args.steps):
-        s, t, ev = nxt
-        main_stream.wait_event(ev)
+        b_ = i & 1
+        main_stream.wait_event(ready)
         if i + 1 < args.steps:
-            nxt = stage()
-        res = one_step(module, s, src_t, t, cots)
-        for x in s + t:
-            x.record_stream(main_stream)
+            ready = stage(b_ ^ 1)
+        res = one_step(module, [x.detach() for x in bufs[b_][0]], src_t, [x.detach() for x in bufs[b_][1]], cots)
+        consumed[b_] = torch.cuda.Event()
+        consumed[b_].record(main_stream)
         host = [r.cpu() for r in res if r is not None]
         d2h = sum(h.numel() * 4 for h in host)
     f1.record()

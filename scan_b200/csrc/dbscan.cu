@@ -375,16 +375,69 @@ __global__ void __launch_bounds__(256) db_flatten_kernel(const int* info, int n_
   }
 }
 
+// Dense regimes (the trained-like maps of the benchmark: ~40 k points, one giant cluster) have ~n^2/2 set adjacency bits and
+// nearly all of them join two points that the min-hook pass has already put into the same set.  Testing each bit costs two
+// dependent random loads (count[j], parent[j]), so the pass below first filters whole 32-bit words against a mask of the
+// points that can be skipped for rows of the DOMINANT set: non-core points and core points whose (flattened) root is the
+// dominant root.  Two points with equal roots after the flatten stay in one set for ever, so the filter never drops a
+// necessary union; a poor choice of the dominant root only costs speed.
+__global__ void __launch_bounds__(1024) db_pick_root_kernel(const int* info, int n_fixed, int min_samples, const int* __restrict__ count,
+                                                            const int* __restrict__ parent, int* __restrict__ rstar) {
+  __shared__ int cand[1024];
+  __shared__ int best_v[32], best_c[32];
+  const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
+  const int t = threadIdx.x;
+  const long long idx = n >= 1024 ? (long long)t * n / 1024 : (t < n ? t : -1);
+  int c = -1;
+  if (idx >= 0 && count[idx] >= min_samples) c = parent[idx];
+  cand[t] = c;
+  __syncthreads();
+  int v = 0;
+  if (c >= 0)
+    for (int k = 0; k < 1024; ++k) v += (cand[k] == c);
+  // block argmax of (votes, candidate)
+  int bv = v, bc = c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ov = __shfl_xor_sync(0xffffffffu, bv, o), oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    if (ov > bv || (ov == bv && oc > bc)) { bv = ov; bc = oc; }
+  }
+  if ((t & 31) == 0) { best_v[t >> 5] = bv; best_c[t >> 5] = bc; }
+  __syncthreads();
+  if (t == 0) {
+    for (int k = 1; k < 32; ++k)
+      if (best_v[k] > bv || (best_v[k] == bv && best_c[k] > bc)) { bv = best_v[k]; bc = best_c[k]; }
+    rstar[0] = bv > 0 ? bc : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) db_dom_mask_kernel(const int* info, int n_fixed, int cap, int min_samples,
+                                                          const int* __restrict__ count, const int* __restrict__ parent,
+                                                          const int* __restrict__ rstar, uint32_t* __restrict__ dmask) {
+  const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
+  const int rs = rstar[0];
+  const int words = (cap + 31) / 32;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < words * 32; j += gridDim.x * blockDim.x) {
+    const bool skip = j >= n || count[j] < min_samples || parent[j] == rs;
+    const unsigned b = __ballot_sync(0xffffffffu, skip);
+    if ((threadIdx.x & 31) == 0) dmask[j >> 5] = b;
+  }
+}
+
 __global__ void __launch_bounds__(256) db_union_rest_kernel(const uint32_t* __restrict__ adj, const int* info, int n_fixed, long long wpr,
-                                                            int min_samples, const int* __restrict__ count, int* parent) {
+                                                            int min_samples, const int* __restrict__ count, int* parent,
+                                                            const int* __restrict__ rstar, const uint32_t* __restrict__ dmask) {
   const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int rs = rstar[0];
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     if (count[i] < min_samples) continue;
     const int ri = parent[i];  // flattened root at the start of this pass
+    const bool dom = ri == rs;
     const int nw = (i >> 5) + 1;
     for (int w = lane; w < nw; w += 32) {
       uint32_t bits = __ldg(adj + (long long)i * wpr + w);
+      if (dom) bits &= ~__ldg(dmask + w);
       while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
@@ -526,7 +579,13 @@ static int cluster_points(const DbWs& ws, const float* points, const float* sq, 
   SCAN_LAUNCH_CHECK("db_union_min_kernel");
   db_flatten_kernel<<<2 * sms, 256, 0, st>>>(info, n_fixed, ws.parent);
   SCAN_LAUNCH_CHECK("db_flatten_kernel");
-  db_union_rest_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, min_samples, ws.count, ws.parent);
+  // scratch: the cluster-id array is not in use before db_roots_kernel; word 0 of block_cnt2 holds the dominant root
+  uint32_t* dmask = (uint32_t*)ws.cid;
+  db_pick_root_kernel<<<1, 1024, 0, st>>>(info, n_fixed, min_samples, ws.count, ws.parent, ws.block_cnt2);
+  SCAN_LAUNCH_CHECK("db_pick_root_kernel");
+  db_dom_mask_kernel<<<2 * sms, 256, 0, st>>>(info, n_fixed, cap, min_samples, ws.count, ws.parent, ws.block_cnt2, dmask);
+  SCAN_LAUNCH_CHECK("db_dom_mask_kernel");
+  db_union_rest_kernel<<<4 * sms, 256, 0, st>>>(ws.adj, info, n_fixed, ws.wpr, min_samples, ws.count, ws.parent, ws.block_cnt2, dmask);
   SCAN_LAUNCH_CHECK("db_union_rest_kernel");
   const int nb = (cap + DB_SB - 1) / DB_SB;
   db_roots_kernel<<<nb, DB_SB, 0, st>>>(info, n_fixed, min_samples, ws.count, ws.parent, ws.cid, ws.block_cnt2);
