@@ -147,8 +147,8 @@ int scan_condconv_fwd(const scan_levels_t* lv, const float* rows, const float* w
  * loss_scale: ACT_LOSS_WEIGHT / normaliser (0 when there is no act loss); d_loss: device scalar
  * d(total)/d(act_loss) or NULL (= 1), read on the device so that backward needs no host sync.
  * Outputs: d_rows [R,256] (overwritten), d_weight [K,256] and d_bias [K] (overwritten; d_bias may be NULL).
- * workspace: scan_condconv_bwd_workspace_bytes(). */
-int64_t scan_condconv_bwd_workspace_bytes(int32_t num_classes);
+ * workspace: scan_condconv_bwd_workspace_bytes(lv, num_classes) (d_weight partials + the [R, num_classes] d_logit matrix). */
+int64_t scan_condconv_bwd_workspace_bytes(const scan_levels_t* lv, int32_t num_classes);
 int scan_condconv_bwd(const scan_levels_t* lv, const float* rows, const float* weight,
                       int32_t num_classes, int32_t act_mode, const void* const* act_nchw_host,
                       const void* const* d_act_nchw_host, const int64_t* labels, float loss_scale,

@@ -462,15 +462,108 @@ __global__ void __launch_bounds__(CB_THREADS) condconv_bwd_kernel(Levels lv, con
   if (threadIdx.x < 16) partial_b[blockIdx.x * 16 + threadIdx.x] = bacc;
 }
 
+// ---- the product backward: two streaming passes -----------------------------------------------------------------
+// pass A  d(logit) of every row from the saved maps, the upstream map gradients and the focal term -> dz [R, KP] (KP =
+//         num_classes) in the workspace, plus per-block column sums (the bias gradient).  Thread = pixel, so the NCHW map
+//         reads are coalesced along the pixel axis.
+// pass B  one pass over the rows: d_rows = dz . W and per-CTA d_weight partials.  Thread = channel, the dz tile of 64 rows
+//         is broadcast from shared memory with 128-bit loads, 8 independent row loads in flight per thread, 4 CTAs / SM.
+//         Per (row, channel): 2 KP FMAs -- with KP = 9 that is below the fp32 issue budget of an HBM-bound stream.
+__global__ void __launch_bounds__(256) condconv_dlogit_kernel(Levels lv, ConstActPtrs act, ConstActPtrs dact, const int64_t* __restrict__ labels,
+                                                              float loss_scale, const float* __restrict__ d_loss, int K, int act_mode,
+                                                              float* __restrict__ dzw, float* __restrict__ partial_b) {
+  __shared__ float red[8][16];
+  const long long R = lv.row_off[SCAN_MAX_LEVELS];
+  if (d_loss) loss_scale *= __ldg(d_loss);  // d(total)/d(act_loss), a device scalar: no host sync
+  float bsum[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) bsum[k] = 0.f;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < R; g += (long long)gridDim.x * blockDim.x) {
+    float dz[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dz[k] = 0.f;
+    row_dlogits(lv, act, dact, g, K, act_mode, labels, loss_scale, dz);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) {
+        dzw[g * K + k] = dz[k];
+        bsum[k] += dz[k];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float s = warp_sum(bsum[k]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partial_b[blockIdx.x * 16 + threadIdx.x] = s;
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(CB_THREADS, 4) condconv_bwd_rows_kernel(const float* __restrict__ rows, const float* __restrict__ weight,
+                                                                         const float* __restrict__ dzw, long long R, int num_tiles,
+                                                                         float* __restrict__ d_rows, float* __restrict__ partial_w) {
+  constexpr int KS = (KP + 3) / 4 * 4;   // shared-memory row stride: whole float4s
+  __shared__ __align__(16) float dzs[CB_ROWS * KS];
+  const int c = threadIdx.x;
+  float w[KP], acc[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    w[k] = __ldg(weight + k * CC_C + c);
+    acc[k] = 0.f;
+  }
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const long long g0 = (long long)tile * CB_ROWS;
+    const int nrows = (int)min((long long)CB_ROWS, R - g0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < CB_ROWS * KP; i += CB_THREADS) {
+      const int r = i / KP, k = i - r * KP;
+      dzs[r * KS + k] = r < nrows ? __ldg(dzw + g0 * KP + i) : 0.f;
+    }
+    __syncthreads();
+    const float* xr = rows + g0 * CC_C + c;
+    float* dr = d_rows + g0 * CC_C + c;
+    for (int r0 = 0; r0 < CB_ROWS; r0 += 8) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (r0 + j < nrows) ? __ldg(xr + (long long)(r0 + j) * CC_C) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* d4 = reinterpret_cast<const float4*>(dzs + (r0 + j) * KS);
+        float dz[KS];
+#pragma unroll
+        for (int q = 0; q < KS / 4; ++q) {
+          const float4 d = d4[q];
+          dz[4 * q] = d.x; dz[4 * q + 1] = d.y; dz[4 * q + 2] = d.z; dz[4 * q + 3] = d.w;
+        }
+        float dx = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          dx = fmaf(dz[k], w[k], dx);
+          acc[k] = fmaf(dz[k], x[j], acc[k]);
+        }
+        if (r0 + j < nrows) dr[(long long)(r0 + j) * CC_C] = dx;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KP; ++k) partial_w[((long long)blockIdx.x * 16 + k) * CC_C + c] = acc[k];
+}
+
 __global__ void __launch_bounds__(256) condconv_bwd_reduce_kernel(const float* __restrict__ partial_w, const float* __restrict__ partial_b,
-                                                                  int n_parts, int K, float* __restrict__ d_weight, float* __restrict__ d_bias) {
+                                                                  int n_parts, int n_parts_b, int K, float* __restrict__ d_weight,
+                                                                  float* __restrict__ d_bias) {
   const int k = blockIdx.x, c = threadIdx.x;
   float s = 0.f;
   for (int i = 0; i < n_parts; ++i) s += partial_w[((long long)i * 16 + k) * CC_C + c];
   d_weight[k * CC_C + c] = s;
   if (d_bias && c == 0) {
     float b = 0.f;
-    for (int i = 0; i < n_parts; ++i) b += partial_b[i * 16 + k];
+    for (int i = 0; i < n_parts_b; ++i) b += partial_b[i * 16 + k];
     d_bias[k] = b;
   }
 }
@@ -581,9 +674,12 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
   return SCAN_OK;
 }
 
-extern "C" int64_t scan_condconv_bwd_workspace_bytes(int32_t /*num_classes*/) {
+extern "C" int64_t scan_condconv_bwd_workspace_bytes(const scan_levels_t* lvh, int32_t num_classes) {
+  scan::Levels lv;
+  if (scan::make_levels(lvh, &lv) || num_classes < 1 || num_classes > SCAN_MAX_CLASSES) return 0;
   const int64_t parts = 4ll * scan::sm_count();
-  return parts * 16 * scan::CC_C * 4 + parts * 16 * 4 + 256;
+  // d_weight partials [parts][16][256] | bias partials [parts][16] | dz [R][num_classes]
+  return parts * 16 * scan::CC_C * 4 + parts * 16 * 4 + lv.row_off[SCAN_MAX_LEVELS] * num_classes * 4 + 512;
 }
 
 extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, const float* weight, int32_t num_classes,
@@ -596,7 +692,7 @@ extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, co
   if (rc) return rc;
   if (!rows || !weight || !act_nchw_host || !d_rows || !d_weight || !workspace) return SCAN_EINVAL;
   if (num_classes < 1 || num_classes > SCAN_MAX_CLASSES || (act_mode != 0 && act_mode != 1)) return SCAN_EINVAL;
-  if (workspace_bytes < scan_condconv_bwd_workspace_bytes(num_classes)) return SCAN_ECAPACITY;
+  if (workspace_bytes < scan_condconv_bwd_workspace_bytes(lvh, num_classes)) return SCAN_ECAPACITY;
   ConstActPtrs act, dact;
   for (int l = 0; l < SCAN_MAX_LEVELS; ++l) {
     act.p[l] = l < lv.n_levels ? (const float*)act_nchw_host[l] : nullptr;
@@ -606,13 +702,34 @@ extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, co
   const long long R = lv.row_off[SCAN_MAX_LEVELS];
   const int num_tiles = (int)ceil_div(R, CB_ROWS);
   const int parts = std::min(num_tiles, 4 * sm_count());
+  const int parts_b = (int)std::min<long long>(ceil_div(R, 256), 4 * sm_count());
   float* pw = (float*)workspace;
   float* pb = pw + (long long)4 * sm_count() * 16 * CC_C;
+  float* dzw = pb + (long long)4 * sm_count() * 16 + 64;
   cudaStream_t st = (cudaStream_t)stream;
-  condconv_bwd_kernel<<<parts, CB_THREADS, 0, st>>>(lv, rows, weight, act, dact, labels, loss_scale, d_loss, num_classes, act_mode,
-                                                   num_tiles, d_rows, pw, pb);
-  SCAN_LAUNCH_CHECK("condconv_bwd_kernel");
-  condconv_bwd_reduce_kernel<<<num_classes, 256, 0, st>>>(pw, pb, parts, num_classes, d_weight, d_bias);
+  static const int fused = getenv("SCAN_B200_CONDCONV_BWD_FUSED") ? atoi(getenv("SCAN_B200_CONDCONV_BWD_FUSED")) : 0;
+  if (fused) {  // round-1 single-pass kernel (kept for comparison)
+    condconv_bwd_kernel<<<parts, CB_THREADS, 0, st>>>(lv, rows, weight, act, dact, labels, loss_scale, d_loss, num_classes, act_mode,
+                                                     num_tiles, d_rows, pw, pb);
+    SCAN_LAUNCH_CHECK("condconv_bwd_kernel");
+    condconv_bwd_reduce_kernel<<<num_classes, 256, 0, st>>>(pw, pb, parts, parts, num_classes, d_weight, d_bias);
+    SCAN_LAUNCH_CHECK("condconv_bwd_reduce_kernel");
+    return SCAN_OK;
+  }
+  condconv_dlogit_kernel<<<parts_b, 256, 0, st>>>(lv, act, dact, labels, loss_scale, d_loss, num_classes, act_mode, dzw, pb);
+  SCAN_LAUNCH_CHECK("condconv_dlogit_kernel");
+  switch (num_classes) {
+#define SCAN_BWD_CASE(KP)                                                                                                \
+  case KP:                                                                                                               \
+    condconv_bwd_rows_kernel<KP><<<parts, CB_THREADS, 0, st>>>(rows, weight, dzw, R, num_tiles, d_rows, pw);           \
+    break;
+    SCAN_BWD_CASE(1) SCAN_BWD_CASE(2) SCAN_BWD_CASE(3) SCAN_BWD_CASE(4) SCAN_BWD_CASE(5) SCAN_BWD_CASE(6) SCAN_BWD_CASE(7) SCAN_BWD_CASE(8)
+    SCAN_BWD_CASE(9) SCAN_BWD_CASE(10) SCAN_BWD_CASE(11) SCAN_BWD_CASE(12) SCAN_BWD_CASE(13) SCAN_BWD_CASE(14) SCAN_BWD_CASE(15)
+    SCAN_BWD_CASE(16)
+#undef SCAN_BWD_CASE
+  }
+  SCAN_LAUNCH_CHECK("condconv_bwd_rows_kernel");
+  condconv_bwd_reduce_kernel<<<num_classes, 256, 0, st>>>(pw, pb, parts, parts_b, num_classes, d_weight, d_bias);
   SCAN_LAUNCH_CHECK("condconv_bwd_reduce_kernel");
   return SCAN_OK;
 }

@@ -376,7 +376,7 @@ class _CondConv(torch.autograd.Function):
         d_rows = torch.empty_like(rows)
         d_weight = torch.empty_like(weight)
         d_bias = torch.empty((k,), device=dev, dtype=torch.float32) if ctx.has_bias else None
-        ws_bytes = _lib.lib().scan_condconv_bwd_workspace_bytes(k)
+        ws_bytes = _lib.lib().scan_condconv_bwd_workspace_bytes(geo.ref(), k)
         ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
         call("scan_condconv_bwd", geo.ref(), _ptr(rows), _ptr(weight), k, ctx.act_mode, _ptr_array(acts),
              _ptr_array(d_acts), _ptr(labels), ctx.loss_scale, _ptr(d_loss_dev), _ptr(d_rows), _ptr(d_weight),
