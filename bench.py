@@ -302,7 +302,11 @@ def main():
         bytes_per_launch = n * L_PER_IMAGE * (1024 + 9 * 4) + n * L_PER_IMAGE * 8 * 0.5
         ach = bytes_per_launch / (cc["ms"] / max(cc["calls"], 1) / 1e3) / 1e9 if cc["calls"] else None
         roofline = {"kernel": "condconv_fwd_ts_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src}
+                    "frac": (ach / peak) if ach else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture at 8 images
+                    # (profiles/r01_hot_kernels_ncu_summary.txt: 185.3 + 9.3 MB), scaled to the images of this run
+                    "traffic": 194.6e6 * n / 8, "traffic_unit": "bytes/launch", "algorithmic_bytes": bytes_per_launch,
+                    "peak_source": peak_src}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             ips, t = cpu_reference_run(args, 3, 1)
