@@ -208,7 +208,10 @@ def main():
         dist.broadcast(module.prototype, 0)
     module.train()
     g = torch.Generator().manual_seed(5)
-    cots = ([(torch.randn((n, 256, h, w), generator=g) / 1e5).to(dev) for h, w in FULL_SHAPES],
+    # the module returns channels-last feature tensors; the FCOS head that consumes them hands back gradients in the same
+    # memory format (cuDNN's backward-data follows its input), so the stand-in cotangents are channels-last as well
+    cots = ([(torch.randn((n, 256, h, w), generator=g) / 1e5).to(dev).contiguous(memory_format=torch.channels_last)
+             for h, w in FULL_SHAPES],
             [(torch.randn((n, 9, h, w), generator=g) / 1e5).to(dev) for h, w in FULL_SHAPES])
 
     def barrier():

@@ -74,13 +74,26 @@ int scan_unpack_rows(const scan_levels_t* lv, const float* rows, int32_t channel
  * Backward: dy_levels_host like x_levels_host; dx_rows [R,256] in rows order; dgamma, dbeta [256].
  * Workspace: scan_gn_workspace_bytes(lv) bytes.  Deterministic (per-block partials combined in fp64). */
 int64_t scan_gn_workspace_bytes(const scan_levels_t* lv);
-int scan_gn_relu_fwd(const scan_levels_t* lv, const void* const* x_levels_host, const float* gamma,
-                     const float* beta, float eps, float* y_rows, float* stats, void* workspace,
-                     int64_t workspace_bytes, void* stream);
+/* conv_bias (nullable, [256]): the bias of the preceding convolution, added on the fly so that the convolution
+ * itself runs bias-free; the backward then also returns d_conv_bias (column sums of dx) instead of a
+ * separate full-tensor reduction.  conv_bias and d_conv_bias must both be given or both be NULL. */
+int scan_gn_relu_fwd(const scan_levels_t* lv, const void* const* x_levels_host, const float* conv_bias,
+                     const float* gamma, const float* beta, float eps, float* y_rows, float* stats,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 int scan_gn_relu_bwd(const scan_levels_t* lv, const void* const* x_levels_host,
-                     const void* const* dy_levels_host, const float* y_rows, const float* gamma,
-                     const float* stats, float* dx_rows, float* dgamma, float* dbeta, void* workspace,
-                     int64_t workspace_bytes, void* stream);
+                     const void* const* dy_levels_host, const float* conv_bias, const float* y_rows,
+                     const float* gamma, const float* stats, float* dx_rows, float* dgamma, float* dbeta,
+                     float* d_conv_bias, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- f1: head_out epilogue y = relu(u + v + bias) (condgraph.py:379-384 with the concat removed:
+ *      u = conv3x3(features, W[:, :256]), v = conv3x3(act maps, W[:, 256:])) --------------------------
+ * u_levels_host / v_levels_host (v nullable): per-level NHWC-dense [N*H_l*W_l, 256]; y_rows [R,256].
+ * Backward: d_rows [R,256] = dy * [y > 0] (the gradient of both u and v), d_bias [256] (nullable;
+ * needs a workspace of scan_gn_workspace_bytes(lv)). */
+int scan_add_relu_fwd(const scan_levels_t* lv, const void* const* u_levels_host,
+                      const void* const* v_levels_host, const float* bias, float* y_rows, void* stream);
+int scan_add_relu_bwd(const scan_levels_t* lv, const void* const* dy_levels_host, const float* y_rows,
+                      float* d_rows, float* d_bias, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- K1a: FCOS ground-truth assignment (loss.py:262-343, PrototypeComputation.prepare_targets +
  *      compute_targets_for_locations; locations of condgraph.py:631-655 are computed from the index) --

@@ -89,13 +89,15 @@ class GRAPHHead(nn.Module):
             conv = layers[i]
             i += 1
             w = conv.weight.contiguous(memory_format=torch.channels_last)
-            outs = [F.conv2d(ops.nhwc_dense(x), w, conv.bias, padding=1) for x in h]
             if i + 1 < len(layers) and isinstance(layers[i], nn.GroupNorm) and isinstance(layers[i + 1], nn.ReLU) \
                     and layers[i].num_groups == 32:
                 gn = layers[i]
                 i += 2
-                h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs)
+                # bias-free convolution: the GroupNorm kernel adds the bias and returns its gradient as a by-product
+                outs = [F.conv2d(ops.nhwc_dense(x), w, None, padding=1) for x in h]
+                h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs, conv_bias=conv.bias)
             else:   # IN / BN variants and the norm-free head_out: torch modules (not used by the shipped configs' head_in)
+                outs = [F.conv2d(ops.nhwc_dense(x), w, conv.bias, padding=1) for x in h]
                 while i < len(layers) and not isinstance(layers[i], nn.Conv2d):
                     outs = [layers[i](o) for o in outs]
                     i += 1
@@ -318,10 +320,14 @@ class GRAPHModule(nn.Module):
         conv = layers[0]
         wf = conv.weight[:, :ops.C].contiguous(memory_format=torch.channels_last)
         wa = conv.weight[:, ops.C:].contiguous(memory_format=torch.channels_last)
+        us = [F.conv2d(ops.nhwc_dense(f), wf, None, padding=1) for f in features]
+        vs = [F.conv2d(a.contiguous(memory_format=torch.channels_last), wa, None, padding=1) for a in act_maps]
+        if len(layers) == 2 and isinstance(layers[1], nn.ReLU):
+            geo = ops.Geometry.of(features, self.fpn_strides)
+            return ops.add_relu_levels(geo, conv.bias, us, vs)      # relu(u + v + bias), all levels in one launch
         outs = []
-        for f, a in zip(features, act_maps):
-            y = F.conv2d(ops.nhwc_dense(f), wf, conv.bias, padding=1)
-            y = y + F.conv2d(a.contiguous(memory_format=torch.channels_last), wa, None, padding=1)
+        for u, v in zip(us, vs):
+            y = u + v + conv.bias.view(1, -1, 1, 1)
             for layer in layers[1:]:
                 y = layer(y)
             outs.append(y)

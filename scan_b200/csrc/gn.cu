@@ -46,14 +46,26 @@ __device__ __forceinline__ GnBlock gn_decode(const Levels& lv, const GnLevels& g
 }
 
 // ---------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(256) gn_stats_kernel(Levels lv, GnLevels g, float* __restrict__ partial /* [blocks][32][2] */) {
+// cbias (may be null): the bias of the preceding convolution, added here so that the convolution runs bias-free and its bias
+// gradient comes out of gn_bwd_apply_kernel instead of a separate full-tensor reduction
+__device__ __forceinline__ float4 gn_bias4(const float* cbias, int c4) {
+  return cbias ? __ldg(reinterpret_cast<const float4*>(cbias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float4 gn_ldx(const float4* p, const float4& cb) {
+  const float4 v = __ldg(p);
+  return make_float4(v.x + cb.x, v.y + cb.y, v.z + cb.z, v.w + cb.w);
+}
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
+                                                       float* __restrict__ partial /* [blocks][32][2] */) {
   __shared__ float red[4][GN_G][2];
   const GnBlock b = gn_decode(lv, g, blockIdx.x);
   const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const float4 cb = gn_bias4(cbias, c4);
   const float4* x = reinterpret_cast<const float4*>(g.x[b.l] + ((long long)b.n * b.hw + b.p0) * GN_C) + c4;
   float s = 0.f, ss = 0.f;
   for (int p = rsub; p < b.np; p += 4) {
-    const float4 v = __ldg(x + (long long)p * (GN_C / 4));
+    const float4 v = gn_ldx(x + (long long)p * (GN_C / 4), cb);
     s += (v.x + v.y) + (v.z + v.w);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
@@ -94,11 +106,12 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(Levels lv, GnLevels g,
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(Levels lv, GnLevels g, const float* __restrict__ stats,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float* __restrict__ y_rows) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
+                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* __restrict__ y_rows) {
   const GnBlock b = gn_decode(lv, g, blockIdx.x);
   const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const float4 cb = gn_bias4(cbias, c4);
   const float mean = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)));
   const float rstd = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)) + 1);
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
@@ -108,7 +121,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Levels lv, GnLevels g, co
   const float4* x = reinterpret_cast<const float4*>(g.x[b.l] + ((long long)b.n * b.hw + b.p0) * GN_C) + c4;
   float4* y = reinterpret_cast<float4*>(y_rows + b.row0 * GN_C) + c4;
   for (int p = rsub; p < b.np; p += 4) {
-    const float4 v = __ldg(x + (long long)p * (GN_C / 4));
+    const float4 v = gn_ldx(x + (long long)p * (GN_C / 4), cb);
     y[(long long)p * (GN_C / 4)] = make_float4(fmaxf(fmaf(v.x, a.x, c.x), 0.f), fmaxf(fmaf(v.y, a.y, c.y), 0.f),
                                                fmaxf(fmaf(v.z, a.z, c.z), 0.f), fmaxf(fmaf(v.w, a.w, c.w), 0.f));
   }
@@ -116,12 +129,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Levels lv, GnLevels g, co
 
 // ---------------------------------------------------------------------------- backward
 // per block and channel: A_c = sum dyr, B_c = sum dyr * xhat, with dyr = dy * [y > 0], xhat = (x - mean) * rstd
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Levels lv, GnLevels g, const float* __restrict__ stats,
-                                                            const float* __restrict__ y_rows,
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
+                                                            const float* __restrict__ stats, const float* __restrict__ y_rows,
                                                             float* __restrict__ partial /* [blocks][256][2] */) {
   __shared__ float red[4][GN_C][2];
   const GnBlock b = gn_decode(lv, g, blockIdx.x);
   const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const float4 cb = gn_bias4(cbias, c4);
   const float mean = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)));
   const float rstd = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)) + 1);
   const long long base = ((long long)b.n * b.hw + b.p0) * GN_C;
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Levels lv, GnLevels 
   float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int p = rsub; p < b.np; p += 4) {
     const long long o = (long long)p * (GN_C / 4);
-    const float4 xv = __ldg(x + o), dv = __ldg(dy + o), yv = __ldg(y + o);
+    const float4 xv = gn_ldx(x + o, cb), dv = __ldg(dy + o), yv = __ldg(y + o);
     const float d0 = yv.x > 0.f ? dv.x : 0.f, d1 = yv.y > 0.f ? dv.y : 0.f, d2 = yv.z > 0.f ? dv.z : 0.f, d3 = yv.w > 0.f ? dv.w : 0.f;
     a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
     bb[0] += d0 * ((xv.x - mean) * rstd);
@@ -196,11 +210,15 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(Levels lv, GnLevel
   }
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Levels lv, GnLevels g, const float* __restrict__ stats,
-                                                           const float* __restrict__ gsum, const float* __restrict__ gamma,
-                                                           const float* __restrict__ y_rows, float* __restrict__ dx_rows) {
+// dx, plus (when the convolution bias is folded in) per-block column sums of dx = the convolution's bias gradient partials
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
+                                                           const float* __restrict__ stats, const float* __restrict__ gsum,
+                                                           const float* __restrict__ gamma, const float* __restrict__ y_rows,
+                                                           float* __restrict__ dx_rows, float* __restrict__ colsum /* [blocks][256] or null */) {
+  __shared__ float red[4][GN_C];
   const GnBlock b = gn_decode(lv, g, blockIdx.x);
   const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const float4 cb = gn_bias4(cbias, c4);
   const int si = b.stat * GN_G + (c4 >> 1);
   const float mean = __ldg(stats + 2 * si), rstd = __ldg(stats + 2 * si + 1);
   const float inv_m = 1.f / ((float)b.hw * 8.f);
@@ -211,9 +229,10 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Levels lv, GnLevels g
   const float4* dy = reinterpret_cast<const float4*>(g.dy[b.l] + base) + c4;
   const float4* y = reinterpret_cast<const float4*>(y_rows + b.row0 * GN_C) + c4;
   float4* dx = reinterpret_cast<float4*>(dx_rows + b.row0 * GN_C) + c4;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = rsub; p < b.np; p += 4) {
     const long long o = (long long)p * (GN_C / 4);
-    const float4 xv = __ldg(x + o), dv = __ldg(dy + o), yv = __ldg(y + o);
+    const float4 xv = gn_ldx(x + o, cb), dv = __ldg(dy + o), yv = __ldg(y + o);
     float4 r;
     // dx = rstd * (dyr * gamma - (s1 + xhat * s2) / m)
     r.x = rstd * ((yv.x > 0.f ? dv.x : 0.f) * ga.x - (k1 + (xv.x - mean) * rstd * k2));
@@ -221,10 +240,76 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Levels lv, GnLevels g
     r.z = rstd * ((yv.z > 0.f ? dv.z : 0.f) * ga.z - (k1 + (xv.z - mean) * rstd * k2));
     r.w = rstd * ((yv.w > 0.f ? dv.w : 0.f) * ga.w - (k1 + (xv.w - mean) * rstd * k2));
     dx[o] = r;
+    cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w;
+  }
+  if (colsum) {
+    red[rsub][4 * c4 + 0] = cs.x; red[rsub][4 * c4 + 1] = cs.y; red[rsub][4 * c4 + 2] = cs.z; red[rsub][4 * c4 + 3] = cs.w;
+    __syncthreads();
+    const int c = threadIdx.x;
+    colsum[(long long)blockIdx.x * GN_C + c] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
   }
 }
 
-static int gn_build(const scan_levels_t* in, const void* const* x, const void* const* dy, Levels* lv, GnLevels* g) {
+// out[c] = sum over blocks of colsum[block][c]: one warp per channel, fp64, fixed order
+__global__ void __launch_bounds__(256) gn_colsum_kernel(const float* __restrict__ colsum, int n_blocks, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= GN_C) return;
+  double s = 0.0;
+  for (int b = lane; b < n_blocks; b += 32) s += (double)__ldg(colsum + (long long)b * GN_C + c);
+  s = warp_sum_d(s);
+  if (lane == 0) out[c] = (float)s;
+}
+
+// ---------------------------------------------------------------------------- head_out epilogue: y = relu(u + v + bias)
+// u = conv(features, W[:, :256]), v = conv(act maps, W[:, 256:]) (condgraph.py:379-384 without the concat); all levels per
+// launch, output in the rows layout.  Backward: du = dv = dy * [y > 0], d_bias = column sums.
+__global__ void __launch_bounds__(256) add_relu_kernel(Levels lv, GnLevels g /* x = u, dy = v */, const float* __restrict__ bias,
+                                                       float* __restrict__ y_rows) {
+  const GnBlock b = gn_decode(lv, g, blockIdx.x);
+  const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const float4 cb = gn_bias4(bias, c4);
+  const long long base = ((long long)b.n * b.hw + b.p0) * GN_C;
+  const float4* u = reinterpret_cast<const float4*>(g.x[b.l] + base) + c4;
+  const float4* v = g.dy[b.l] ? reinterpret_cast<const float4*>(g.dy[b.l] + base) + c4 : nullptr;
+  float4* y = reinterpret_cast<float4*>(y_rows + b.row0 * GN_C) + c4;
+  for (int p = rsub; p < b.np; p += 4) {
+    const long long o = (long long)p * (GN_C / 4);
+    float4 a = gn_ldx(u + o, cb);
+    if (v) {
+      const float4 w = __ldg(v + o);
+      a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w;
+    }
+    y[o] = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+  }
+}
+
+__global__ void __launch_bounds__(256) add_relu_bwd_kernel(Levels lv, GnLevels g /* dy = upstream */, const float* __restrict__ y_rows,
+                                                           float* __restrict__ d_rows, float* __restrict__ colsum) {
+  __shared__ float red[4][GN_C];
+  const GnBlock b = gn_decode(lv, g, blockIdx.x);
+  const int c4 = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  const long long base = ((long long)b.n * b.hw + b.p0) * GN_C;
+  const float4* dy = reinterpret_cast<const float4*>(g.dy[b.l] + base) + c4;
+  const float4* y = reinterpret_cast<const float4*>(y_rows + b.row0 * GN_C) + c4;
+  float4* d = reinterpret_cast<float4*>(d_rows + b.row0 * GN_C) + c4;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = rsub; p < b.np; p += 4) {
+    const long long o = (long long)p * (GN_C / 4);
+    const float4 dv = __ldg(dy + o), yv = __ldg(y + o);
+    const float4 r = make_float4(yv.x > 0.f ? dv.x : 0.f, yv.y > 0.f ? dv.y : 0.f, yv.z > 0.f ? dv.z : 0.f, yv.w > 0.f ? dv.w : 0.f);
+    d[o] = r;
+    cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w;
+  }
+  if (colsum) {
+    red[rsub][4 * c4 + 0] = cs.x; red[rsub][4 * c4 + 1] = cs.y; red[rsub][4 * c4 + 2] = cs.z; red[rsub][4 * c4 + 3] = cs.w;
+    __syncthreads();
+    const int c = threadIdx.x;
+    colsum[(long long)blockIdx.x * GN_C + c] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
+  }
+}
+
+static int gn_build(const scan_levels_t* in, const void* const* x, const void* const* dy, Levels* lv, GnLevels* g,
+                    bool need_x = true) {
   int rc = make_levels(in, lv);
   if (rc) return rc;
   int off = 0;
@@ -233,8 +318,8 @@ static int gn_build(const scan_levels_t* in, const void* const* x, const void* c
     g->x[l] = g->dy[l] = nullptr;
     g->chunks[l] = 1;
     if (l < lv->n_levels) {
-      if (!x || !x[l] || (dy && !dy[l])) return SCAN_EINVAL;
-      g->x[l] = (const float*)x[l];
+      if ((need_x && (!x || !x[l])) || (dy && !dy[l])) return SCAN_EINVAL;
+      g->x[l] = x ? (const float*)x[l] : nullptr;
       g->dy[l] = dy ? (const float*)dy[l] : nullptr;
       g->chunks[l] = (lv->h[l] * lv->w[l] + GN_ROWS - 1) / GN_ROWS;
       off += lv->n_images * g->chunks[l];
@@ -256,12 +341,13 @@ static long long gn_blocks(const scan_levels_t* in) {
 
 extern "C" int64_t scan_gn_workspace_bytes(const scan_levels_t* lv) {
   if (!lv || lv->n_levels < 1 || lv->n_levels > SCAN_MAX_LEVELS) return 0;
-  // backward partials dominate: [blocks][256][2] floats, + group sums
-  return scan::gn_blocks(lv) * scan::GN_C * 2 * 4 + (long long)lv->n_levels * lv->n_images * scan::GN_G * 2 * 4 + 256;
+  // backward partials dominate: [blocks][256][2] floats, + group sums, + dx column sums [blocks][256]
+  return scan::gn_blocks(lv) * scan::GN_C * 3 * 4 + (long long)lv->n_levels * lv->n_images * scan::GN_G * 2 * 4 + 512;
 }
 
-extern "C" int scan_gn_relu_fwd(const scan_levels_t* lv_in, const void* const* x_levels_host, const float* gamma, const float* beta,
-                                float eps, float* y_rows, float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int scan_gn_relu_fwd(const scan_levels_t* lv_in, const void* const* x_levels_host, const float* conv_bias, const float* gamma,
+                                const float* beta, float eps, float* y_rows, float* stats, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
   using namespace scan;
   Levels lv;
   GnLevels g;
@@ -272,36 +358,77 @@ extern "C" int scan_gn_relu_fwd(const scan_levels_t* lv_in, const void* const* x
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = g.blk_off[lv.n_levels];
   float* partial = (float*)workspace;
-  gn_stats_kernel<<<blocks, 256, 0, st>>>(lv, g, partial);
+  gn_stats_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, partial);
   SCAN_LAUNCH_CHECK("gn_stats_kernel");
   const int n_stats = lv.n_levels * lv.n_images * GN_G;
   gn_finalize_kernel<<<(n_stats + 7) / 8, 256, 0, st>>>(lv, g, partial, eps, stats);
   SCAN_LAUNCH_CHECK("gn_finalize_kernel");
-  gn_apply_kernel<<<blocks, 256, 0, st>>>(lv, g, stats, gamma, beta, y_rows);
+  gn_apply_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, gamma, beta, y_rows);
   SCAN_LAUNCH_CHECK("gn_apply_kernel");
   return SCAN_OK;
 }
 
 extern "C" int scan_gn_relu_bwd(const scan_levels_t* lv_in, const void* const* x_levels_host, const void* const* dy_levels_host,
-                                const float* y_rows, const float* gamma, const float* stats, float* dx_rows, float* dgamma,
-                                float* dbeta, void* workspace, int64_t workspace_bytes, void* stream) {
+                                const float* conv_bias, const float* y_rows, const float* gamma, const float* stats, float* dx_rows,
+                                float* dgamma, float* dbeta, float* d_conv_bias, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
   using namespace scan;
   Levels lv;
   GnLevels g;
   int rc = gn_build(lv_in, x_levels_host, dy_levels_host, &lv, &g);
   if (rc) return rc;
   if (!dy_levels_host || !y_rows || !gamma || !stats || !dx_rows || !dgamma || !dbeta || !workspace) return SCAN_EINVAL;
+  if ((conv_bias != nullptr) != (d_conv_bias != nullptr)) return SCAN_EINVAL;
   if (workspace_bytes < scan_gn_workspace_bytes(lv_in)) return SCAN_ECAPACITY;
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = g.blk_off[lv.n_levels];
   float* partial = (float*)workspace;
   float* gsum = partial + (long long)blocks * GN_C * 2;
-  gn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(lv, g, stats, y_rows, partial);
+  float* colsum = gsum + (long long)lv.n_levels * lv.n_images * GN_G * 2 + 64;
+  gn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, y_rows, partial);
   SCAN_LAUNCH_CHECK("gn_bwd_reduce_kernel");
   const int n_fin = lv.n_levels * lv.n_images * GN_G + GN_C;
   gn_bwd_finalize_kernel<<<(n_fin + 7) / 8, 256, 0, st>>>(lv, g, partial, gamma, gsum, dgamma, dbeta);
   SCAN_LAUNCH_CHECK("gn_bwd_finalize_kernel");
-  gn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(lv, g, stats, gsum, gamma, y_rows, dx_rows);
+  gn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, gsum, gamma, y_rows, dx_rows, d_conv_bias ? colsum : nullptr);
   SCAN_LAUNCH_CHECK("gn_bwd_apply_kernel");
+  if (d_conv_bias) {
+    gn_colsum_kernel<<<GN_C / 8, 256, 0, st>>>(colsum, blocks, d_conv_bias);
+    SCAN_LAUNCH_CHECK("gn_colsum_kernel");
+  }
+  return SCAN_OK;
+}
+
+extern "C" int scan_add_relu_fwd(const scan_levels_t* lv_in, const void* const* u_levels_host, const void* const* v_levels_host,
+                                 const float* bias, float* y_rows, void* stream) {
+  using namespace scan;
+  Levels lv;
+  GnLevels g;
+  int rc = gn_build(lv_in, u_levels_host, v_levels_host, &lv, &g);
+  if (rc) return rc;
+  if (!y_rows) return SCAN_EINVAL;
+  add_relu_kernel<<<g.blk_off[lv.n_levels], 256, 0, (cudaStream_t)stream>>>(lv, g, bias, y_rows);
+  SCAN_LAUNCH_CHECK("add_relu_kernel");
+  return SCAN_OK;
+}
+
+extern "C" int scan_add_relu_bwd(const scan_levels_t* lv_in, const void* const* dy_levels_host, const float* y_rows, float* d_rows,
+                                 float* d_bias, void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace scan;
+  Levels lv;
+  GnLevels g;
+  int rc = gn_build(lv_in, nullptr, dy_levels_host, &lv, &g, false);
+  if (rc) return rc;
+  if (!dy_levels_host || !y_rows || !d_rows || (d_bias && !workspace)) return SCAN_EINVAL;
+  if (d_bias && workspace_bytes < scan_gn_workspace_bytes(lv_in)) return SCAN_ECAPACITY;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = g.blk_off[lv.n_levels];
+  float* colsum = (float*)workspace;
+  add_relu_bwd_kernel<<<blocks, 256, 0, st>>>(lv, g, y_rows, d_rows, d_bias ? colsum : nullptr);
+  SCAN_LAUNCH_CHECK("add_relu_bwd_kernel");
+  if (d_bias) {
+    gn_colsum_kernel<<<GN_C / 8, 256, 0, st>>>(colsum, blocks, d_bias);
+    SCAN_LAUNCH_CHECK("gn_colsum_kernel");
+  }
   return SCAN_OK;
 }

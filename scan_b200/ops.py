@@ -203,46 +203,93 @@ def join_rows(geo, levels):
 
 
 class _GnReluLevels(torch.autograd.Function):
-    """relu(group_norm(x, 32)) of the five per-level convolution outputs in one launch sequence; the result is ONE rows
-    buffer handed out as per-level channels_last views."""
+    """relu(group_norm(x + conv_bias, 32)) of the five per-level convolution outputs in one launch sequence; the result is
+    ONE rows buffer handed out as per-level channels_last views.  conv_bias (optional) is the bias of the convolution that
+    produced x: folded in here so that the convolution runs bias-free and its bias gradient is a by-product."""
 
     @staticmethod
-    def forward(ctx, geo, gamma, beta, eps, *xs):
+    def forward(ctx, geo, gamma, beta, conv_bias, eps, *xs):
         xs = [nhwc_dense(x) for x in xs]
         dev = xs[0].device
         gamma, beta = gamma.contiguous(), beta.contiguous()
+        conv_bias = None if conv_bias is None else conv_bias.contiguous()
         y_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
         stats = torch.empty((len(xs) * geo.n_images * 32 * 2,), device=dev, dtype=torch.float32)
         ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
-        call("scan_gn_relu_fwd", geo.ref(), _ptr_array(xs), _ptr(gamma), _ptr(beta), float(eps), _ptr(y_rows), _ptr(stats),
-             _ptr(ws), ws.numel(), _stream())
+        call("scan_gn_relu_fwd", geo.ref(), _ptr_array(xs), _ptr(conv_bias), _ptr(gamma), _ptr(beta), float(eps), _ptr(y_rows),
+             _ptr(stats), _ptr(ws), ws.numel(), _stream())
         ctx.geo = geo
-        ctx.save_for_backward(gamma, stats, y_rows, *xs)
+        ctx.has_cbias = conv_bias is not None
+        ctx.save_for_backward(gamma, stats, y_rows, gamma if conv_bias is None else conv_bias, *xs)
         return tuple(level_views(geo, y_rows))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *d_levels):
         geo = ctx.geo
-        gamma, stats, y_rows = ctx.saved_tensors[:3]
-        xs = ctx.saved_tensors[3:]
+        gamma, stats, y_rows, cbias = ctx.saved_tensors[:4]
+        xs = ctx.saved_tensors[4:]
         dev = y_rows.device
+        if not ctx.has_cbias:
+            cbias = None
         dys = [nhwc_dense(g) if g is not None else torch.zeros_like(x) for g, x in zip(d_levels, xs)]
         dx_rows = torch.empty_like(y_rows)
         dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        dcb = torch.empty_like(gamma) if cbias is not None else None
         ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
-        call("scan_gn_relu_bwd", geo.ref(), _ptr_array(xs), _ptr_array(dys), _ptr(y_rows), _ptr(gamma), _ptr(stats),
-             _ptr(dx_rows), _ptr(dgamma), _ptr(dbeta), _ptr(ws), ws.numel(), _stream())
-        return (None, dgamma, dbeta, None) + tuple(level_views(geo, dx_rows))
+        call("scan_gn_relu_bwd", geo.ref(), _ptr_array(xs), _ptr_array(dys), _ptr(cbias), _ptr(y_rows), _ptr(gamma), _ptr(stats),
+             _ptr(dx_rows), _ptr(dgamma), _ptr(dbeta), _ptr(dcb), _ptr(ws), ws.numel(), _stream())
+        return (None, dgamma, dbeta, dcb, None) + tuple(level_views(geo, dx_rows))
 
 
-def gn_relu_levels(geo, gamma, beta, eps, xs):
+def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None):
     if gamma.numel() != C:
         raise RuntimeError("the GroupNorm kernel is built for %d channels in 32 groups" % C)
     for x in xs:
         if not x.is_cuda or x.dtype != torch.float32 or x.shape[1] != C:
             raise RuntimeError("gn_relu_levels expects CUDA fp32 [N,%d,H,W] tensors (no CPU fallback)" % C)
-    return list(_GnReluLevels.apply(geo, gamma, beta, eps, *xs))
+    return list(_GnReluLevels.apply(geo, gamma, beta, conv_bias, eps, *xs))
+
+
+class _AddReluLevels(torch.autograd.Function):
+    """relu(u + v + bias) per level (head_out without the concat), all levels per launch, output = views of one rows buffer."""
+
+    @staticmethod
+    def forward(ctx, geo, bias, n_levels, *uv):
+        us = [nhwc_dense(t) for t in uv[:n_levels]]
+        vs = [nhwc_dense(t) for t in uv[n_levels:]]
+        dev = us[0].device
+        bias = None if bias is None else bias.contiguous()
+        y_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
+        call("scan_add_relu_fwd", geo.ref(), _ptr_array(us), _ptr_array(vs) if vs else None, _ptr(bias), _ptr(y_rows), _stream())
+        ctx.geo = geo
+        ctx.has_bias = bias is not None
+        ctx.n_levels, ctx.has_v = n_levels, bool(vs)
+        ctx.save_for_backward(y_rows)
+        return tuple(level_views(geo, y_rows))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *d_levels):
+        geo = ctx.geo
+        (y_rows,) = ctx.saved_tensors
+        dev = y_rows.device
+        views = level_views(geo, y_rows)
+        dys = [nhwc_dense(g) if g is not None else torch.zeros_like(v) for g, v in zip(d_levels, views)]
+        d_rows = torch.empty_like(y_rows)
+        d_bias = torch.empty((C,), device=dev, dtype=torch.float32) if ctx.has_bias else None
+        ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8) if ctx.has_bias else None
+        call("scan_add_relu_bwd", geo.ref(), _ptr_array(dys), _ptr(y_rows), _ptr(d_rows), _ptr(d_bias), _ptr(ws),
+             0 if ws is None else ws.numel(), _stream())
+        d = tuple(level_views(geo, d_rows))
+        return (None, d_bias, None) + d + (d if ctx.has_v else ())
+
+
+def add_relu_levels(geo, bias, us, vs=None):
+    for x in list(us) + list(vs or []):
+        if not x.is_cuda or x.dtype != torch.float32 or x.shape[1] != C:
+            raise RuntimeError("add_relu_levels expects CUDA fp32 [N,%d,H,W] tensors (no CPU fallback)" % C)
+    return list(_AddReluLevels.apply(geo, bias, len(us), *(list(us) + list(vs or []))))
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -140,11 +140,14 @@ def test_gn_relu_levels_matches_torch_group_norm(shapes, n):
     cots = [torch.randn(n, 256, h, w, generator=g) for h, w in shapes]
     xr = [x.clone().requires_grad_(True) for x in xs]
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-    yr = [torch.relu(torch.nn.functional.group_norm(x, 32, gr, br, 1e-5)) for x in xr]
+    cb = torch.randn(256, generator=g) * 0.5            # bias of the preceding convolution, folded into the kernel
+    cbr = cb.clone().requires_grad_(True)
+    yr = [torch.relu(torch.nn.functional.group_norm(x + cbr.view(1, -1, 1, 1), 32, gr, br, 1e-5)) for x in xr]
     sum((y * c).sum() for y, c in zip(yr, cots)).backward()
     xd = [x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for x in xs]
     gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
-    yd = ops.gn_relu_levels(geo, gd, bd, 1e-5, xd)
+    cbd = cb.to(DEV).requires_grad_(True)
+    yd = ops.gn_relu_levels(geo, gd, bd, 1e-5, xd, conv_bias=cbd)
     rows = ops.join_rows(geo, yd)                       # zero-copy: the levels are adjacent views of one buffer
     assert rows.data_ptr() == yd[0].data_ptr() and rows.shape == (geo.R, 256)
     (sum((y * c.to(DEV)).sum() for y, c in zip(yd, cots)) + 0.0 * rows.sum()).backward()
@@ -155,6 +158,30 @@ def test_gn_relu_levels_matches_torch_group_norm(shapes, n):
         assert torch.allclose(rows[geo.row_off[l]:geo.row_off[l + 1]].cpu(), want_rows.detach(), rtol=1e-4, atol=1e-5)
     _close(gd.grad, gr.grad, 5e-5, "dgamma")
     _close(bd.grad, br.grad, 5e-5, "dbeta")
+    _close(cbd.grad, cbr.grad, 5e-5, "d_conv_bias", atol=2e-4)      # sums to ~0 analytically within each group
+
+
+@pytest.mark.parametrize("shapes,n", [(SHAPES, 2), ([(1, 1), (5, 3)], 1)])
+def test_add_relu_levels(shapes, n):
+    g = torch.Generator().manual_seed(13)
+    geo = ops.Geometry(shapes, STRIDES[:len(shapes)], n)
+    us = [torch.randn(n, 256, h, w, generator=g) for h, w in shapes]
+    vs = [torch.randn(n, 256, h, w, generator=g) for h, w in shapes]
+    bias = torch.randn(256, generator=g)
+    cots = [torch.randn(n, 256, h, w, generator=g) for h, w in shapes]
+    ur, vr, br = [t.clone().requires_grad_(True) for t in us], [t.clone().requires_grad_(True) for t in vs], bias.clone().requires_grad_(True)
+    yr = [torch.relu(u + v + br.view(1, -1, 1, 1)) for u, v in zip(ur, vr)]
+    sum((y * c).sum() for y, c in zip(yr, cots)).backward()
+    ud = [t.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in us]
+    vd = [t.to(DEV).requires_grad_(True) for t in vs]            # NCHW-contiguous inputs are converted inside
+    bd = bias.to(DEV).requires_grad_(True)
+    yd = ops.add_relu_levels(geo, bd, ud, vd)
+    sum((y * c.to(DEV)).sum() for y, c in zip(yd, cots)).backward()
+    for l in range(len(shapes)):
+        _close(yd[l], yr[l], 1e-6, "y_l%d" % l)            # (u + bias) + v here, (u + v) + bias in torch: last-bit differences
+        flip = (yr[l].detach().abs() < 1e-5)                # the ReLU mask may differ where the pre-activation is ~0
+        assert torch.equal(ud[l].grad.cpu()[~flip], ur[l].grad[~flip]) and torch.equal(vd[l].grad.cpu()[~flip], vr[l].grad[~flip])
+    _close(bd.grad, br.grad, 1e-4, "d_bias")
 
 
 def test_pack_levels_roundtrip_and_gradient():
