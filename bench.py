@@ -190,6 +190,8 @@ def main():
     from scan_b200.config import scan_cfg
     from scan_b200.fixtures import fixture_state_dict
 
+    if os.environ.get("SCAN_CUDNN_BENCHMARK", "1") == "1":
+        torch.backends.cudnn.benchmark = True     # fixed shapes: let cuDNN pick the tower-convolution algorithms by measurement
     cfg = scan_cfg("c2f")
     module = build_condgraph(cfg, 256)
     module.load_state_dict(fixture_state_dict(module, seed=99))
