@@ -168,6 +168,26 @@ int scan_condconv_bwd(const scan_levels_t* lv, const float* rows, const float* w
                       const float* d_loss, float* d_rows, float* d_weight, float* d_bias, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* ---- K4a: paradigm manifestation, RNN variant (condgraph.py:313-336 get_conded_weight with USE_RNN:
+ *      nn.RNN(I->H, 2 layers, tanh) over the P paradigm slots of the K classes, then the (P x 1)
+ *      convolution cond_nx1) --------------------------------------------------------------------------
+ * proto [K, I, P] (the `prototype` buffer), RNN parameters in torch's nn.RNN layout (weight_ih_l0 [H,I],
+ * weight_hh_l0 [H,H], biases [H], layer 1 [H,H]), wc = cond_nx1.weight [O, H, P, 1], bc [O].
+ * kernel_out [K, O]; `saved` (scan_manifest_rnn_saved_floats floats) keeps the activations for backward.
+ * K <= 16, P <= 16, I and H multiples of 4.  Backward returns the gradients of all ten parameters
+ * (the prototype buffer takes no gradient in the reference). */
+int64_t scan_manifest_rnn_saved_floats(int32_t K, int32_t P, int32_t I, int32_t H);
+int64_t scan_manifest_rnn_workspace_bytes(int32_t K, int32_t P, int32_t H);
+int scan_manifest_rnn_fwd(const float* proto, int32_t K, int32_t P, int32_t I, int32_t H, int32_t O,
+                          const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
+                          const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,
+                          const float* wc, const float* bc, float* kernel_out, float* saved, void* stream);
+int scan_manifest_rnn_bwd(const float* d_kernel, int32_t K, int32_t P, int32_t I, int32_t H, int32_t O,
+                          const float* w_hh0, const float* w_ih1, const float* w_hh1, const float* wc,
+                          const float* saved, float* d_w_ih0, float* d_w_hh0, float* d_b_ih0, float* d_b_hh0,
+                          float* d_w_ih1, float* d_w_hh1, float* d_b_ih1, float* d_b_hh1, float* d_wc,
+                          float* d_bc, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- K3a: graph aggregation, global variant (layers/transformer.py:5-90 dot_attention inside
  *      MultiHeadAttention, called at condgraph.py:390-393) ----------------------------------------
  * q,k,v [M,256] are the three linear projections.  The reference's .view(4,-1,64) makes 4 independent

@@ -226,9 +226,8 @@ class GRAPHModule(nn.Module):
     # ------------------------------------------------------------------ manifestation (condgraph.py:313-336)
     def get_conded_weight(self):
         if self.use_rnn:
-            h, _ = self.cond_rnn(self.prototype.permute(2, 0, 1).contiguous())       # [P,K,512]
-            w = self.cond_nx1.weight[:, :, :, 0]                                     # [256,512,P]
-            return torch.einsum("pkc,ocp->ko", h, w) + self.cond_nx1.bias
+            # h = cond_rnn(prototype.permute(2, 0, 1)); kernel = einsum("pkc,ocp->ko", h, cond_nx1.weight[..., 0]) + bias
+            return ops.manifest_rnn(self.prototype, self.cond_rnn, self.cond_nx1)
         if self.prototype_iter > 1:
             w = self.cond_nx1.weight[:, :, :, 0]
             hcat = torch.einsum("kcp,ocp->ko", self.prototype, w) + self.cond_nx1.bias

@@ -441,6 +441,48 @@ def condconv(geo, rows, weight, bias, num_classes, act_mode, labels=None, loss_w
 
 
 # ----------------------------------------------------------------------------------------------------
+# K4a: manifestation (RNN variant)
+# ----------------------------------------------------------------------------------------------------
+class _ManifestRnn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proto, w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, wc, bc):
+        ps = [t.contiguous() for t in (w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, wc, bc)]
+        proto = proto.contiguous()
+        k, i, p = proto.shape
+        h, o = ps[0].shape[0], ps[8].shape[0]
+        dev = proto.device
+        out = torch.empty((k, o), device=dev, dtype=torch.float32)
+        saved = torch.empty((_lib.lib().scan_manifest_rnn_saved_floats(k, p, i, h),), device=dev, dtype=torch.float32)
+        call("scan_manifest_rnn_fwd", _ptr(proto), k, p, i, h, o, *[_ptr(t) for t in ps], _ptr(out), _ptr(saved), _stream())
+        ctx.dims = (k, p, i, h, o)
+        ctx.save_for_backward(saved, *ps)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_out):
+        k, p, i, h, o = ctx.dims
+        saved = ctx.saved_tensors[0]
+        w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, wc, bc = ctx.saved_tensors[1:]
+        d_out = d_out.contiguous()
+        grads = [torch.empty_like(t) for t in (w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, wc, bc)]
+        ws = torch.empty((_lib.lib().scan_manifest_rnn_workspace_bytes(k, p, h),), device=d_out.device, dtype=torch.uint8)
+        call("scan_manifest_rnn_bwd", _ptr(d_out), k, p, i, h, o, _ptr(w_hh0), _ptr(w_ih1), _ptr(w_hh1), _ptr(wc), _ptr(saved),
+             *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream())
+        return (None,) + tuple(grads)
+
+
+def manifest_rnn(proto, rnn, conv):
+    """get_conded_weight (condgraph.py:313-336), RNN variant: `rnn` = nn.RNN(I, H, 2, tanh), `conv` = cond_nx1 (P x 1)."""
+    if rnn.num_layers != 2 or rnn.nonlinearity != "tanh" or rnn.bidirectional or rnn.batch_first or not rnn.bias:
+        raise RuntimeError("manifest_rnn implements the reference's nn.RNN(256, 512, 2, nonlinearity='tanh')")
+    if not proto.is_cuda or proto.dtype != torch.float32:
+        raise RuntimeError("manifest_rnn expects a CUDA fp32 prototype buffer (no CPU fallback)")
+    return _ManifestRnn.apply(proto, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0, rnn.weight_ih_l1,
+                              rnn.weight_hh_l1, rnn.bias_ih_l1, rnn.bias_hh_l1, conv.weight, conv.bias)
+
+
+# ----------------------------------------------------------------------------------------------------
 # K3a: attention
 # ----------------------------------------------------------------------------------------------------
 # implementations: "t5" = tcgen05 kernels (product), "ffma" = fp32 verification kernels (SCAN_B200_ATTN_FWD/BWD=ffma)

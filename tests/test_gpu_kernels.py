@@ -322,6 +322,28 @@ def test_attention_tcgen05_and_ffma_kernels_agree(m, drop):
         _close(a, b, 5e-5, name, atol=2e-5)
 
 
+@pytest.mark.parametrize("k,p", [(9, 3), (2, 1), (16, 5)])
+def test_manifest_rnn_matches_torch(k, p):
+    """K4a: nn.RNN(256, 512, 2, tanh) over the paradigm slots + the (P x 1) convolution, forward and all parameter gradients."""
+    torch.manual_seed(3 + k)
+    rnn = torch.nn.RNN(256, 512, 2, nonlinearity="tanh")
+    conv = torch.nn.Conv2d(512, 256, kernel_size=(p, 1))
+    proto = torch.randn(k, 256, p)
+    cot = torch.randn(k, 256)
+    h, _ = rnn(proto.permute(2, 0, 1).contiguous())
+    want = torch.einsum("pkc,ocp->ko", h, conv.weight[:, :, :, 0]) + conv.bias
+    (want * cot).sum().backward()
+    ref = {n: t.grad.clone() for n, t in list(rnn.named_parameters()) + [("wc", conv.weight), ("bc", conv.bias)]}
+    rnn_d, conv_d = torch.nn.RNN(256, 512, 2, nonlinearity="tanh").to(DEV), torch.nn.Conv2d(512, 256, kernel_size=(p, 1)).to(DEV)
+    rnn_d.load_state_dict(rnn.state_dict())
+    conv_d.load_state_dict(conv.state_dict())
+    got = ops.manifest_rnn(proto.to(DEV), rnn_d, conv_d)
+    (got * cot.to(DEV)).sum().backward()
+    _close(got, want, 2e-5, "kernel")
+    for n, t in list(rnn_d.named_parameters()) + [("wc", conv_d.weight), ("bc", conv_d.bias)]:
+        _close(t.grad, ref[n], 5e-5, "d_" + n)
+
+
 def test_class_sums_and_proto_update():
     g = torch.Generator().manual_seed(4)
     m, k = 3000, 9
