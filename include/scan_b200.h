@@ -174,10 +174,10 @@ int scan_condconv_bwd(const scan_levels_t* lv, const float* rows, const float* w
  * proto [K, I, P] (the `prototype` buffer), RNN parameters in torch's nn.RNN layout (weight_ih_l0 [H,I],
  * weight_hh_l0 [H,H], biases [H], layer 1 [H,H]), wc = cond_nx1.weight [O, H, P, 1], bc [O].
  * kernel_out [K, O]; `saved` (scan_manifest_rnn_saved_floats floats) keeps the activations for backward.
- * K <= 16, P <= 16, I and H multiples of 4.  Backward returns the gradients of all ten parameters
+ * K <= 16, P <= 16, I, H and O multiples of 4.  Backward returns the gradients of all ten parameters
  * (the prototype buffer takes no gradient in the reference). */
 int64_t scan_manifest_rnn_saved_floats(int32_t K, int32_t P, int32_t I, int32_t H);
-int64_t scan_manifest_rnn_workspace_bytes(int32_t K, int32_t P, int32_t H);
+int64_t scan_manifest_rnn_workspace_bytes(int32_t K, int32_t P, int32_t H, int32_t O);
 int scan_manifest_rnn_fwd(const float* proto, int32_t K, int32_t P, int32_t I, int32_t H, int32_t O,
                           const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
                           const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,

@@ -466,7 +466,7 @@ class _ManifestRnn(torch.autograd.Function):
         w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, wc, bc = ctx.saved_tensors[1:]
         d_out = d_out.contiguous()
         grads = [torch.empty_like(t) for t in (w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1, wc, bc)]
-        ws = torch.empty((_lib.lib().scan_manifest_rnn_workspace_bytes(k, p, h),), device=d_out.device, dtype=torch.uint8)
+        ws = torch.empty((_lib.lib().scan_manifest_rnn_workspace_bytes(k, p, h, o),), device=d_out.device, dtype=torch.uint8)
         call("scan_manifest_rnn_bwd", _ptr(d_out), k, p, i, h, o, _ptr(w_hh0), _ptr(w_ih1), _ptr(w_hh1), _ptr(wc), _ptr(saved),
              *[_ptr(g) for g in grads], _ptr(ws), ws.numel(), _stream())
         return (None,) + tuple(grads)

@@ -203,6 +203,23 @@ def test_pack_levels_roundtrip_and_gradient():
         assert torch.equal(f.grad.cpu(), want)
 
 
+def test_join_rows_copies_when_levels_are_not_adjacent():
+    """join_rows is zero-copy only for adjacent views of one buffer; anything else (torch-produced tower outputs of the IN / BN
+    tower variants, NCHW-contiguous tensors) goes through one concatenating copy with the same values and gradients."""
+    g = torch.Generator().manual_seed(14)
+    geo = ops.Geometry(SHAPES, STRIDES, 2)
+    feats = [torch.randn(2, 256, h, w, generator=g) for h, w in SHAPES]
+    fd = [f.to(DEV).requires_grad_(True) for f in feats]                 # separately allocated, NCHW-contiguous
+    rows = ops.join_rows(geo, fd)
+    want = torch.cat([f.permute(0, 2, 3, 1).reshape(-1, 256) for f in feats])
+    assert torch.equal(rows.cpu(), want)
+    cot = torch.randn(rows.shape, generator=g)
+    (rows * cot.to(DEV)).sum().backward()
+    for l, f in enumerate(fd):
+        h, w = SHAPES[l]
+        assert torch.equal(f.grad.cpu(), cot[geo.row_off[l]:geo.row_off[l + 1]].view(2, h, w, 256).permute(0, 3, 1, 2))
+
+
 def _condconv_reference(feats, weight, bias, labels, mode, lam):
     k = weight.shape[0]
     logits = [torch.nn.functional.conv2d(f, weight.reshape(k, -1, 1, 1), bias) for f in feats]
