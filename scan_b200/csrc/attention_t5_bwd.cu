@@ -6,6 +6,8 @@
 //        S^T = K Q^T, dP^T = V dO^T -> P~^T, dS^T -> hi/lo to TMEM -> dV += P~^T dO, dK += dS^T Q (B = dO^T / Q^T planes)
 // Every product is 3xTF32 with the "hi x (hi | lo)" pair fused into one wide-N MMA.  No atomics: dQ, dK, dV are each
 // written once.  Operand planes come from attn_bwd_prep_kernel.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -189,7 +191,13 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const int chunk = blockIdx.y;
   const long long base = (long long)chunk * m;
   const int i0 = blockIdx.x * 128;
-  const int n_tiles = (m + 63) / 64;
+  // gridDim.z > 1: the key tiles are split over z (fills the machine when the (query tile, chunk) grid leaves SMs idle in
+  // the last wave); every split then ADDS its partial dQ into the zero-initialised output with the same vector reductions
+  // the drains use
+  const int n_tiles_all = (m + 63) / 64;
+  const int t0 = (int)((long long)n_tiles_all * blockIdx.z / gridDim.z);
+  const int n_tiles = (int)((long long)n_tiles_all * (blockIdx.z + 1) / gridDim.z) - t0;
+  const bool accum = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 12; ++i) mbar_init(smem_u32(bars + i), (i == 8 || i == 9) ? B5_EW : 1);
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           tma_load_2d(smem_u32(do_s + (part * 2 + kb) * B5_BOX128), &map_do, smem_u32(r_full), part * 64 + kb * 32, (int)(base + i0));
         }
       for (int t = 0; t < n_tiles; ++t) {
-        const int j0 = t * 64;
+        const int j0 = (t0 + t) * 64;
         const uint32_t ph = (uint32_t)(t & 1);
         mbar_wait(smem_u32(k_empty), ph ^ 1);
         mbar_expect_tx(smem_u32(k_full), 4 * B5_BOX64);
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   } else if (warp == 2) {
     if (lane == 0) {
       for (int t = 0; t < n_tiles; ++t) {
-        const int j0 = t * 64;
+        const int j0 = (t0 + t) * 64;
         mbar_wait(smem_u32(v_empty), (uint32_t)(t & 1) ^ 1);
         mbar_expect_tx(smem_u32(v_full), 4 * B5_BOX64);
         for (int kb = 0; kb < 2; ++kb)
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     // K/V prefetch for the next S/dP
     if (lane == 0) {
       for (int t = 0; t < n_tiles; ++t) {
-        const int j0 = t * 64;
+        const int j0 = (t0 + t) * 64;
         mbar_wait(smem_u32(kt_empty), (uint32_t)(t & 1) ^ 1);
         mbar_expect_tx(smem_u32(kt_full), 4 * B5_BOX64);
         for (int kb = 0; kb < 2; ++kb)
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       if (drain) {
         mbar_wait(smem_u32(dq_done), (uint32_t)((t - 1) & 1));
         tcgen05_fence_after();
-        drain_dq(t == DQ_FLUSH);
+        drain_dq(!accum && t == DQ_FLUSH);
         tcgen05_fence_before();
       }
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       b5_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(sp_free));
-      const int j0 = t * 64 + cq * 16;
+      const int j0 = (t0 + t) * 64 + cq * 16;
       const int lim = m - j0;
       const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
       uint32_t hi[16], lo[16];
@@ -372,11 +380,13 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       tcgen05_fence_before();
       mbar_arrive(smem_u32(ds_full));
     };
-    for (int t = 0; t + 1 < n_tiles; ++t) ew_tile(t, std::false_type{});
-    ew_tile(n_tiles - 1, std::true_type{});
+    for (int t = 0; t < n_tiles; ++t) {
+      if (t0 + t == n_tiles_all - 1) ew_tile(t, std::true_type{});
+      else ew_tile(t, std::false_type{});
+    }
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
-    drain_dq(n_tiles <= DQ_FLUSH);
+    drain_dq(!accum && n_tiles <= DQ_FLUSH);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -425,7 +435,10 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const int chunk = blockIdx.y;
   const long long base = (long long)chunk * m;
   const int j0 = blockIdx.x * 128;            // first key of this CTA
-  const int n_tiles = (m + 31) / 32;
+  const int n_tiles_all = (m + 31) / 32;       // gridDim.z > 1: query tiles split over z, partial dK / dV added (see the dQ kernel)
+  const int t0 = (int)((long long)n_tiles_all * blockIdx.z / gridDim.z);
+  const int n_tiles = (int)((long long)n_tiles_all * (blockIdx.z + 1) / gridDim.z) - t0;
+  const bool accum = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 12; ++i) mbar_init(smem_u32(bars + i), (i == 8 || i == 9) ? B5_EW : 1);
@@ -450,7 +463,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
           tma_load_2d(smem_u32(v_s + (part * 2 + kb) * B5_BOX128), &map_v, smem_u32(r_full), part * 64 + kb * 32, (int)(base + j0));
         }
       for (int t = 0; t < n_tiles; ++t) {
-        const int i0 = t * 32, st = t & 1;
+        const int i0 = (t0 + t) * 32, st = t & 1;
         uint8_t* qs = q_s + st * DKV_QSTAGE;
         mbar_wait(smem_u32(q_empty + st), (uint32_t)((t >> 1) & 1) ^ 1);
         mbar_expect_tx(smem_u32(q_full + st), 8 * B5_BOX32);
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   } else if (warp == 3) {
     if (lane == 0) {
       for (int t = 0; t < n_tiles; ++t) {
-        const int i0 = t * 32;
+        const int i0 = (t0 + t) * 32;
         mbar_wait(smem_u32(t_empty), (uint32_t)(t & 1) ^ 1);
         mbar_expect_tx(smem_u32(t_full), 4 * B5_BOX64);
         for (int part = 0; part < 2; ++part) {
@@ -554,13 +567,13 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       if (drain) {
         mbar_wait(smem_u32(acc_done), (uint32_t)((t - 1) & 1));
         tcgen05_fence_after();
-        drain_one(256, dv, 1.f, t == DKV_FLUSH);
-        drain_one(384, dk, scale, t == DKV_FLUSH);
+        drain_one(256, dv, 1.f, !accum && t == DKV_FLUSH);
+        drain_one(384, dk, scale, !accum && t == DKV_FLUSH);
         tcgen05_fence_before();
       }
       // per-query statistics of the 8 columns of this warp (padded rows: lse = +huge -> probability exactly 0)
-      const float4 l0 = __ldg(lse4 + t * 8), l1 = __ldg(lse4 + t * 8 + 1);
-      const float4 d0 = __ldg(dl4 + t * 8), d1 = __ldg(dl4 + t * 8 + 1);
+      const float4 l0 = __ldg(lse4 + (t0 + t) * 8), l1 = __ldg(lse4 + (t0 + t) * 8 + 1);
+      const float4 d0 = __ldg(dl4 + (t0 + t) * 8), d1 = __ldg(dl4 + (t0 + t) * 8 + 1);
       const float lse_c[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
       const float dl_c[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
       mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
@@ -572,7 +585,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       b5_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(sp_free));
-      const uint32_t hq = (uint32_t)(t * 32 + cq * 8) * ATTN_DROP_CI;
+      const uint32_t hq = (uint32_t)((t0 + t) * 32 + cq * 8) * ATTN_DROP_CI;
       uint32_t ph_[8], pl_[8], sh_[8], sl_[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -598,8 +611,8 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     }
     mbar_wait(smem_u32(acc_full), 0);
     tcgen05_fence_after();
-    drain_one(256, dv, 1.f, n_tiles <= DKV_FLUSH);
-    drain_one(384, dk, scale, n_tiles <= DKV_FLUSH);
+    drain_one(256, dv, 1.f, !accum && n_tiles <= DKV_FLUSH);
+    drain_one(384, dk, scale, !accum && n_tiles <= DKV_FLUSH);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -656,7 +669,25 @@ int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const flo
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     g_b5_attr = 1;
   }
-  dim3 grid((m + 127) / 128, 4);
+  // split the inner loop over gridDim.z when the (tile, chunk) grid fills the last wave badly: pick the split count that
+  // minimises waves / split (ties -> fewer splits), and only if it buys at least 8 %
+  const int ctas = ((m + 127) / 128) * 4, sms = sm_count();
+  int split = 1;
+  double best = (double)((ctas + sms - 1) / sms);
+  const double base_cost = best;
+  for (int sp = 2; sp <= 6 && sp * 8 <= (m + 63) / 64; ++sp) {
+    const double cost = (double)((ctas * sp + sms - 1) / sms) / sp + 0.02 * sp;   // + per-split prologue
+    if (cost < best - 1e-9) { best = cost; split = sp; }
+  }
+  if (best > 0.92 * base_cost) split = 1;
+  static const int forced = getenv("SCAN_B200_ATTN_SPLIT") ? atoi(getenv("SCAN_B200_ATTN_SPLIT")) : 0;
+  if (forced > 0) split = forced;
+  if (split > 1) {   // partial results are added: outputs start from zero (nondeterministic fp32 add order across splits)
+    SCAN_CUDA_CHECK(cudaMemsetAsync(dq, 0, sizeof(float) * 4ull * m * 64, st));
+    SCAN_CUDA_CHECK(cudaMemsetAsync(dk, 0, sizeof(float) * 4ull * m * 64, st));
+    SCAN_CUDA_CHECK(cudaMemsetAsync(dv, 0, sizeof(float) * 4ull * m * 64, st));
+  }
+  dim3 grid((m + 127) / 128, 4, split);
   if (drop_p > 0.f) {
     attn_bwd_dq_t5_kernel<true><<<grid, B5_THREADS, DQ_SMEM, st>>>(mq128, mdo128, mk64, mv64, mkt, lse, delta, m, scale, drop_p, seed, dq);
     SCAN_LAUNCH_CHECK("attn_bwd_dq_t5_kernel");
