@@ -28,6 +28,7 @@ struct DbWs {
   int* parent;         // [cap]
   int* cid;            // [cap] cluster id of roots / scan buffer
   int* block_cnt2;     // [cap/1024 + 1]
+  unsigned long long* re_list;   // [DB_RE_CAP] deferred exact re-evaluations: (i << 32) | j
   long long wpr;       // words per adjacency row
 };
 
@@ -53,6 +54,7 @@ static long long dbws_layout(long long cap, long long n_entries, int dim, char* 
   w.parent = (int*)take(cap * 4);
   w.cid = (int*)take(cap * 4);
   w.block_cnt2 = (int*)take((cap / DB_SB + 2) * 4);
+  w.re_list = (unsigned long long*)take((long long)DB_RE_CAP * 8);
   w.wpr = wpr;
   if (ws) *ws = w;
   return off;
@@ -565,7 +567,7 @@ static int cluster_points(const DbWs& ws, const float* points, const float* sq, 
     db_adj_kernel<<<4 * sms, 256, 0, st>>>(points, sq, info, n_fixed, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w);
     SCAN_LAUNCH_CHECK("db_adj_kernel");
   } else {
-    int rc = launch_db_adj_tc(points, sq, info, n_fixed, cap, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w, st);
+    int rc = launch_db_adj_tc(points, sq, info, n_fixed, cap, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w, ws.re_list, st);
     if (rc == SCAN_ENOTSUP) {  // point width other than 256: FFMA tiles
       db_adj_kernel<<<4 * sms, 256, 0, st>>>(points, sq, info, n_fixed, dim, eps2f, eps * eps, ws.wpr, ws.adj, info_w);
       SCAN_LAUNCH_CHECK("db_adj_kernel");

@@ -19,7 +19,11 @@ static __device__ __noinline__ bool db_exact_within(const float* __restrict__ a,
 }
 
 
+// capacity of the deferred re-evaluation list of the tensor-core distance kernel (pairs inside the tf32 error band);
+// pairs beyond it are re-evaluated inline
+constexpr int DB_RE_CAP = 1 << 21;
+
 int launch_db_adj_tc(const float* points, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
-                     long long wpr, uint32_t* adj, int* info_w, cudaStream_t st);
+                     long long wpr, uint32_t* adj, int* info_w, unsigned long long* re_list, cudaStream_t st);
 
 }  // namespace scan

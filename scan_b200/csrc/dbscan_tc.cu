@@ -26,12 +26,32 @@ constexpr int G_DIM = 256;
 constexpr int G_KB = G_DIM / GK;                 // 8 k-blocks
 constexpr int G_BOX_BYTES = GT * GK * 4;         // 16 KB
 constexpr int G_A_BYTES = G_KB * G_BOX_BYTES;    // 128 KB resident A tile
-constexpr int G_STAGES = 4;                      // B ring
+constexpr int G_STAGES = 4;                      // B ring (6 stages measured: no change)
 constexpr int G_SMEM = 1024 + G_A_BYTES + G_STAGES * G_BOX_BYTES + 1024;
 constexpr int G_EPI_WARPS = 16;                 // epilogue warp e: TMEM lane quarter e % 4, 32-column block e / 4
 constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;
 constexpr int DB_CHUNK = 48;                     // column blocks per unit
 constexpr uint32_t G_IDESC = umma_idesc_tf32(GT, GT);
+
+// packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -99,8 +119,10 @@ __device__ __noinline__ bool warp_exact_within(const float* __restrict__ a, cons
 
 __global__ void __launch_bounds__(G_THREADS, 1)
     db_adj_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ points, const float* __restrict__ sq,
-                     const int* info, int n_fixed, float eps2f, double eps2, long long wpr, uint32_t* __restrict__ adj, int* info_w) {
+                     const int* info, int n_fixed, float eps2f, double eps2, long long wpr, uint32_t* __restrict__ adj, int* info_w,
+                     unsigned long long* __restrict__ re_list) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float4 colv[G_EPI_WARPS][16];   // per epilogue warp: 16 column pairs (sq_c, sq_c+1, 2.2e-3 sq_c, 2.2e-3 sq_c+1)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_tile = smem;
   uint8_t* stages = smem + G_A_BYTES;
@@ -203,7 +225,6 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     const int c0 = (e >> 2) * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int n_re = 0;
     UnitIter it(nt);
     int row, jb0, jb1;
     while (it.next(row, jb0, jb1)) {
@@ -220,15 +241,36 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         tcgen05_fence_before();
         mbar_arrive(smem_u32(acc_empty + acc));   // the accumulator block is in registers
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        // pass 1: d = d2 - eps^2 = (si + sj - eps^2) - 2 g ; within <=> d < 0 ; unsure <=> |d| <= tol
+        // pass 1: d = d2 - eps^2 = ((si - eps^2) + sj) - 2 g ; within <=> d < 0 ; unsure <=> |d| < tol = (2.2e-3 si + k) + 2.2e-3 sj.
+        // The epilogue is the issue-bound part of this kernel (ncu: the MMA warp never waits for operands, the epilogue warps
+        // ran ~21 instructions per entry): the per-column terms come from shared memory two columns per 128-bit broadcast
+        // load, the arithmetic is packed fp32x2 (FADD2 / FFMA2), and the two bit masks are assembled from SIGN bits with a
+        // shift-in (entries exactly on a boundary are inside the band and re-evaluated exactly anyway).
+        __syncwarp();
+        {
+          float* slot = reinterpret_cast<float*>(&colv[e][lane >> 1]);
+          slot[lane & 1] = sj_lane;
+          slot[2 + (lane & 1)] = 2.2e-3f * sj_lane;
+        }
+        __syncwarp();
         uint32_t word = 0, unsure = 0;
+        const unsigned long long a2 = pack2(si - eps2f, si - eps2f);
+        const float bq = fmaf(2.2e-3f, si, 1e-6f * eps2f);
+        const unsigned long long b2 = pack2(bq, bq), m2 = pack2(-2.f, -2.f);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float t = si + __shfl_sync(0xffffffffu, sj_lane, c);
-          const float d = fmaf(-2.f, g[c], t - eps2f);
-          const float tol = fmaf(2.2e-3f, t, 1e-6f * eps2f);
-          word |= (d < 0.f ? 1u : 0u) << c;
-          unsure |= (fabsf(d) <= tol ? 1u : 0u) << c;
+        for (int cp = 0; cp < 16; ++cp) {
+          const float4 v = colv[e][cp];
+          const unsigned long long t2 = add2(a2, pack2(v.x, v.y));
+          const unsigned long long d2 = fma2(m2, pack2(g[2 * cp], g[2 * cp + 1]), t2);
+          const unsigned long long tol2 = add2(b2, pack2(v.z, v.w));
+          float d0, d1, t0, t1;
+          unpack2(d2, d0, d1);
+          unpack2(tol2, t0, t1);
+          const float e0 = fabsf(d0) - t0, e1 = fabsf(d1) - t1;
+          word = (word >> 1) | (__float_as_uint(d0) & 0x80000000u);
+          unsure = (unsure >> 1) | (__float_as_uint(e0) & 0x80000000u);
+          word = (word >> 1) | (__float_as_uint(d1) & 0x80000000u);
+          unsure = (unsure >> 1) | (__float_as_uint(e1) & 0x80000000u);
         }
         // validity: columns beyond n, rows beyond n; the diagonal is always "within" and never rechecked
         const int ncol = n - (j0 + c0);
@@ -238,9 +280,37 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         const uint32_t diag = (dcol >= 0 && dcol < 32) ? (1u << dcol) : 0u;
         word = (word | diag) & rowmask;
         unsure = unsure & rowmask & ~diag;
-        // pass 2 (rolled): exact re-evaluation of the in-band pairs by the whole warp
+        // pass 2: the in-band pairs need sklearn's float64 test.  Doing it here puts a chain of dependent global loads into
+        // the tile loop, and every tile waits for its slowest warp (measured: 16 pairs per tile on average tripled the tile
+        // time).  The pairs are appended to a work list instead (one atomic per warp and tile) and db_recheck_kernel flips
+        // the provisional bits afterwards with full parallelism; only when the list is full are they evaluated inline.
+        {
+          const int cnt = __popc(unsure);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(info_w + 5, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            int slot = base + incl - cnt;
+            uint32_t bits = unsure, keep = 0;
+            while (bits) {
+              const int c = __ffs(bits) - 1;
+              bits &= bits - 1;
+              if (slot < DB_RE_CAP) re_list[slot] = ((unsigned long long)(uint32_t)i << 32) | (uint32_t)(j0 + c0 + c);
+              else keep |= 1u << c;
+              ++slot;
+            }
+            unsure = keep;
+          }
+        }
         uint32_t lanes = __ballot_sync(0xffffffffu, unsure != 0u);
-        while (lanes) {
+        while (lanes) {   // overflow of the work list only
           const int src = __ffs(lanes) - 1;
           lanes &= lanes - 1;
           uint32_t bits = __shfl_sync(0xffffffffu, unsure, src);
@@ -250,19 +320,35 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             bits &= bits - 1;
             const bool r = warp_exact_within(pi, points + (long long)(j0 + c0 + c) * G_DIM, eps2, lane);
             if (lane == src) word = (word & ~(1u << c)) | ((r ? 1u : 0u) << c);
-            ++n_re;
           }
         }
         if (i < n) adj[(long long)i * wpr + ((j0 + c0) >> 5)] = word;
       }
     }
-    if (lane == 0 && n_re) atomicAdd(info_w + 5, n_re);
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * GT));
+  }
+}
+
+// exact float64 re-evaluation of the deferred in-band pairs: one warp per pair, flips the provisional bit when it is wrong
+__global__ void __launch_bounds__(256) db_recheck_kernel(const float* __restrict__ points, const int* __restrict__ info_w, double eps2,
+                                                         long long wpr, const unsigned long long* __restrict__ re_list,
+                                                         uint32_t* __restrict__ adj) {
+  const int n_re = min(info_w[5], DB_RE_CAP);
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < n_re; p += gridDim.x * wpb) {
+    const unsigned long long e = re_list[p];
+    const int i = (int)(e >> 32), j = (int)(e & 0xffffffffu);
+    const bool r = warp_exact_within(points + (long long)i * G_DIM, points + (long long)j * G_DIM, eps2, lane);
+    if (lane == 0) {
+      uint32_t* w = adj + (long long)i * wpr + (j >> 5);
+      const uint32_t bit = 1u << (j & 31);
+      if ((((*w) & bit) != 0u) != r) atomicXor(w, bit);
+    }
   }
 }
 
@@ -293,7 +379,7 @@ __global__ void __launch_bounds__(256) db_mirror_kernel(const int* info, int n_f
 static int g_adj_attr = 0;
 
 int launch_db_adj_tc(const float* points, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
-                     long long wpr, uint32_t* adj, int* info_w, cudaStream_t st) {
+                     long long wpr, uint32_t* adj, int* info_w, unsigned long long* re_list, cudaStream_t st) {
   if (dim != G_DIM) return SCAN_ENOTSUP;  // callers fall back to the FFMA tile kernel for other widths
   if (((uintptr_t)points & 15) || wpr % 4) return SCAN_EINVAL;
   CUtensorMap map;
@@ -303,8 +389,10 @@ int launch_db_adj_tc(const float* points, const float* sq, const int* info, int 
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(db_adj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     g_adj_attr = 1;
   }
-  db_adj_tc_kernel<<<sm_count(), G_THREADS, G_SMEM, st>>>(map, points, sq, info, n_fixed, eps2f, eps2, wpr, adj, info_w);
+  db_adj_tc_kernel<<<sm_count(), G_THREADS, G_SMEM, st>>>(map, points, sq, info, n_fixed, eps2f, eps2, wpr, adj, info_w, re_list);
   SCAN_LAUNCH_CHECK("db_adj_tc_kernel");
+  db_recheck_kernel<<<8 * sm_count(), 256, 0, st>>>(points, info_w, eps2, wpr, re_list, adj);
+  SCAN_LAUNCH_CHECK("db_recheck_kernel");
   db_mirror_kernel<<<8 * sm_count(), 256, 0, st>>>(info, n_fixed, wpr, adj);
   SCAN_LAUNCH_CHECK("db_mirror_kernel");
   return SCAN_OK;
