@@ -109,10 +109,13 @@ def pretrain(module, feats, targets, steps):
     fit_trained_like(module, [f[:1] for f in feats], targets[:1])
 
 
-def one_step(module, src, src_targets, tgt, cots):
-    """source fwd+bwd, target fwd+bwd.  Cotangents stand in for the FCOS head / discriminator gradients."""
+def one_step(module, src, src_targets, tgt, cots, ready=None):
+    """source fwd+bwd, target fwd+bwd.  Cotangents stand in for the FCOS head / discriminator gradients.
+    ready: optional (event, event): the copy-stream events after which the source / target inputs are valid."""
     res = []
-    for mode, feats in (("source", src), ("target", tgt)):
+    for idx, (mode, feats) in enumerate((("source", src), ("target", tgt))):
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready[idx])
         feats = [f.requires_grad_(True) for f in feats]
         if mode == "source":
             out = module(None, feats, targets=src_targets, mode="source")
@@ -266,21 +269,24 @@ def main():
         with torch.cuda.stream(copy_stream):
             if consumed[b] is not None:
                 copy_stream.wait_event(consumed[b])
-            for d_, h_ in zip(bufs[b][0] + bufs[b][1], src_h + tgt_h):
-                d_.copy_(h_, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return ev
+            evs = []
+            for dst, src_ in ((bufs[b][0], src_h), (bufs[b][1], tgt_h)):     # the source pass can start before the target batch is in
+                for d_, h_ in zip(dst, src_):
+                    d_.copy_(h_, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                evs.append(ev)
+        return evs
 
     barrier()
     f0.record()
     ready = stage(0)
     for i in range(args.steps):
         b_ = i & 1
-        main_stream.wait_event(ready)
+        cur = ready
         if i + 1 < args.steps:
             ready = stage(b_ ^ 1)
-        res = one_step(module, [x.detach() for x in bufs[b_][0]], src_t, [x.detach() for x in bufs[b_][1]], cots)
+        res = one_step(module, [x.detach() for x in bufs[b_][0]], src_t, [x.detach() for x in bufs[b_][1]], cots, ready=cur)
         consumed[b_] = torch.cuda.Event()
         consumed[b_].record(main_stream)
         host = [r.cpu() for r in res if r is not None]

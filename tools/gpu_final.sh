@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout -k 10 "$TMO" "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?"; tail -n "${TAILN:-12}" gpurun_out/$name.log; }
+TMO=900 TAILN=3 run gpu_tests python -m pytest tests -m gpu -q --tb=short
+TMO=300 TAILN=2 run smoke python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
+TMO=900 TAILN=1 run bench_full python bench.py
+TMO=600 TAILN=1 run bench_ref python bench.py --impl reference --steps 2 --warmup 1
+TMO=300 TAILN=30 run microbench python tools/bench_kernels.py 8
