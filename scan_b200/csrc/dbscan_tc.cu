@@ -11,10 +11,12 @@
 //   * fp32 accumulators in TMEM, 2 x 128 columns, so the epilogue of one tile overlaps the MMAs of the next.
 //
 // Exactness: the tensor core truncates the fp32 operands to tf32 (<= 2^-10 relative per operand), so a Gram entry is
-// only trusted outside the band |d2 - eps^2| > 2.2e-3 (|p_i|^2 + |p_j|^2); pairs inside the band are re-evaluated
-// exactly as sklearn does (float64 accumulation of the fp32 inputs) by the WHOLE WARP cooperatively (8 dims per lane,
-// shuffle reduction) -- a per-thread recheck serialises 256-step fp64 loops behind one lane (measured 13 ms).
-// Labels stay bit-exact with sklearn (tests/test_gpu_kernels.py::test_dbscan_*).
+// only trusted outside the band |d2 - eps^2| > 2.2e-3 (|p_i|^2 + |p_j|^2); pairs inside the band get a provisional bit and
+// are appended to a work list; db_recheck_kernel re-evaluates them exactly as sklearn does (float64 accumulation of the
+// fp32 inputs, one warp per pair: 8 dims per lane, shuffle reduction) and flips the bits that were wrong.  (History: a
+// per-thread recheck inside the epilogue serialised 256-step fp64 loops behind one lane, 13 ms; a warp-cooperative recheck
+// inside the epilogue still made every tile wait for its slowest warp's chain of dependent loads, 1.2 ms; deferred: 0.73 +
+// 0.18 ms.)  Labels stay bit-exact with sklearn (tests/test_gpu_kernels.py::test_dbscan_*).
 #include "dbscan_common.cuh"
 #include "tc_common.cuh"
 
