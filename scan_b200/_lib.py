@@ -77,7 +77,7 @@ _lib = None
 # kernels each entry point launches (memsets excluded): bench.py's gpu_launches is counted from this table
 LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_fcos_assign": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
             "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_attn_fwd": 2, "scan_attn_bwd": 4,
-            "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 21, "scan_dbscan_points": 15,
+            "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
             "scan_sigmoid_focal_fwd": 1, "scan_sigmoid_focal_bwd": 1, "scan_ensemble": 1}
 CALLS = {"n": 0, "launches": 0}
 
