@@ -8,7 +8,7 @@ Parity status: PINNED AGAINST THE REFERENCE ITSELF.  The reference's own tests h
 golden vector for this path, so the pin is (1) `tests/test_oracle_vs_reference.py`,
 which runs the unmodified reference (imported through `oracle/ref_shim.py`, only possible in
 the build container) and this file on the same seeded inputs, and (2) the committed fixtures
-under `tests/golden/` that `tools/make_golden.py` generated from the unmodified reference.
+under `tests/golden/` that `tests/tools/make_golden.py` generated from the unmodified reference.
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/fcos_core/).  Third-party arithmetic on the path: `sklearn.cluster.DBSCAN`

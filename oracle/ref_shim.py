@@ -1,7 +1,7 @@
 """Import shim for the UNMODIFIED reference middle head (TEST INFRASTRUCTURE ONLY).
 
 This file is part of the oracle, i.e. test infrastructure: only `tests/`,
-`tools/make_golden.py` and the validation of `oracle/condgraph_oracle.py` may use it.
+`tests/tools/make_golden.py` and the validation of `oracle/condgraph_oracle.py` may use it.
 It can only work inside the build container, where `/root/reference` is mounted;
 on the GPU box it raises `ReferenceUnavailable` and callers skip.
 

@@ -2,7 +2,7 @@
 through oracle/ref_shim.py, the CPU oracle, or the CUDA product) through the same seeded sequence of
 steps and reduces what it produced to a flat dict of numpy arrays.
 
-`tools/make_golden.py` runs it on the reference and commits the result under tests/golden/;
+`tests/tools/make_golden.py` runs it on the reference and commits the result under tests/golden/;
 the tests run it on the oracle (CPU) and on scan_b200 (GPU) and compare.
 """
 import hashlib
@@ -280,7 +280,7 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False):
         if err > rtol * scale + atol_scale * 1e-6:
             # Gradients that pass through a ReLU (head_in / head_out towers, both torch ops) are discontinuous: an
             # activation within ~1e-6 of zero gets the opposite mask on the GPU and on the CPU, which changes a FEW
-            # gradient entries by O(1) relative amounts (measured: tools/diag_grad.py; the same happens between the
+            # gradient entries by O(1) relative amounts (measured: tests/tools/diag_grad.py; the same happens between the
             # reference on CPU and the reference on GPU).  Such tensors pass if the outliers are sparse and the
             # relative L2 error is small; everything else must meet the max-norm bound.
             d = np.abs(g.astype(np.float64) - w.astype(np.float64))
@@ -292,7 +292,7 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False):
             # d(input features) and the head_in parameter gradients are produced by torch's OWN backward (cuDNN
             # backward-data / backward-filter, GroupNorm) from d(features_in) = "dfin", which is what the scan_b200
             # kernels produce and which is held to rtol above.  cuDNN's backward at the P3 shape differs from the CPU
-            # implementation by up to ~3e-3 relL2 on identical inputs (tools/diag_grad2.py: dfin agrees to 1e-6 while
+            # implementation by up to ~3e-3 relL2 on identical inputs (tests/tools/diag_grad2.py: dfin agrees to 1e-6 while
             # dfeat_l0 does not), so those torch-only tensors get a looser L2 bound.
             # "dfin" (total) additionally contains head_out's backward-data: one flipped ReLU at a coarse level (24
             # pixels at P6) touches a 3x3 neighbourhood x 256 channels, i.e. a third of the tensor.  The hot path's own

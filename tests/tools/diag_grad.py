@@ -1,8 +1,8 @@
 """Diagnostic: precision of torch's own CUDA ops (cuDNN conv fwd/bwd etc.) vs CPU under the tf32 flags, and
 per-key product-vs-oracle errors."""
 import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import torch.nn.functional as F
 

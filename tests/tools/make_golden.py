@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
 
-    PYTHONPATH=. python tools/make_golden.py [case ...]
+    PYTHONPATH=. python tests/tools/make_golden.py [case ...]
 
 Imports /root/reference through oracle/ref_shim.py, drives it through tests/harness.py:run_case
 (seeded inputs, fixture weights, dropout off) and stores the reduced results.  The fixtures are
@@ -13,7 +13,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
