@@ -427,12 +427,12 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
       mbar_arrive(smem_u32(s_empty + 0));
       const int j0 = t * T5_BK + cq * 16;
       const int lim = m - j0;
-      const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
+      [[maybe_unused]] const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         float p = t5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse2_row));
-        if (DROP) p = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? p * inv_keep : 0.f;
+        if constexpr (DROP) p = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? p * inv_keep : 0.f;
         if (LAST) p = e < lim ? p : 0.f;
         uint32_t u;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(p));

@@ -361,13 +361,13 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       mbar_arrive(smem_u32(sp_free));
       const int j0 = (t0 + t) * 64 + cq * 16;
       const int lim = m - j0;
-      const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
+      [[maybe_unused]] const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const float p = b5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse2));
         float dp = x[e];
-        if (DROP) dp = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? dp * inv_keep : 0.f;
+        if constexpr (DROP) dp = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? dp * inv_keep : 0.f;
         float ds = p * (dp - dl_r);
         if (LAST) ds = e < lim ? ds : 0.f;
         b5_split(ds, hi[e], lo[e]);
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       for (int e = 0; e < 8; ++e) {
         const float p = b5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse_c[e]));
         float pt = p, dp = x[e];
-        if (DROP) {
+        if constexpr (DROP) {
           const bool keep = attn_drop_mix(hkey ^ (hq + (uint32_t)e * ATTN_DROP_CI)) >= drop_thr;
           pt = keep ? p * inv_keep : 0.f;
           dp = keep ? dp * inv_keep : 0.f;
