@@ -383,20 +383,21 @@ __global__ void __launch_bounds__(256) db_flatten_kernel(const int* info, int n_
 // points that can be skipped for rows of the DOMINANT set: non-core points and core points whose (flattened) root is the
 // dominant root.  Two points with equal roots after the flatten stay in one set for ever, so the filter never drops a
 // necessary union; a poor choice of the dominant root only costs speed.
-__global__ void __launch_bounds__(1024) db_pick_root_kernel(const int* info, int n_fixed, int min_samples, const int* __restrict__ count,
-                                                            const int* __restrict__ parent, int* __restrict__ rstar) {
-  __shared__ int cand[1024];
-  __shared__ int best_v[32], best_c[32];
+constexpr int DB_PICK = 256;    // sampled core points that vote for the dominant root
+__global__ void __launch_bounds__(DB_PICK) db_pick_root_kernel(const int* info, int n_fixed, int min_samples, const int* __restrict__ count,
+                                                               const int* __restrict__ parent, int* __restrict__ rstar) {
+  __shared__ int cand[DB_PICK];
+  __shared__ int best_v[DB_PICK / 32], best_c[DB_PICK / 32];
   const int n = n_fixed >= 0 ? n_fixed : (info[4] ? 0 : info[0]);
   const int t = threadIdx.x;
-  const long long idx = n >= 1024 ? (long long)t * n / 1024 : (t < n ? t : -1);
+  const long long idx = n >= DB_PICK ? (long long)t * n / DB_PICK : (t < n ? t : -1);
   int c = -1;
   if (idx >= 0 && count[idx] >= min_samples) c = parent[idx];
   cand[t] = c;
   __syncthreads();
   int v = 0;
   if (c >= 0)
-    for (int k = 0; k < 1024; ++k) v += (cand[k] == c);
+    for (int k = 0; k < DB_PICK; ++k) v += (cand[k] == c);
   // block argmax of (votes, candidate)
   int bv = v, bc = c;
 #pragma unroll
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(1024) db_pick_root_kernel(const int* info, int
   if ((t & 31) == 0) { best_v[t >> 5] = bv; best_c[t >> 5] = bc; }
   __syncthreads();
   if (t == 0) {
-    for (int k = 1; k < 32; ++k)
+    for (int k = 1; k < DB_PICK / 32; ++k)
       if (best_v[k] > bv || (best_v[k] == bv && best_c[k] > bc)) { bv = best_v[k]; bc = best_c[k]; }
     rstar[0] = bv > 0 ? bc : -1;
   }
@@ -583,7 +584,7 @@ static int cluster_points(const DbWs& ws, const float* points, const float* sq, 
   SCAN_LAUNCH_CHECK("db_flatten_kernel");
   // scratch: the cluster-id array is not in use before db_roots_kernel; word 0 of block_cnt2 holds the dominant root
   uint32_t* dmask = (uint32_t*)ws.cid;
-  db_pick_root_kernel<<<1, 1024, 0, st>>>(info, n_fixed, min_samples, ws.count, ws.parent, ws.block_cnt2);
+  db_pick_root_kernel<<<1, DB_PICK, 0, st>>>(info, n_fixed, min_samples, ws.count, ws.parent, ws.block_cnt2);
   SCAN_LAUNCH_CHECK("db_pick_root_kernel");
   db_dom_mask_kernel<<<2 * sms, 256, 0, st>>>(info, n_fixed, cap, min_samples, ws.count, ws.parent, ws.block_cnt2, dmask);
   SCAN_LAUNCH_CHECK("db_dom_mask_kernel");

@@ -354,6 +354,21 @@ __global__ void __launch_bounds__(256) db_recheck_kernel(const float* __restrict
   }
 }
 
+// 32 x 32 bit-matrix transpose across a warp (lane r holds row r, bit c = column c): five butterfly steps that swap the
+// off-diagonal sub-blocks of size j (recursive block transpose; ~45 instructions instead of 32 ballots + selects)
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    const bool hi = (lane & j) != 0;
+    const uint32_t low = hi ? y : x, high = hi ? x : y;
+    const uint32_t t = ((low >> j) ^ high) & m;
+    x = hi ? (x ^ t) : (x ^ (t << j));
+  }
+  return x;
+}
+
 // adjacency is symmetric: the tile kernel wrote the 32x32 bit blocks (I, J) of tiles with tile(I) <= tile(J); this adds
 // the transposed blocks (J, I) for tile(I) < tile(J).  One warp per block: lane r loads row r's word, 32 ballots
 // transpose it, lane c stores row c of the mirrored block.  Memory-bound pass over n^2/16 bytes.
@@ -375,14 +390,7 @@ __global__ void __launch_bounds__(128) db_mirror_kernel(const int* info, int n_f
     __syncthreads();
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {     // block (rows w*32.., word jb) -> block (rows jb*32.., word w)
-      const uint32_t word = tin[w * 32 + lane][jb];
-      uint32_t mine = 0;
-#pragma unroll 8
-      for (int c = 0; c < 32; ++c) {
-        const uint32_t tw = __ballot_sync(0xffffffffu, (word >> c) & 1u);
-        if (lane == c) mine = tw;
-      }
-      tout[jb * 32 + lane][w] = mine;
+      tout[jb * 32 + lane][w] = warp_transpose32(tin[w * 32 + lane][jb], lane);
     }
     __syncthreads();
     const int gj = TJ * 128 + r;
