@@ -331,6 +331,8 @@ def main():
                                        "synthetic images per GPU per step, 800x1344 FPN features, 8 classes + bg" % (n, n),
                            "parallelism": "dp%d (image shards, prototype all-reduce)" % world, "settle_steps": args.settle,
                            "attention_dropout": args.dropout,
+                           "towers": "3x3 convolutions = cuDNN NHWC tf32 implicit GEMM (torch's default allow_tf32), "
+                                     "cudnn.benchmark %s" % ("on" if torch.backends.cudnn.benchmark else "off"),
                            "e2e_input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i",
                            "l2_note": "inputs 2x%d MB per step exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
