@@ -72,3 +72,43 @@ def test_state_dict_matches_reference_contract():
         assert k in sd
     from oracle.condgraph_oracle import build_oracle
     assert list(build_oracle(scan_cfg("c2f")).state_dict().keys()) == list(sd.keys())
+
+
+def test_rows_layout_views_and_join_host_logic():
+    """The zero-copy plumbing of the rows layout is plain torch view arithmetic: a level's slice of the rows matrix IS a
+    channels-last [N,C,H,W] tensor, and join_rows recognises adjacent views of one buffer (no copy) vs anything else."""
+    import torch
+    from scan_b200 import ops
+    shapes = [(5, 7), (3, 4), (2, 2)]
+    geo = ops.Geometry(shapes, [8, 16, 32], 2)
+    rows = torch.arange(geo.R * ops.C, dtype=torch.float32).reshape(geo.R, ops.C)
+    views = ops.level_views(geo, rows)
+    for l, (h, w) in enumerate(shapes):
+        v = views[l]
+        assert v.shape == (2, ops.C, h, w) and v.is_contiguous(memory_format=torch.channels_last)
+        assert v.data_ptr() == rows.data_ptr() + geo.row_off[l] * ops.C * 4
+        # the reference's flattening: features[l].permute(0, 2, 3, 1).reshape(-1, C)   (loss.py:440)
+        assert torch.equal(v.permute(0, 2, 3, 1).reshape(-1, ops.C), rows[geo.row_off[l]:geo.row_off[l + 1]])
+        assert ops.nhwc_dense(v) is v
+    joined = ops._JoinRows.apply(geo, *views)
+    assert joined.data_ptr() == rows.data_ptr() and torch.equal(joined, rows)            # adjacent views: zero-copy
+    separate = [v.clone(memory_format=torch.contiguous_format) for v in views]            # NCHW copies: concatenating path
+    joined2 = ops._JoinRows.apply(geo, *separate)
+    assert joined2.data_ptr() != separate[0].data_ptr() and torch.equal(joined2, rows)
+    # gradients come back as per-level views of the incoming [R, C] gradient
+    leaves = [s.clone().requires_grad_(True) for s in separate]
+    out = ops._JoinRows.apply(geo, *leaves)
+    cot = torch.randn(geo.R, ops.C)
+    (out * cot).sum().backward()
+    for l, (h, w) in enumerate(shapes):
+        want = cot[geo.row_off[l]:geo.row_off[l + 1]].view(2, h, w, ops.C).permute(0, 3, 1, 2)
+        assert torch.equal(leaves[l].grad, want)
+
+
+def test_launch_table_covers_every_compute_entry_point():
+    """bench.py's gpu_launches is counted from _lib.LAUNCHES: every entry point that launches kernels must be listed."""
+    no_kernels = {"scan_abi_version", "scan_strerror", "scan_last_cuda_error", "scan_init", "scan_condconv_num_partials"}
+    for name in _lib.SIGNATURES:
+        if name in no_kernels or name.endswith("_bytes") or name.endswith("_floats"):
+            continue
+        assert name in _lib.LAUNCHES and _lib.LAUNCHES[name] >= 1, name
