@@ -48,6 +48,7 @@ def fcos_assign(level_shapes, strides, boxes_per_image, labels_per_image):
         per_image = []
         for boxes, labels in zip(boxes_per_image, labels_per_image):
             boxes = boxes.float()
+            xs, ys = xs.to(boxes.device), ys.to(boxes.device)
             if boxes.shape[0] == 0:
                 raise RuntimeError("G == 0 is unsupported by the reference (empty min, loss.py:333)")
             area = (boxes[:, 2] - boxes[:, 0] + 1) * (boxes[:, 3] - boxes[:, 1] + 1)
@@ -60,7 +61,7 @@ def fcos_assign(level_shapes, strides, boxes_per_image, labels_per_image):
             ok = (mn > 0) & (mx >= lo) & (mx <= hi)
             cost = torch.where(ok, area[None, :].expand_as(mn), torch.full_like(mn, INF_AREA))
             best, idx = cost.min(dim=1)
-            lab = labels.long()[idx]
+            lab = labels.long().to(boxes.device)[idx]
             lab = torch.where(best == INF_AREA, torch.zeros_like(lab), lab)
             per_image.append(lab)
         out.append(torch.cat(per_image))
@@ -109,7 +110,7 @@ def source_node_indices(labels_per_level, with_bg=True):
                 sel = n
             else:
                 k = floor_linspace(n.numel() - 2, p.numel())
-                sel = n[torch.from_numpy(k)] if k.size else n[:0]   # negative k wraps like python indexing
+                sel = n[torch.from_numpy(k).to(n.device)] if k.size else n[:0]   # negative k wraps like python indexing
             neg.append((l, sel, torch.zeros_like(sel)))
     seq = (neg + pos) if with_bg else pos
     lv = torch.cat([torch.full_like(idx, l) for l, idx, _ in seq])
@@ -123,7 +124,7 @@ def gather_nodes(features, lv, rows):
     chunks = []
     # node order is a concatenation of per-level runs, so gather run by run
     start = 0
-    lv_np = lv.numpy()
+    lv_np = lv.cpu().numpy()
     while start < len(lv_np):
         end = start
         while end < len(lv_np) and lv_np[end] == lv_np[start]:
@@ -253,20 +254,21 @@ def dbscan_location_mask(act_fg, feature, eps, thr, use_sklearn=True):
     act_fg = act_fg.detach()
     feature = feature.detach()
     flat, pts = dbscan_points(act_fg, feature, thr)
-    val = torch.zeros(n * cls * h * w)
+    dev = act_fg.device      # on CUDA this is the reference's own D2H -> DBSCAN -> H2D round trip (loss.py:414-421)
+    val = torch.zeros(n * cls * h * w, device=dev)
     val[flat] = 1.0
     labels = None
     if pts.numel() and bool(pts.bool().any()):
         if use_sklearn:
             from sklearn.cluster import DBSCAN
-            labels = DBSCAN(eps=eps, n_jobs=-1).fit_predict(pts.numpy())
+            labels = DBSCAN(eps=eps, n_jobs=-1).fit_predict(pts.cpu().numpy())
         elif _c_dbscan():
-            labels = dbscan_labels_c(pts.numpy(), eps)
+            labels = dbscan_labels_c(pts.cpu().numpy(), eps)
         else:
-            labels = dbscan_labels(pts.numpy(), eps)
+            labels = dbscan_labels(pts.cpu().numpy(), eps)
         y = labels.copy()
         y[y < 0] = 1                       # loss.py:417: noise kept as "1", cluster 0 dropped
-        val[flat] = torch.from_numpy(y.astype(np.float32))
+        val[flat] = torch.from_numpy(y.astype(np.float32)).to(dev)
     pos = val.reshape(n, cls, h, w).permute(0, 2, 3, 1).reshape(-1, cls).sum(-1).bool()
     return pos, flat, labels
 
@@ -293,7 +295,7 @@ def target_node_indices(act_maps, features, eps, thr, use_sklearn=True, sampling
             kidx = floor_linspace(n_.numel() - 2, p.numel())
             if n_.numel() == 0:
                 raise IndexError("no negative location left at level %d (loss.py:503-504)" % l)
-            sel = n_[torch.from_numpy(kidx)]
+            sel = n_[torch.from_numpy(kidx).to(n_.device)]
             pos.append((l, p, plab))
             neg.append((l, sel, torch.zeros_like(sel)))
     if not pos:
@@ -571,8 +573,8 @@ class OracleCondGraph(nn.Module):
             if self.training and a.p_drop > 0:
                 m = nodes.shape[0]
                 keep = 1.0 - a.p_drop
-                da = torch.bernoulli(torch.full((a.heads, m, m), keep)) / keep
-                do = torch.bernoulli(torch.full((m, nodes.shape[1]), keep)) / keep
+                da = torch.bernoulli(torch.full((a.heads, m, m), keep, device=nodes.device)) / keep
+                do = torch.bernoulli(torch.full((m, nodes.shape[1]), keep, device=nodes.device)) / keep
             out = chunked_attention(nodes, params, a.heads, da, do)
             if mh.GCN_SHORTCUT:
                 out = out + nodes
@@ -638,8 +640,8 @@ class OracleCondGraph(nn.Module):
         if mh.ACT_LOSS == "softmaxFL":
             return mh.ACT_LOSS_WEIGHT * softmax_focal_loss(flat, lab)
         if mh.ACT_LOSS == "sigmoidFL":
-            onehot = torch.zeros(lab.numel(), 2)
-            onehot[torch.arange(lab.numel()), lab] = 1
+            onehot = torch.zeros(lab.numel(), 2, device=flat.device)
+            onehot[torch.arange(lab.numel(), device=flat.device), lab] = 1
             return mh.ACT_LOSS_WEIGHT * bce_focal_loss(flat, onehot)
         return None
 

@@ -118,7 +118,6 @@ class MultiHeadAttention(nn.Module):
         self.linear_final = nn.Linear(model_dim, model_dim)
         self.layer_norm = nn.LayerNorm(model_dim)
         self.p_drop = dropout
-        self._calls = 0
 
     def forward(self, x):
         """x [M,256] (the reference passes (key, value, query) = (x, x, x), condgraph.py:392)."""
@@ -127,8 +126,9 @@ class MultiHeadAttention(nn.Module):
         p = self.p_drop if self.training else 0.0
         seed = 0
         if p > 0:
-            seed = int(torch.initial_seed() * 1000003 + self._calls) & 0x7FFFFFFFFFFFFFFF
-            self._calls += 1
+            # one 63-bit draw per call from torch's default CPU generator: the masks follow torch.manual_seed / get_rng_state /
+            # fork_rng and a checkpoint's RNG state like nn.Dropout does, and differ per rank when the ranks' generators do
+            seed = int(torch.randint(0, 0x7FFFFFFFFFFFFFFF, (1,), dtype=torch.int64).item())
         ctx = ops.chunked_attention(q, k, v, scale, p, seed)
         out = self.linear_final(ctx)
         out = F.dropout(out, p, self.training)
@@ -171,7 +171,12 @@ class GRAPHModule(nn.Module):
         self.dbscan_eps = float(mh.DBSCAN_EPS)
         self.dbscan_thr = float(mh.DBSCAN_THR)
         self.plabel_th = float(cfg.SOLVER.MIDDLE_HEAD.PLABEL_TH[0])
-        self.dbscan_cap = 65536          # points per level the DBSCAN workspace is sized for
+        # DBSCAN workspace capacity in points per level (adjacency = cap^2 / 8 bytes: 0.5 GB at 65 536, 1.25 GB at 100 000).
+        # Not a limit: a level that selects more points grows the workspace and is re-run (see _sample_target); the
+        # optional key MODEL.MIDDLE_HEAD.DBSCAN_MAX_POINTS only presets the initial size.
+        self.dbscan_cap = int(getattr(mh, "DBSCAN_MAX_POINTS", 65536))
+        self.dbscan_cap_limit = 700000   # 61 GB of adjacency bits: beyond this the O(n^2) clustering itself is hopeless
+        self.record = False              # keep intermediate results of the last call in self.last (parity tests, bench stats)
         channel = mh.PROTO_CHANNEL
         hidden = mh.COND_HIDDEN_CHANNEL
         if channel != ops.C or in_channels != ops.C:
@@ -220,7 +225,7 @@ class GRAPHModule(nn.Module):
         for layer in (self.cond_2, self.proto_cls, self.proto_cls_hidden):
             nn.init.normal_(layer.weight, std=0.01)
             nn.init.constant_(layer.bias, 0)
-        self.last = {}     # intermediate results of the last call (labels, node indices, masks) for parity tests
+        self.last = {}     # intermediate results of the last call, only filled when self.record is set
         self.dist_group = None   # set by scan_b200.dist.attach() to all-reduce the prototype sums
 
     # ------------------------------------------------------------------ manifestation (condgraph.py:313-336)
@@ -343,13 +348,15 @@ class GRAPHModule(nn.Module):
         self._record_nodes(geo, smp, labels=labels)
         pos_points = ops.gather_rows(rows, smp.node_rows)
         node_loss, packed, _ = self._forward_gcns(pos_points, smp.node_labels)
-        self.last["prototype_batch"] = self.update_prototype_ensemble(packed)
+        proto_batch = self.update_prototype_ensemble(packed)
         weight, bias = self._split_kernel(self.get_conded_weight())
-        self.last["conded_weight"] = weight
+        if self.record:
+            self.last["prototype_batch"], self.last["conded_weight"] = proto_batch, weight
         with_loss = self.act_loss_cfg in ("softmaxFL", "sigmoidFL")
         acts, act_loss, flags = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode(),
                                              labels if with_loss else None, self.lamda2)
-        self.last["act_loss_flags"] = flags
+        if self.record:
+            self.last["act_loss_flags"] = flags
         out = self.features_post_processing(features, acts)
         return out, (node_loss, 0), act_loss, acts
 
@@ -385,13 +392,7 @@ class GRAPHModule(nn.Module):
         plabel = torch.empty((geo.R,), device=dev, dtype=torch.int64)
         infos = []
         if self.target_sampling == "dbscan":
-            caps = [min(geo.n_images * (k - 1) * h * w, self.dbscan_cap) for h, w in geo.shapes]
-            ws = ops.dbscan_workspace(max(caps), dev)
-            for l in range(len(geo.shapes)):
-                a, b = geo.row_off[l], geo.row_off[l + 1]
-                _, info = ops.dbscan_level(rows.detach()[a:b], acts[l].detach(), self.dbscan_thr, self.dbscan_eps, caps[l],
-                                           pos_mask[a:b], plabel[a:b], ws)
-                infos.append(info)
+            infos = self._dbscan_levels(geo, rows, acts, pos_mask, plabel)
         elif self.target_sampling == "score_threshold":
             # loss.py:479-481 (alternative sampler; torch ops, not a north-star kernel)
             for l, act in enumerate(acts):
@@ -403,12 +404,37 @@ class GRAPHModule(nn.Module):
             raise KeyError("unknown target labels!")   # 'mean_shift' / 'kmeans' samplers are out of scope
         smp = ops.sample_nodes(geo, 1, True, pos_mask=pos_mask, plabel=plabel)
         if infos:
+            # ONE deferred status read for all levels (the sampling above already synchronised).  A level that selected more
+            # points than the workspace holds wrote nothing: grow the workspace to what it asked for and redo the pass.
             info = torch.stack(infos).cpu()
             if bool((info[:, 4] != 0).any()):
-                raise RuntimeError("DBSCAN point capacity (%d per level) exceeded: raise module.dbscan_cap" % self.dbscan_cap)
-            self.last["dbscan_info"] = info
-            self.last["dbscan_masks"] = [m.bool() for m in geo.split_rows(pos_mask)]
+                need = int(info[:, 0].max())
+                if need > self.dbscan_cap_limit:
+                    raise RuntimeError("DBSCAN: %d points at one level (limit %d: the adjacency alone would take %.0f GB)"
+                                       % (need, self.dbscan_cap_limit, need * need / 8e9))
+                self.dbscan_cap = min(self.dbscan_cap_limit, (need * 5 // 4 + 1023) // 1024 * 1024)
+                infos = self._dbscan_levels(geo, rows, acts, pos_mask, plabel)
+                smp = ops.sample_nodes(geo, 1, True, pos_mask=pos_mask, plabel=plabel)
+                info = torch.stack(infos).cpu()
+                if bool((info[:, 4] != 0).any()):
+                    raise RuntimeError("DBSCAN workspace growth failed")
+            if self.record:
+                self.last["dbscan_info"] = info
+                self.last["dbscan_masks"] = [m.bool() for m in geo.split_rows(pos_mask)]
         return smp
+
+    def _dbscan_levels(self, geo, rows, acts, pos_mask, plabel):
+        """scan_dbscan_level per FPN level into the shared pos_mask / plabel vectors; returns the per-level info records."""
+        k = self.used_num_classes
+        caps = [min(geo.n_images * (k - 1) * h * w, self.dbscan_cap) for h, w in geo.shapes]
+        ws = ops.dbscan_workspace(max(caps), rows.device)
+        infos = []
+        for l in range(len(geo.shapes)):
+            a, b = geo.row_off[l], geo.row_off[l + 1]
+            _, info = ops.dbscan_level(rows.detach()[a:b], acts[l].detach(), self.dbscan_thr, self.dbscan_eps, caps[l],
+                                       pos_mask[a:b], plabel[a:b], ws)
+            infos.append(info)
+        return infos
 
     def _forward_train_target(self, images, features, targets=None, return_maps=False):
         geo = ops.Geometry.of(features, self.fpn_strides)
@@ -458,7 +484,7 @@ class GRAPHModule(nn.Module):
             raise RuntimeError("scan_b200.GRAPHModule runs on CUDA only (no CPU fallback)")
         geo = ops.Geometry.of(features, self.fpn_strides)
         features = self.head_in.forward_levels(geo, ops.pack_levels(geo, features))
-        self.last = {"features_in": features}
+        self.last = {"features_in": features} if self.record else {}
         if self.training and targets and mode == "source":
             return self._forward_train_source(images, features, targets, return_maps)
         elif self.training and mode == "target" and forward_target:
@@ -467,6 +493,8 @@ class GRAPHModule(nn.Module):
 
     # ------------------------------------------------------------------ bookkeeping for tests
     def _record_nodes(self, geo, smp, labels=None):
+        if not self.record:
+            return
         if labels is not None:
             self.last["labels"] = geo.split_rows(labels)
         if smp.n_nodes == 0:

@@ -11,14 +11,6 @@
 
 namespace scan {
 
-// mma.sync 3xTF32 versions (attention_tc.cu), selected with SCAN_B200_ATTN_TC=1.  Round-1 measurement (B200, M = 8.7 k):
-// fwd 4.37 ms vs 4.55 ms FFMA, bwd 9.37 vs 9.57 -- the legacy tensor path is bound by the per-fragment hi/lo splits and
-// 32-bit shared loads, and its q/k gradients sit at 1e-3 relL2 on the 40 k-node target case; the FFMA kernels below
-// therefore stay the default until the tcgen05 version lands.
-int launch_attn_fwd_tc(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
-                       float* lse, cudaStream_t st);
-int launch_attn_bwd_tc(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
-                       float scale, float drop_p, uint64_t seed, float* dq, float* dk, float* dv, cudaStream_t st);
 // tcgen05 version (attention_t5.cu): used by scan_attn_fwd when the caller provides a workspace
 int64_t attn_t5_workspace_bytes(int m);
 int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
@@ -26,11 +18,6 @@ int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, fl
 int64_t attn_t5_bwd_workspace_bytes(int m);
 int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const float* lse, const float* delta, const float* d_ctx, int m,
                        float scale, float drop_p, uint64_t seed, float* dq, float* dk, float* dv, void* workspace, cudaStream_t st);
-static int attn_simt() {
-  static const int v = getenv("SCAN_B200_ATTN_TC") ? !atoi(getenv("SCAN_B200_ATTN_TC")) : 1;
-  return v;
-}
-
 constexpr int AT_D = 64;   // sub-token width
 constexpr int AT_T = 64;   // tile edge
 constexpr int AT_LD = 68;  // padded leading dimension (floats): 272-byte rows, 16-byte aligned
@@ -303,12 +290,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
   }
 }
 
-static int g_attn_attr = 0;
+static unsigned long long g_attn_attr = 0;
 static int set_attn_attrs() {
-  if (g_attn_attr) return SCAN_OK;
+  if (!first_use_on_device(&g_attn_attr)) return SCAN_OK;
   SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * AT_TILE * 4));
   SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * AT_TILE * 4));
-  g_attn_attr = 1;
   return SCAN_OK;
 }
 
@@ -327,7 +313,6 @@ extern "C" int scan_attn_fwd(const float* q, const float* k, const float* v, int
     if (workspace_bytes < attn_t5_workspace_bytes(m)) return SCAN_ECAPACITY;
     return launch_attn_fwd_t5(q, k, v, m, scale, dropout_p, seed, ctx, lse, workspace, (cudaStream_t)stream);
   }
-  if (!attn_simt()) return launch_attn_fwd_tc(q, k, v, m, scale, dropout_p, seed, ctx, lse, (cudaStream_t)stream);
   int rc = set_attn_attrs();
   if (rc) return rc;
   dim3 grid((m + AT_T - 1) / AT_T, 4);
@@ -353,7 +338,6 @@ extern "C" int scan_attn_bwd(const float* q, const float* k, const float* v, con
     return launch_attn_bwd_t5(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv, workspace, st);
   }
   SCAN_CUDA_CHECK(cudaMemsetAsync(dq, 0, sizeof(float) * n_rows * AT_D, st));
-  if (!attn_simt()) return launch_attn_bwd_tc(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv, st);
   dim3 grid((m + AT_T - 1) / AT_T, 4);
   attn_bwd_kernel<<<grid, 256, 6 * AT_TILE * 4, st>>>(q, k, v, lse, delta_ws, d_ctx, m, scale, dropout_p, seed, dq, dk, dv);
   SCAN_LAUNCH_CHECK("attn_bwd_kernel");

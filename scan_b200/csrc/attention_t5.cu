@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
   }
 }
 
-static int g_t5_attr = 0;
+static unsigned long long g_t5_attr = 0;
 
 int64_t attn_t5_workspace_bytes(int m) {
   const long long mp = ((long long)m + 63) / 64 * 64;
@@ -487,10 +487,9 @@ int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, fl
   if (rc) return rc;
   rc = make_rowmajor_map(&mv, vt, 4ull * 128, (uint64_t)mp, 64);
   if (rc) return rc;
-  if (!g_t5_attr) {
+  if (first_use_on_device(&g_t5_attr)) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
-    g_t5_attr = 1;
   }
   dim3 grid((m + T5_BQ - 1) / T5_BQ, 4);
   if (drop_p > 0.f)

@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------- host side
-static int g_b5_attr = 0;
+static unsigned long long g_b5_attr = 0;
 
 int64_t attn_t5_bwd_workspace_bytes(int m) {
   const long long mp = ((long long)m + 63) / 64 * 64;
@@ -662,12 +662,11 @@ int launch_attn_bwd_t5(const float* q, const float* k, const float* v, const flo
   rc |= make_rowmajor_map(&mdot, dot, 4ull * 128, (uint64_t)mp, 64);
   rc |= make_rowmajor_map(&mqt, qt, 4ull * 128, (uint64_t)mp, 64);
   if (rc) return SCAN_ECUDA;
-  if (!g_b5_attr) {
+  if (first_use_on_device(&g_b5_attr)) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    g_b5_attr = 1;
   }
   // split the inner loop over gridDim.z when the (tile, chunk) grid fills the last wave badly: pick the split count that
   // minimises waves / split (ties -> fewer splits), and only if it buys at least 8 %

@@ -52,6 +52,16 @@ __device__ __forceinline__ int level_of_row(const Levels& lv, long long g) {
 
 void set_cuda_error(cudaError_t e, const char* where);
 int sm_count();
+// true the first time it is called on the current device for this mask (per-device one-shot work such as
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-device setting)
+inline bool first_use_on_device(unsigned long long* mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
 
 #define SCAN_CUDA_CHECK(expr)                                  \
   do {                                                         \

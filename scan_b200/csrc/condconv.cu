@@ -4,20 +4,14 @@
 // layers/sigmoid_focal_loss_wbg.py:7-64 (FocalLoss) and :148-177 (BCEFocalLoss).
 //
 // Forward = one skinny GEMM  logits[R, K] = rows[R, 256] . W[K, 256]^T  (K <= 16), HBM-bound (AI ~ 4 flop/B).
-//   * persistent CTAs, one per SM; tile = 128 pixels x 256 channels;
-//   * A (pixels x channels, K-major) streamed by TMA in 8 k-blocks of [128 x 32] fp32 = 16 KB with the 128-byte
-//     swizzle, 6-stage mbarrier ring (96 KB in flight per SM);
-//   * 3xTF32 error compensation so the tensor-core path keeps fp32-level accuracy (a plain tf32 read truncates the
-//     activations: measured 1e-3..5e-3 absolute error on the maps, coherent bias in the weight gradients): a
-//     converter warpgroup splits every landed stage IN SHARED MEMORY into hi = rna_tf32(x) (in place) and
-//     lo = x - hi (second buffer), element-wise and therefore swizzle-agnostic; the MMA warp issues
-//     hi*Whi + hi*Wlo + lo*Whi (3 MMAs per k-step; the tensor pipe stays < 15 % busy);
+//   * persistent CTAs, one per SM; tile = 128 pixels x 256 channels; the kernel itself is condconv_ts.inl (TMA ring ->
+//     converter warps -> hi/lo operand slots in TENSOR MEMORY -> tcgen05.mma kind::tf32, 3xTF32 error compensation);
 //   * B = the conditioned kernels, zero-padded to N = 16 by TMA out-of-bounds fill, resident in shared memory
-//     for the whole kernel, split once into hi + lo the same way;
-//   * tcgen05.mma kind::tf32, M=128 N=16 K=8, fp32 accumulators in TMEM, 4-deep accumulator ring;
+//     for the whole kernel, split once into hi + lo;
 //   * epilogue warps: one TMEM lane = one pixel, so softmax / sigmoid, the NCHW activation-map store and the
 //     focal-loss term are computed per thread in registers (tcgen05.ld 32x32b.x16).
-// Backward = one pass over rows producing d_rows (dense write) and per-CTA partial d_weight (fp32 FFMA).
+// Backward = two streaming passes (d_logit, then d_rows + per-CTA d_weight partials; fp32 FFMA, HBM-bound).
+// condconv_fwd_simt_kernel is the fp32 verification kernel the tests compare the tensor-core path with.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -29,14 +23,9 @@ constexpr int CC_BM = 128;
 constexpr int CC_BK = 32;
 constexpr int CC_KB = CC_C / CC_BK;  // 8 k-blocks per tile
 constexpr int CC_N = 16;
-constexpr int CC_STAGES = 6;
-constexpr int CC_ACC = 4;
 constexpr int CC_STAGE_BYTES = CC_BM * CC_BK * 4;  // 16384
 constexpr int CC_WBLK_BYTES = CC_N * CC_BK * 4;    // 2048
 constexpr int CC_W_BYTES = CC_KB * CC_WBLK_BYTES;  // 16384
-constexpr int CC_SMEM = 1024 + 2 * CC_W_BYTES + 2 * CC_STAGES * CC_STAGE_BYTES + 1024;  // hi + lo per stage
-constexpr int CC_CONV_GROUPS = 2;  // converter warpgroups; group c converts the k-blocks with index % CC_CONV_GROUPS == c
-constexpr int CC_THREADS = 256 + 128 * CC_CONV_GROUPS;  // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-7: epilogue, 8..: converters
 constexpr int CC_MAX_PARTIALS = 1024;
 
 struct ActPtrs {
@@ -124,174 +113,6 @@ __device__ __forceinline__ double act_epilogue(const Levels& lv, const ActPtrs& 
       }
   }
   return loss;
-}
-
-// ---------------------------------------------------------------------------- forward, tcgen05
-__global__ void __launch_bounds__(CC_THREADS, 1)
-    condconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, Levels lv,
-                           ActPtrs act, const float* __restrict__ bias, const int64_t* __restrict__ labels,
-                           double* __restrict__ loss_partials, int* __restrict__ flags, int K, int act_mode, int num_tiles) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_hi = smem;
-  uint8_t* w_lo = smem + CC_W_BYTES;
-  uint8_t* stages = smem + 2 * CC_W_BYTES;                    // hi parts (TMA destination, converted in place)
-  uint8_t* stages_lo = stages + CC_STAGES * CC_STAGE_BYTES;   // lo parts
-  uint64_t* bars = (uint64_t*)(stages_lo + CC_STAGES * CC_STAGE_BYTES);
-  uint64_t* full_bar = bars;                         // [CC_STAGES] TMA -> converter
-  uint64_t* empty_bar = bars + CC_STAGES;            // [CC_STAGES] MMA -> TMA
-  uint64_t* ready_bar = bars + 2 * CC_STAGES;        // [CC_STAGES] converter -> MMA
-  uint64_t* acc_full = bars + 3 * CC_STAGES;         // [CC_ACC]
-  uint64_t* acc_empty = bars + 3 * CC_STAGES + CC_ACC;  // [CC_ACC]
-  uint64_t* w_bar = bars + 3 * CC_STAGES + 2 * CC_ACC;
-  uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
-  __shared__ double red[4];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long R = lv.row_off[SCAN_MAX_LEVELS];
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < CC_STAGES; ++i) {
-      mbar_init(smem_u32(full_bar + i), 1);
-      mbar_init(smem_u32(empty_bar + i), 1);
-      mbar_init(smem_u32(ready_bar + i), 128);
-    }
-    for (int i = 0; i < CC_ACC; ++i) {
-      mbar_init(smem_u32(acc_full + i), 1);
-      mbar_init(smem_u32(acc_empty + i), 128);
-    }
-    mbar_init(smem_u32(w_bar), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 2) {  // TMEM allocation: CC_ACC x 16 columns = 64
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(CC_ACC * CC_N));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // conditioned kernels -> shared memory (raw fp32 via TMA, rows >= K zero-filled), then hi/lo split in place
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(smem_u32(w_bar), CC_W_BYTES);
-    for (int kb = 0; kb < CC_KB; ++kb) tma_load_2d(smem_u32(w_hi + kb * CC_WBLK_BYTES), &tmap_w, smem_u32(w_bar), kb * CC_BK, 0);
-  }
-  mbar_wait(smem_u32(w_bar), 0);
-  for (int i = threadIdx.x; i < CC_W_BYTES / 4; i += CC_THREADS) {
-    const float wv = ((float*)w_hi)[i];
-    uint32_t hi;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(wv));
-    ((float*)w_hi)[i] = __uint_as_float(hi);
-    ((float*)w_lo)[i] = wv - __uint_as_float(hi);
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < CC_KB; ++kb) {
-          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-          mbar_expect_tx(smem_u32(full_bar + stage), CC_STAGE_BYTES);
-          tma_load_2d(smem_u32(stages + stage * CC_STAGE_BYTES), &tmap_x, smem_u32(full_bar + stage), kb * CC_BK, tile * CC_BM);
-          if (++stage == CC_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(acc_empty + acc), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + acc * CC_N;
-        for (int kb = 0; kb < CC_KB; ++kb) {
-          mbar_wait(smem_u32(ready_bar + stage), phase);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(stages + stage * CC_STAGE_BYTES);
-          const uint32_t al_addr = smem_u32(stages_lo + stage * CC_STAGE_BYTES);
-          const uint32_t bh_addr = smem_u32(w_hi + kb * CC_WBLK_BYTES);
-          const uint32_t bl_addr = smem_u32(w_lo + kb * CC_WBLK_BYTES);
-#pragma unroll
-          for (int k = 0; k < CC_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32);
-            const uint64_t dbh = umma_desc_sw128(bh_addr + k * 32);
-            umma_tf32(d, da, dbh, CC_IDESC, (kb | k) != 0);
-            umma_tf32(d, da, umma_desc_sw128(bl_addr + k * 32), CC_IDESC, 1);
-            umma_tf32(d, umma_desc_sw128(al_addr + k * 32), dbh, CC_IDESC, 1);
-          }
-          umma_commit(smem_u32(empty_bar + stage));  // frees the smem stage when these MMAs retire
-          if (++stage == CC_STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(smem_u32(acc_full + acc));
-        if (++acc == CC_ACC) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp >= 8) {
-    // ===== converter: fp32 stage -> tf32 hi (in place) + lo (second buffer); element-wise, swizzle-agnostic =====
-    const int t = (threadIdx.x - 256) & 127;
-    const int group = (threadIdx.x - 256) >> 7;
-    long long it = 0;  // running k-block index of this CTA: stage = it % CC_STAGES, phase = (it / CC_STAGES) & 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < CC_KB; ++kb, ++it) {
-        if ((int)(it % CC_CONV_GROUPS) != group) continue;
-        const int stage = (int)(it % CC_STAGES);
-        const uint32_t phase = (uint32_t)((it / CC_STAGES) & 1);
-        mbar_wait(smem_u32(full_bar + stage), phase);
-        float4* hi = reinterpret_cast<float4*>(stages + stage * CC_STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(stages_lo + stage * CC_STAGE_BYTES);
-#pragma unroll
-        for (int j = 0; j < CC_STAGE_BYTES / 16 / 128; ++j) {
-          const float4 v = hi[j * 128 + t];
-          uint32_t hx, hy, hz, hw;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hz) : "f"(v.z));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hw) : "f"(v.w));
-          const float4 h = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
-          hi[j * 128 + t] = h;
-          lo[j * 128 + t] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
-        mbar_arrive(smem_u32(ready_bar + stage));
-      }
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) =====
-    const int q = warp - 4;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    double loss = 0.0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(acc_full + acc), acc_phase);
-      tcgen05_fence_after();
-      float z[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * CC_N, z);
-      tcgen05_fence_before();
-      mbar_arrive(smem_u32(acc_empty + acc));
-      const long long g = (long long)tile * CC_BM + q * 32 + lane;
-      if (g < R) loss += act_epilogue(lv, act, g, z, K, act_mode, bias, labels, flags);
-      if (++acc == CC_ACC) { acc = 0; acc_phase ^= 1; }
-    }
-    if (loss_partials) {
-      loss = warp_sum_d(loss);
-      if (lane == 0) red[q] = loss;
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0 && loss_partials) loss_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
-  if (warp == 2) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CC_ACC * CC_N));
-  }
 }
 
 #include "condconv_ts.inl"
@@ -396,70 +217,6 @@ __device__ __forceinline__ void row_dlogits(const Levels& lv, const ConstActPtrs
         dz[k] = d;
       }
   }
-}
-
-__global__ void __launch_bounds__(CB_THREADS) condconv_bwd_kernel(Levels lv, const float* __restrict__ rows, const float* __restrict__ weight,
-                                                                  ConstActPtrs act, ConstActPtrs dact, const int64_t* __restrict__ labels,
-                                                                  float loss_scale, const float* __restrict__ d_loss, int K, int act_mode,
-                                                                  int num_tiles,
-                                                                  float* __restrict__ d_rows, float* __restrict__ partial_w,
-                                                                  float* __restrict__ partial_b) {
-  __shared__ __align__(16) float dzs[CB_ROWS][16];
-  const long long R = lv.row_off[SCAN_MAX_LEVELS];
-  const int c = threadIdx.x;
-  float w[16], acc[16];
-  float bacc = 0.f;
-  if (d_loss) loss_scale *= __ldg(d_loss);  // d(total)/d(act_loss), a device scalar: no host sync
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    w[k] = (k < K) ? __ldg(weight + k * CC_C + c) : 0.f;
-    acc[k] = 0.f;
-  }
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const long long g0 = (long long)tile * CB_ROWS;
-    __syncthreads();
-    if (threadIdx.x < CB_ROWS) {
-      float dz[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) dz[k] = 0.f;
-      if (g0 + threadIdx.x < R) row_dlogits(lv, act, dact, g0 + threadIdx.x, K, act_mode, labels, loss_scale, dz);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) dzs[threadIdx.x][k] = dz[k];
-    }
-    __syncthreads();
-    const int nrows = (int)min((long long)CB_ROWS, R - g0);
-    if (threadIdx.x < 16) {
-      float s = 0.f;
-      for (int r = 0; r < nrows; ++r) s += dzs[r][threadIdx.x];
-      bacc += s;
-    }
-#pragma unroll 8
-    for (int r = 0; r < CB_ROWS; ++r) {
-      if (r < nrows) {
-        const float x = __ldg(rows + (g0 + r) * CC_C + c);
-        const float4* d4 = reinterpret_cast<const float4*>(dzs[r]);
-        float dx = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          if (k4 * 4 < K) {
-            const float4 d = d4[k4];
-            dx = fmaf(d.x, w[k4 * 4 + 0], dx);
-            dx = fmaf(d.y, w[k4 * 4 + 1], dx);
-            dx = fmaf(d.z, w[k4 * 4 + 2], dx);
-            dx = fmaf(d.w, w[k4 * 4 + 3], dx);
-            acc[k4 * 4 + 0] = fmaf(d.x, x, acc[k4 * 4 + 0]);
-            acc[k4 * 4 + 1] = fmaf(d.y, x, acc[k4 * 4 + 1]);
-            acc[k4 * 4 + 2] = fmaf(d.z, x, acc[k4 * 4 + 2]);
-            acc[k4 * 4 + 3] = fmaf(d.w, x, acc[k4 * 4 + 3]);
-          }
-        }
-        d_rows[(g0 + r) * CC_C + c] = dx;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 16; ++k) partial_w[((long long)blockIdx.x * 16 + k) * CC_C + c] = acc[k];
-  if (threadIdx.x < 16) partial_b[blockIdx.x * 16 + threadIdx.x] = bacc;
 }
 
 // ---- the product backward: two streaming passes -----------------------------------------------------------------
@@ -603,8 +360,6 @@ int make_rowmajor_map(CUtensorMap* m, const float* base, uint64_t n_rows, uint64
   return SCAN_OK;
 }
 
-static int g_fwd_attr_set = 0;
-
 }  // namespace scan
 
 extern "C" int32_t scan_condconv_num_partials(void) { return scan::CC_MAX_PARTIALS; }
@@ -619,7 +374,7 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
   if (!rows || !weight || !act_nchw_host || num_classes < 1 || num_classes > SCAN_MAX_CLASSES) return SCAN_EINVAL;
   if (act_mode != 0 && act_mode != 1) return SCAN_EINVAL;
   if (labels && !loss_partials) return SCAN_EINVAL;
-  // impl 0: tcgen05, operands in tensor memory (product); 1: fp32 FFMA (verification); 2: tcgen05, operands in shared memory
+  // impl 0: tcgen05, A operands in tensor memory (product); 1: fp32 FFMA (verification kernel for the tests)
   if (((uintptr_t)rows & 15) || ((uintptr_t)weight & 15)) return SCAN_EINVAL;
   ActPtrs act;
   for (int l = 0; l < SCAN_MAX_LEVELS; ++l) {
@@ -641,36 +396,19 @@ extern "C" int scan_condconv_fwd(const scan_levels_t* lvh, const float* rows, co
     SCAN_LAUNCH_CHECK("condconv_fwd_simt_kernel");
     return SCAN_OK;
   }
-  if (impl != 0 && impl != 2) return SCAN_EINVAL;
+  if (impl != 0) return SCAN_EINVAL;
   CUtensorMap mx, mw;
   rc = make_rowmajor_map(&mx, rows, (uint64_t)R, CC_C, CC_BM);
   if (rc) return rc;
   rc = make_rowmajor_map(&mw, weight, (uint64_t)num_classes, CC_C, CC_N);
   if (rc) return rc;
-  if (!g_fwd_attr_set) {
-    SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
-    g_fwd_attr_set = 1;
-  }
-  if (impl == 0) {  // product kernel: A operands in tensor memory (condconv_ts.inl)
-    static int ts_attr = 0;
-    if (!ts_attr) {
-      SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-      ts_attr = 1;
-    }
-    // layout experiment (tools/bench_kernels.py): SCAN_B200_CC_KMAJOR=1 -> `rows` holds the k-block-major copy [8][R][32]
-    static const int kmajor = getenv("SCAN_B200_CC_KMAJOR") ? atoi(getenv("SCAN_B200_CC_KMAJOR")) : 0;
-    if (kmajor) {
-      rc = make_rowmajor_map(&mx, rows, (uint64_t)R * CC_KB, CC_BK, CC_BM);
-      if (rc) return rc;
-    }
-    condconv_fwd_ts_kernel<<<grid, TS_THREADS, TS_SMEM, st>>>(mx, mw, lv, act, bias, labels, labels ? loss_partials : nullptr, flags,
-                                                             num_classes, act_mode, num_tiles, kmajor ? R : 0);
-    SCAN_LAUNCH_CHECK("condconv_fwd_ts_kernel");
-    return SCAN_OK;
-  }
-  condconv_fwd_tc_kernel<<<grid, CC_THREADS, CC_SMEM, st>>>(mx, mw, lv, act, bias, labels, labels ? loss_partials : nullptr, flags,
-                                                           num_classes, act_mode, num_tiles);
-  SCAN_LAUNCH_CHECK("condconv_fwd_tc_kernel");
+  // product kernel: A operands in tensor memory (condconv_ts.inl)
+  static unsigned long long ts_attr = 0;
+  if (first_use_on_device(&ts_attr))
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(condconv_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+  condconv_fwd_ts_kernel<<<grid, TS_THREADS, TS_SMEM, st>>>(mx, mw, lv, act, bias, labels, labels ? loss_partials : nullptr, flags,
+                                                           num_classes, act_mode, num_tiles, 0);
+  SCAN_LAUNCH_CHECK("condconv_fwd_ts_kernel");
   return SCAN_OK;
 }
 
@@ -707,15 +445,6 @@ extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, co
   float* pb = pw + (long long)4 * sm_count() * 16 * CC_C;
   float* dzw = pb + (long long)4 * sm_count() * 16 + 64;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int fused = getenv("SCAN_B200_CONDCONV_BWD_FUSED") ? atoi(getenv("SCAN_B200_CONDCONV_BWD_FUSED")) : 0;
-  if (fused) {  // round-1 single-pass kernel (kept for comparison)
-    condconv_bwd_kernel<<<parts, CB_THREADS, 0, st>>>(lv, rows, weight, act, dact, labels, loss_scale, d_loss, num_classes, act_mode,
-                                                     num_tiles, d_rows, pw, pb);
-    SCAN_LAUNCH_CHECK("condconv_bwd_kernel");
-    condconv_bwd_reduce_kernel<<<num_classes, 256, 0, st>>>(pw, pb, parts, parts, num_classes, d_weight, d_bias);
-    SCAN_LAUNCH_CHECK("condconv_bwd_reduce_kernel");
-    return SCAN_OK;
-  }
   condconv_dlogit_kernel<<<parts_b, 256, 0, st>>>(lv, act, dact, labels, loss_scale, d_loss, num_classes, act_mode, dzw, pb);
   SCAN_LAUNCH_CHECK("condconv_dlogit_kernel");
   switch (num_classes) {

@@ -5,22 +5,18 @@
 
 namespace scan {
 static thread_local char g_err[512] = "";
-static int g_sm_count = 0;
+static int g_sm_count[64] = {0};
 
 void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
 int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sm_count = n;
-    else
-      g_sm_count = 148;
-  }
-  return g_sm_count;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& slot = g_sm_count[dev & 63];
+  if (slot == 0) slot = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  return slot;
 }
 }  // namespace scan
 

@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) db_mirror_kernel(const int* info, int n_f
   }
 }
 
-static int g_adj_attr = 0;
+static unsigned long long g_adj_attr = 0;
 
 int launch_db_adj_tc(const float* points, const float* sq, const int* info, int n_fixed, int cap, int dim, float eps2f, double eps2,
                      long long wpr, uint32_t* adj, int* info_w, unsigned long long* re_list, cudaStream_t st) {
@@ -408,9 +408,8 @@ int launch_db_adj_tc(const float* points, const float* sq, const int* info, int 
   CUtensorMap map;
   int rc = make_rowmajor_map(&map, points, (uint64_t)cap, (uint64_t)dim, GT);
   if (rc) return rc;
-  if (!g_adj_attr) {
+  if (first_use_on_device(&g_adj_attr)) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(db_adj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-    g_adj_attr = 1;
   }
   db_adj_tc_kernel<<<sm_count(), G_THREADS, G_SMEM, st>>>(map, points, sq, info, n_fixed, eps2f, eps2, wpr, adj, info_w, re_list);
   SCAN_LAUNCH_CHECK("db_adj_tc_kernel");

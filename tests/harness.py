@@ -62,9 +62,13 @@ def cotangents(shapes, seed):
     return out
 
 
-def _sample(t, limit=1024):
+SAMPLE_LIMIT = {"n": 1024}    # None = keep every element (the bench-size parity tests)
+
+
+def _sample(t, limit=None):
+    limit = SAMPLE_LIMIT["n"] if limit is None else limit
     a = t.detach().float().cpu().reshape(-1).numpy()
-    if a.size <= limit:
+    if limit is None or a.size <= limit:
         return a.copy()
     stride = a.size // limit
     return a[::stride][:limit].copy()
@@ -122,18 +126,24 @@ class ReferenceProbe(object):
         return getattr(self.inner, k)
 
 
-def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture=True):
-    """impl: 'reference' | 'oracle' | 'product'.  Returns dict[str, np.ndarray]."""
-    cfg, case, src_feats, src_targets, tgt_feats = build_case(name, boxlist_cls)
+def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture=True, prepared=None, tf32=False):
+    """impl: 'reference' | 'oracle' | 'product'.  Returns dict[str, np.ndarray].
+    prepared: optional (cfg, case, src_feats, src_targets, tgt_feats) instead of build_case(name) (weights already loaded).
+    tf32: leave torch's cuDNN TF32 default on (the benchmark's flags) instead of forcing true-fp32 towers."""
+    cfg, case, src_feats, src_targets, tgt_feats = prepared if prepared is not None else build_case(name, boxlist_cls)
+    if prepared is not None:
+        load_fixture = False
     if load_fixture:
         kg, gg = case["fixture"]
         sd = fixture_state_dict(module, seed=99, kernel_gain=kg, gn_gain=gg)
         module.load_state_dict(sd)
     module.to(device) if impl != "reference" else None
+    if impl == "product":
+        module.record = True      # keep the intermediate results (labels, node rows, DBSCAN masks) of each call in module.last
     if device != "cpu":
         # parity runs compare against an fp32 CPU reference: keep torch's own conv / matmul kernels (the towers,
         # which stay on cuDNN/cuBLAS) in true fp32; the only tf32 arithmetic left is the tcgen05 conditional conv
-        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = bool(tf32)
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.deterministic = True
         torch.backends.cudnn.benchmark = False
@@ -253,12 +263,31 @@ NOISE_KEYS = ("grad/cond_nx1.bias", "gradnorm/cond_nx1.bias", "grad/cond_2.bias"
 NOISE_ATOL = 5e-6
 
 
-def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False):
+TORCH_ONLY = ("dfeat_l", "dfin_l", "head_in.", "head_out.")     # tensors whose values pass through cuDNN's own backward
+REPORT = []    # (key, max|d|, scale, outlier fraction, relL2) of every tensor that needed a relaxed rule (printed by the tests)
+
+
+def is_torch_only(k):
+    return any(t in k for t in TORCH_ONLY) and "dfin_direct" not in k
+
+
+def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, only=None, cudnn_l2=5e-3):
     """Bit-exact for integer results, rtol (relative to the tensor's max magnitude) for floats.
-    Returns list of human-readable mismatches."""
+    only: optional predicate on the key (compare a subset).  Returns list of human-readable mismatches.
+
+    Relaxed rules (each use is appended to REPORT):
+      * tensors downstream of a tower ReLU (d(features), d(features_in) totals, tower / classifier-hidden gradients) may hold a
+        FEW entries whose ReLU mask flipped (pre-activation within ~1e-6 of zero on one side): pass if <= 2 % of the entries
+        exceed the bound and the relative L2 error is <= 3 rtol.  `dfin_direct` (the hot path's own backward, no tower ReLU in
+        it) is NOT in this class: it must meet the max-norm bound.
+      * device runs against the CPU oracle only: TORCH_ONLY tensors are produced by cuDNN's backward-data / backward-filter,
+        whose result differs from the CPU convolution on identical inputs (tests/tools/diag_grad2.py); they get the relative-L2
+        bound `cudnn_l2`.  The scan_b200 kernels on that path (GroupNorm+ReLU, add+ReLU, unpack) are held to 2e-5 by
+        `compare(got, twin, only=is_torch_only, ...)` against a twin run whose towers use torch's own GPU ops around the SAME
+        cuDNN calls (tests/test_gpu_module.py), so only cuDNN's own difference is excused here."""
     bad = []
     for k, w in want.items():
-        if any(s in k for s in skip):
+        if any(s in k for s in skip) or (only is not None and not only(k)):
             continue
         if k not in got:
             bad.append("missing %s" % k)
@@ -278,30 +307,89 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False):
                 bad.append("noise-floor mismatch %s: max|d|=%.3e" % (k, err))
             continue
         if err > rtol * scale + atol_scale * 1e-6:
-            # Gradients that pass through a ReLU (head_in / head_out towers, both torch ops) are discontinuous: an
-            # activation within ~1e-6 of zero gets the opposite mask on the GPU and on the CPU, which changes a FEW
-            # gradient entries by O(1) relative amounts (measured: tests/tools/diag_grad.py; the same happens between the
-            # reference on CPU and the reference on GPU).  Such tensors pass if the outliers are sparse and the
-            # relative L2 error is small; everything else must meet the max-norm bound.
             d = np.abs(g.astype(np.float64) - w.astype(np.float64))
             frac = float((d > rtol * scale).mean())
             rel_l2 = float(np.linalg.norm(d) / max(np.linalg.norm(w.astype(np.float64)), 1e-30))
-            relu_path = ("dfeat_l" in k) or ("dfin_l" in k) or ("dfin_direct" in k) or ("head_in." in k) or ("head_out." in k) or ("proto_cls_hidden" in k)
+            relu_path = is_torch_only(k) or ("proto_cls_hidden" in k)
             if relu_path and frac <= 0.02 and rel_l2 <= 3 * rtol:
+                REPORT.append((k, err, scale, frac, rel_l2, "relu-flip rule"))
                 continue
-            # d(input features) and the head_in parameter gradients are produced by torch's OWN backward (cuDNN
-            # backward-data / backward-filter, GroupNorm) from d(features_in) = "dfin", which is what the scan_b200
-            # kernels produce and which is held to rtol above.  cuDNN's backward at the P3 shape differs from the CPU
-            # implementation by up to ~3e-3 relL2 on identical inputs (tests/tools/diag_grad2.py: dfin agrees to 1e-6 while
-            # dfeat_l0 does not), so those torch-only tensors get a looser L2 bound.
-            # "dfin" (total) additionally contains head_out's backward-data: one flipped ReLU at a coarse level (24
-            # pixels at P6) touches a 3x3 neighbourhood x 256 channels, i.e. a third of the tensor.  The hot path's own
-            # contribution is checked strictly through "dfin_direct".
-            torch_only = ("dfeat_l" in k) or ("dfin_l" in k) or ("head_in." in k) or ("head_out." in k)
-            if device_run and torch_only and rel_l2 <= 3e-2:
+            if device_run and cudnn_l2 and is_torch_only(k) and rel_l2 <= cudnn_l2:
+                REPORT.append((k, err, scale, frac, rel_l2, "cudnn-vs-cpu L2 rule"))
                 continue
             bad.append("float mismatch %s: max|d|=%.3e scale=%.3e outliers=%.2f%% relL2=%.2e" % (k, err, scale, 100 * frac, rel_l2))
-    for k in got:
-        if k not in want and not any(s in k for s in skip):
-            bad.append("unexpected %s" % k)
+    if only is None:
+        for k in got:
+            if k not in want and not any(s in k for s in skip):
+                bad.append("unexpected %s" % k)
     return bad
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Twin run for device tests: the product module with its tower-side kernels (GroupNorm+ReLU, add+ReLU, NCHW<->rows) replaced
+# by torch's own GPU ops around the SAME cuDNN convolution calls.  TEST CODE: the product never takes this path.
+# ----------------------------------------------------------------------------------------------------------------------
+class torch_tower_twin(object):
+    def __enter__(self):
+        import torch.nn.functional as F
+        from scan_b200 import ops
+        self.ops = ops
+        self.saved = (ops.gn_relu_levels, ops.add_relu_levels, ops.pack_levels)
+
+        def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None):
+            out = []
+            for x in xs:
+                if conv_bias is not None:
+                    x = x + conv_bias.view(1, -1, 1, 1)
+                out.append(torch.relu(F.group_norm(x, 32, gamma, beta, eps)).contiguous(memory_format=torch.channels_last))
+            return out
+
+        def add_relu_levels(geo, bias, us, vs=None):
+            out = []
+            for i, u in enumerate(us):
+                y = u if vs is None else u + vs[i]
+                if bias is not None:
+                    y = y + bias.view(1, -1, 1, 1)
+                out.append(torch.relu(y).contiguous(memory_format=torch.channels_last))
+            return out
+
+        def pack_levels(geo, feats):
+            return [f.contiguous(memory_format=torch.channels_last) for f in feats]
+
+        ops.gn_relu_levels, ops.add_relu_levels, ops.pack_levels = gn_relu_levels, add_relu_levels, pack_levels
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.gn_relu_levels, self.ops.add_relu_levels, self.ops.pack_levels = self.saved
+        return False
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The benchmark's configuration as a parity case (BASELINE.json configs[1]: n source + n target images, 800x1344, K = 9,
+# "trained-like" weights: seeded fixture, settle steps that fill the paradigm buffer, closed-form manifestation fit).
+# The fit runs ONCE on the CPU oracle; the product loads the resulting state dict, so both see identical bits.
+# ----------------------------------------------------------------------------------------------------------------------
+def prepare_bench_like(n, settle=6, steps=("source", "target", "eval"), preset="c2f", num_fg=8, **over):
+    from oracle.condgraph_oracle import build_oracle
+    from scan_b200.fixtures import fit_trained_like
+    cfg = scan_cfg(preset, **over)
+    src_feats, src_targets = make_workload(n, num_fg, seed=1234, dir_seed=77)
+    tgt_feats, _ = make_workload(n, num_fg, seed=4321, dir_seed=77)
+    oracle = build_oracle(cfg)
+    oracle.load_state_dict(fixture_state_dict(oracle, seed=99))
+    oracle.use_sklearn = False          # oracle/dbscan_oracle.c: the point sets exceed what sklearn can hold
+    oracle.train()
+    with torch.no_grad():
+        for _ in range(settle):
+            oracle(None, [f[:1] for f in src_feats], targets=src_targets[:1], mode="source")
+    fit_trained_like(oracle, [f[:1] for f in src_feats], src_targets[:1])
+    case = dict(cfg=(preset, over), n=n, steps=list(steps), fixture=None)
+    counter = oracle.counter_rnn.counter if hasattr(oracle, "counter_rnn") else None
+    return oracle, (cfg, case, src_feats, src_targets, tgt_feats), counter
+
+
+def load_like(module, oracle, counter):
+    module.load_state_dict({k: v.clone() for k, v in oracle.state_dict().items()})
+    if counter is not None:
+        module.counter_rnn.counter = counter
+    return module

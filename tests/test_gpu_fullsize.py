@@ -1,0 +1,129 @@
+"""Kernel-level parity at the sizes the benchmark and BASELINE.json configs[4] actually run (B200):
+DBSCAN at n = 7 k .. 100 k points (multi-unit row blocks, A-tile reload, many mirror tiles, recheck-list overflow,
+dominant-set filter of the union-find), attention at M = 8 728 / 6 026 nodes (1 100-step accumulation chains with the TMEM
+drains, the gridDim.z split of the backward) against float64."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from scan_b200 import ops  # noqa: E402
+from oracle import condgraph_oracle as orc  # noqa: E402
+
+DEV = "cuda"
+
+
+def _structured_points(n, seed, kind, eps=3.0):
+    """256-d point sets with many clusters, border points and noise at eps ~ 3."""
+    rs = np.random.RandomState(seed)
+    if kind == "clusters":      # ~n/400 tight clusters on a coarse grid + 3 % uniform noise + bridges (border points)
+        k = max(n // 400, 2)
+        centers = rs.standard_normal((k, 256)) * 1.2
+        x = centers[rs.randint(0, k, n)] + rs.standard_normal((n, 256)) * 0.12
+        noise = rs.rand(n) < 0.03
+        x[noise] = rs.standard_normal((int(noise.sum()), 256)) * 1.5
+        return x.astype(np.float32)
+    if kind == "planar":        # uniform planar cloud embedded in 256-d: long chains, hundreds of border points
+        p2 = rs.uniform(0, np.sqrt(n * np.pi * eps * eps / 6.5), (n, 2))   # ~6.5 expected neighbours: percolation threshold
+        basis = np.linalg.qr(rs.standard_normal((256, 2)))[0]
+        return (p2 @ basis.T).astype(np.float32)
+    if kind == "dense":         # one dominant cluster (every point within eps of most others: ~n^2/2 adjacency bits) + stragglers
+        x = rs.standard_normal((n, 256)) * 0.12
+        far = rs.rand(n) < 0.01
+        x[far] += rs.standard_normal((int(far.sum()), 256)) * 0.3
+        return x.astype(np.float32)
+    if kind == "shell":         # points on a sphere of radius eps/sqrt(2): pairwise distances concentrate AT eps -> millions of
+        x = rs.standard_normal((n, 256))                     # pairs fall into the tf32 error band (recheck-list overflow)
+        x = x / np.linalg.norm(x, axis=1, keepdims=True) * (3.0 / np.sqrt(2.0))
+        return x.astype(np.float32)
+    raise KeyError(kind)
+
+
+def _check(x, eps, want, what):
+    labels, info = ops.dbscan_points(torch.from_numpy(x).to(DEV), eps)
+    got = labels.cpu().numpy()
+    info = info.cpu().numpy()
+    assert info[4] == 0
+    assert np.array_equal(got, want), "%s: %d label mismatches, first at %s" % (what, int((got != want).sum()), np.nonzero(got != want)[0][:10])
+    assert info[1] == want.max() + 1 and info[2] == int((want < 0).sum())
+    return info
+
+
+@pytest.mark.parametrize("n,kind,eps", [(7000, "clusters", 3.0), (7000, "planar", 3.0), (20000, "clusters", 3.0), (20000, "planar", 2.0)])
+def test_dbscan_bit_exact_vs_sklearn_large(n, kind, eps):
+    """BASELINE.json configs[4]: n ~ 20 000 is the largest point set the sklearn call of the reference survives."""
+    from sklearn.cluster import DBSCAN
+    x = _structured_points(n, n + 1, kind, eps)
+    want = DBSCAN(eps=eps).fit_predict(x)
+    assert want.max() >= 1
+    _check(x, eps, want, "%s n=%d" % (kind, n))
+
+
+@pytest.mark.parametrize("n,kind,eps", [(46452, "clusters", 3.0), (46452, "dense", 3.0), (45000, "planar", 3.0), (65536, "clusters", 3.0),
+                                        (100000, "clusters", 3.0)])
+def test_dbscan_bit_exact_vs_c_oracle_bench_sizes(n, kind, eps):
+    """The benchmark's P3 level hands DBSCAN n ~ 46 k points; configs[4] asks for n ~ 100 k.  Beyond sklearn's memory the
+    checker is oracle/dbscan_oracle.c (itself pinned against sklearn, tests/test_oracle_vs_reference.py)."""
+    x = _structured_points(n, n + 2, kind, eps)
+    want = orc.dbscan_labels_c(x, eps)
+    _check(x, eps, want, "%s n=%d" % (kind, n))
+
+
+def test_dbscan_recheck_list_overflow_falls_back_inline():
+    """> 2^21 pairs inside the tf32 error band around eps^2: the work list overflows and the kernel must re-evaluate the
+    rest inline -- exactness must not depend on the list capacity."""
+    n = 24000
+    x = _structured_points(n, 5, "shell")
+    want = orc.dbscan_labels_c(x, 3.0)
+    info = _check(x, 3.0, want, "shell")
+    assert int(info[5]) > (1 << 21), "only %d in-band pairs: the overflow path was not exercised" % int(info[5])
+
+
+def _attn_ref64(q, k, v, cot, scale):
+    m = q.shape[0]
+    qr, kr, vr = [t.double().clone().requires_grad_(True) for t in (q, k, v)]
+    att = torch.softmax(torch.bmm(qr.reshape(4, m, 64), kr.reshape(4, m, 64).transpose(1, 2)) * scale, dim=2)
+    ctx = torch.bmm(att, vr.reshape(4, m, 64)).reshape(m, 256)
+    (ctx * cot.double()).sum().backward()
+    return ctx.detach(), qr.grad, kr.grad, vr.grad
+
+
+@pytest.mark.parametrize("m", [8728, 6026])
+def test_attention_full_size_vs_float64(m):
+    """M = 8 728 (source, 8 images) / 6 026 (target: the wave-split backward): ctx, dq, dk, dv against a float64 torch
+    reference on the same GPU.  Bound: 5e-5 of each tensor's max magnitude (the 3xTF32 + drained-accumulator design gives
+    3-7e-6; the north-star tolerance is 1e-3)."""
+    g = torch.Generator().manual_seed(m)
+    q, k, v, cot = [torch.randn(m, 256, generator=g).to(DEV) for _ in range(4)]
+    q, k = q * 1.5, k * 1.5                     # scores ~ N(0, 4.5): peaked rows as well as flat ones
+    want = _attn_ref64(q, k, v, cot, 0.25)
+    qd, kd, vd = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    ctx = ops.chunked_attention(qd, kd, vd, 0.25)
+    (ctx * cot).sum().backward()
+    for name, a, b in zip(("ctx", "dq", "dk", "dv"), (ctx.detach(), qd.grad, kd.grad, vd.grad), want):
+        scale = float(b.abs().max())
+        err = float((a.double() - b).abs().max())
+        assert err <= 5e-5 * scale, "%s: max|d|=%.3e scale=%.3e" % (name, err, scale)
+
+
+@pytest.mark.parametrize("m", [8728, 6026])
+def test_attention_full_size_dropout_fwd_bwd_consistent(m):
+    """Dropout 0.1 at full size: the tcgen05 kernels against the fp32 FFMA kernels (same counter-based mask)."""
+    g = torch.Generator().manual_seed(m + 1)
+    q, k, v, cot = [torch.randn(m, 256, generator=g).to(DEV) for _ in range(4)]
+    res = {}
+    saved = dict(ops.ATTN_IMPL)
+    try:
+        for impl in ("ffma", "t5"):
+            ops.ATTN_IMPL.update(fwd=impl, bwd=impl)
+            qd, kd, vd = [t.clone().requires_grad_(True) for t in (q, k, v)]
+            out = ops.chunked_attention(qd, kd, vd, 0.25, 0.1, 99)
+            (out * cot).sum().backward()
+            res[impl] = (out.detach(), qd.grad, kd.grad, vd.grad)
+    finally:
+        ops.ATTN_IMPL.update(saved)
+    for name, a, b in zip(("ctx", "dq", "dk", "dv"), res["t5"], res["ffma"]):
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max())
+        assert err <= 5e-5 * scale + 2e-5, "%s: max|d|=%.3e scale=%.3e" % (name, err, scale)

@@ -236,12 +236,12 @@ def _condconv_reference(feats, weight, bias, labels, mode, lam):
     return acts, loss
 
 
-@pytest.mark.parametrize("impl", [1, 0, 2])
+@pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("k,mode,with_bias,shapes,n", [(9, 0, False, SHAPES, 2), (2, 1, False, SHAPES, 3), (9, 0, True, SHAPES, 1),
                                                        (2, 0, False, SHAPES, 2), (9, 0, False, FULL, 1), (16, 0, False, SHAPES, 1)])
 def test_condconv_forward_backward(impl, k, mode, with_bias, shapes, n):
     """tcgen05 tf32 path (impl 0) within rtol 1e-3 of the fp32 torch reference; FFMA kernel (impl 1) within 1e-5."""
-    rtol = 2e-5 if impl == 1 else 1e-3   # impl 0 / 2: tcgen05 3xTF32 (SS / TS operand form), impl 1: fp32 FFMA
+    rtol = 2e-5 if impl == 1 else 1e-3   # impl 0: tcgen05 3xTF32 (product), impl 1: fp32 FFMA verification kernel
     g = torch.Generator().manual_seed(10 + k)
     feats = [torch.relu(torch.randn(n, 256, h, w, generator=g)) for h, w in shapes]
     weight = torch.randn(k, 256, generator=g) * 0.08
