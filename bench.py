@@ -1,26 +1,38 @@
 #!/usr/bin/env python
 """Benchmark of the condgraph middle head (BASELINE.json metric: fwd+bwd images/s on B200 + roofline fraction).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2f|sim10k|kitti-eval]
 
-One step = one pass of the hot path over one batch: source branch fwd+bwd on `--images` source images, then target
-branch fwd+bwd on `--images` target images (synthetic FPN features of Cityscapes shape, 800x1344 padded, 22 400
-locations/image, 256 channels, K = 9 classes; BASELINE.json configs[1]: 8 + 8 images per GPU).  Weights are the seeded
-fixture, `--settle` untimed source steps that fill the paradigm buffer, then `fixtures.fit_trained_like`: a closed-form
-fit of the manifestation layer that makes the activation maps background-dominant with confident object regions like
-a trained model, so that the target-domain DBSCAN sees a realistic number of points.
+One step = one pass of the hot path over one batch.
+  --config c2f (default; BASELINE.json configs[1]): source branch fwd+bwd on `--images` source images, then target branch
+      fwd+bwd on `--images` target images (synthetic FPN features of Cityscapes shape, 800x1344 padded, 22 400 locations /
+      image, 256 channels, K = 9 classes; 8 + 8 images per GPU).
+  --config sim10k (configs[2]): the same step with the Sim10k->Cityscapes config (K = 2: the degenerate single-class node
+      sampling and DBSCAN path, no transfer loss).
+  --config kitti-eval (configs[3]): inference (module.eval()) on `--images` images + the TEST.MODE map ensembling of all
+      five levels, for TEST.MODE = 'precision' and 'light' (both timed; `value` is 'precision').
+Weights are the seeded fixture, `--settle` untimed source steps that fill the paradigm buffer, then
+`fixtures.fit_trained_like`: a closed-form fit of the manifestation layer that makes the activation maps background-dominant
+with confident object regions like a trained model, so that the target-domain DBSCAN sees a realistic number of points
+(SURVEY 8d).  The SAME configuration is parity-tested element by element (tests/test_gpu_module.py::test_benchmark_*).
 
   value      whole-job images/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same through the public module call with HOST (pinned) inputs: H2D of the step's FPN features and
              D2H of its losses inside the timed region; the batch of step i+1 is copied on a side stream while step i
              computes (a double-buffered input pipeline), the first copy is exposed
-  roofline   conditional-convolution forward kernel: algorithmic bytes / its CUDA-event duration,
-             against MEASURED_PEAKS.json
+  roofline   the DOMINANT hand-written entry point of the step (largest device time) with its algorithmic work / its
+             CUDA-event duration against the measured peak (HBM: MEASURED_PEAKS.json; tensor: cuBLAS tf32 8192^3 measured in
+             this process with the MEASURED_PEAKS recipe), plus `table`: the same for every entry point of the step;
+             `traffic` = dram bytes of that kernel from the committed ncu capture profiles/r02_ncu_traffic.json (null if absent)
+  eager_gpu_baseline
+             the oracle port of the reference (oracle/condgraph_oracle.py: eager torch / cuDNN / cuBLAS, DBSCAN on the host
+             through oracle/dbscan_oracle.c because sklearn cannot hold n ~ 37 k points) on the SAME GPU, same batch: the
+             "today" number of SURVEY 8d.  Checker code used as a baseline only, never on the product path.
   cpu_baseline / --impl reference
-             the CPU oracle port of the reference (oracle/condgraph_oracle.py) on the host cores, bounded sample:
-             1 source + 1 target image per step (BASELINE.json configs[0])
+             the CPU oracle port of the reference on the host cores, bounded sample: 1 source + 1 target image per step
+             (BASELINE.json configs[0])
 N > 1: one process per GPU (torchrun); images are sharded (weak scaling: --images per GPU); the only collective is the
-[K, 257] prototype sum|count all-reduce of every source step (SURVEY §8e).
+[K, 257] prototype sum|count all-reduce of every source step (SURVEY 8e).
 """
 import argparse
 import json
@@ -49,6 +61,8 @@ def parse():
     ap.add_argument("--settle", type=int, default=6, help="untimed source steps that fill the paradigm buffer before the fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="attention dropout (reference train-mode value 0.1)")
+    ap.add_argument("--config", default="c2f", choices=["c2f", "sim10k", "kitti-eval"])
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-torch-on-GPU run of the oracle port")
     return ap.parse_args()
 
 
@@ -89,10 +103,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def make_batches(n_images, device=None, pinned=False):
+def make_batches(n_images, num_fg=8, pinned=False):
     from scan_b200.synthetic import make_workload
-    src_f, src_t = make_workload(n_images, 8, seed=1234, dir_seed=77)
-    tgt_f, _ = make_workload(n_images, 8, seed=4321, dir_seed=77)
+    src_f, src_t = make_workload(n_images, num_fg, seed=1234, dir_seed=77)
+    tgt_f, _ = make_workload(n_images, num_fg, seed=4321, dir_seed=77)
     if pinned:
         src_f = [f.pin_memory() for f in src_f]
         tgt_f = [f.pin_memory() for f in tgt_f]
@@ -109,6 +123,26 @@ def pretrain(module, feats, targets, steps):
     fit_trained_like(module, [f[:1] for f in feats], targets[:1])
 
 
+def one_pass(module, mode, feats, src_targets, cots):
+    feats = [f.requires_grad_(True) for f in feats]
+    if mode == "source":
+        out = module(None, feats, targets=src_targets, mode="source")
+    else:
+        out = module(None, feats, targets=None, mode="target", forward_target=True)
+    out_feats, loss_graph, act_loss, acts = out
+    scalars = []
+    if loss_graph is not None:
+        scalars += [v for v in loss_graph if torch.is_tensor(v)]
+    if torch.is_tensor(act_loss):
+        scalars.append(act_loss)
+    # cotangents are fed straight into autograd (no extra multiply / reduce kernels in the timed region)
+    torch.autograd.backward(list(out_feats) + list(acts) + scalars,
+                            list(cots[0]) + list(cots[1]) + [torch.ones_like(v) for v in scalars])
+    for f in feats:
+        f.grad = None
+    return torch.stack([v.detach().float() for v in scalars]) if scalars else None
+
+
 def one_step(module, src, src_targets, tgt, cots, ready=None):
     """source fwd+bwd, target fwd+bwd.  Cotangents stand in for the FCOS head / discriminator gradients.
     ready: optional (event, event): the copy-stream events after which the source / target inputs are valid."""
@@ -116,24 +150,17 @@ def one_step(module, src, src_targets, tgt, cots, ready=None):
     for idx, (mode, feats) in enumerate((("source", src), ("target", tgt))):
         if ready is not None:
             torch.cuda.current_stream().wait_event(ready[idx])
-        feats = [f.requires_grad_(True) for f in feats]
-        if mode == "source":
-            out = module(None, feats, targets=src_targets, mode="source")
-        else:
-            out = module(None, feats, targets=None, mode="target", forward_target=True)
-        out_feats, loss_graph, act_loss, acts = out
-        scalars = []
-        if loss_graph is not None:
-            scalars += [v for v in loss_graph if torch.is_tensor(v)]
-        if torch.is_tensor(act_loss):
-            scalars.append(act_loss)
-        # cotangents are fed straight into autograd (no extra multiply / reduce kernels in the timed region)
-        torch.autograd.backward(list(out_feats) + list(acts) + scalars,
-                                list(cots[0]) + list(cots[1]) + [torch.ones_like(v) for v in scalars])
-        res.append(torch.stack([v.detach().float() for v in scalars]) if scalars else None)
-        for f in feats:
-            f.grad = None
+        res.append(one_pass(module, mode, feats, src_targets, cots))
     return res
+
+
+def eval_step(module, feats, cls_logits, mode):
+    """configs[3]: _forward_inference + TEST.MODE ensembling of every level (fcos.py:162-169 + inference.py:68)."""
+    from scan_b200 import ops
+    with torch.no_grad():
+        out_feats, _, _, acts = module(None, feats)
+        probs = ops.ensemble_levels(mode, None if mode == "light" else cls_logits, acts)
+    return out_feats, probs
 
 
 def cpu_reference_run(args, steps, warmup):
@@ -142,18 +169,33 @@ def cpu_reference_run(args, steps, warmup):
     from scan_b200.config import scan_cfg
     from scan_b200.fixtures import fixture_state_dict
     torch.set_num_threads(os.cpu_count())
-    cfg = scan_cfg("c2f")
+    preset, num_fg = PRESETS[args.config]
+    cfg = scan_cfg(preset)
     m = build_oracle(cfg)
     m.load_state_dict(fixture_state_dict(m, seed=99))
     m.multihead_attn.p_drop = args.dropout
-    src_f, src_t, tgt_f = make_batches(1)
+    m.use_sklearn = False
+    src_f, src_t, tgt_f = make_batches(1, num_fg)
     pretrain(m, src_f, src_t, args.settle)
-    m.train()
+    k = num_fg + 1
     shapes_f = [(1, 256, h, w) for h, w in FULL_SHAPES]
-    shapes_a = [(1, 9, h, w) for h, w in FULL_SHAPES]
+    shapes_a = [(1, k, h, w) for h, w in FULL_SHAPES]
     g = torch.Generator().manual_seed(5)
     cots = ([torch.randn(s, generator=g) / 1e5 for s in shapes_f], [torch.randn(s, generator=g) / 1e5 for s in shapes_a])
     times = []
+    if args.config == "kitti-eval":
+        from oracle import condgraph_oracle as orc
+        m.eval()
+        cls = [torch.randn((1, num_fg, h, w), generator=g) for h, w in FULL_SHAPES]
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                _, _, _, acts = m(None, [f.clone() for f in src_f])
+                orc.ensemble("precision", cls, acts)
+            times.append(time.perf_counter() - t0)
+        t = sum(times[warmup:]) / max(steps, 1)
+        return 1.0 / t, t
+    m.train()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         one_step(m, [f.clone() for f in src_f], src_t, [f.clone() for f in tgt_f], cots)
@@ -162,22 +204,149 @@ def cpu_reference_run(args, steps, warmup):
     return 2.0 / t, t
 
 
+def eager_gpu_run(args, state, counter, src_d, src_t, tgt_d, cots, steps=2, warmup=1):
+    """The oracle port of the reference in eager torch on THIS GPU, same weights, same batch (SURVEY 8d "today" number).
+    DBSCAN runs on the host like the reference's sklearn call (loss.py:414-421), through the C restatement."""
+    from oracle import condgraph_oracle as orc
+    from scan_b200.config import scan_cfg
+    preset, _ = PRESETS[args.config]
+    m = orc.build_oracle(scan_cfg(preset))
+    m.load_state_dict({k: v.detach().cpu().clone() for k, v in state.items()})
+    m.to(src_d[0].device)
+    if counter is not None:
+        m.counter_rnn.counter = counter
+    m.multihead_attn.p_drop = args.dropout
+    m.use_sklearn = False
+    m.train()
+    db = {"s": 0.0}
+    inner = orc.dbscan_labels_c
+
+    def timed(points, eps, min_samples=5):
+        t0 = time.perf_counter()
+        out = inner(points, eps, min_samples)
+        db["s"] += time.perf_counter() - t0
+        return out
+
+    orc.dbscan_labels_c = timed
+    src_t = [t.to(src_d[0].device) for t in src_t]
+    try:
+        times = []
+        for i in range(warmup + steps):
+            torch.cuda.synchronize()
+            if i == warmup:
+                db["s"] = 0.0
+            t0 = time.perf_counter()
+            one_step(m, [f.detach().clone() for f in src_d], src_t, [f.detach().clone() for f in tgt_d], cots)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+    finally:
+        orc.dbscan_labels_c = inner
+    t = sum(times[warmup:]) / steps
+    n = src_d[0].shape[0]
+    return {"value": 2 * n / t, "unit": "images/s", "ms_per_step": t * 1e3, "host_dbscan_ms_per_step": db["s"] / steps * 1e3,
+            "value_without_host_dbscan": 2 * n / max(t - db["s"] / steps, 1e-9), "steps": steps,
+            "what": "oracle port of the reference (eager torch, cuDNN/cuBLAS, torch defaults incl. cudnn TF32) on this GPU, %d + %d images; "
+                    "DBSCAN on the host cores through oracle/dbscan_oracle.c (the reference calls sklearn there)" % (n, n)}
+
+
+PRESETS = {"c2f": ("c2f", 8), "sim10k": ("sim10k", 1), "kitti-eval": ("kitti", 1)}
+
+
+def measure_tf32_peak(dev):
+    """cuBLAS tf32 8192^3, best of 10 (the MEASURED_PEAKS.json recipe with allow_tf32): the tensor-roofline denominator."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def work_model(n_img, k, m_src, m_tgt, db_points):
+    """Algorithmic work per STEP of every entry point (SURVEY 8d per-unit figures x the units one step processes):
+    {entry: (bound, amount)}; bytes for HBM-bound entries, flops for tensor-bound ones.  R = rows of one pass."""
+    R = n_img * L_PER_IMAGE
+    row = 1024                                   # one fp32 row of 256 channels
+    mm = m_src * m_src + m_tgt * m_tgt
+    ms = m_src + m_tgt
+    return {
+        "pack_rows": ("hbm", 2 * R * 2 * row),                         # 2 passes: NCHW read + rows write
+        "unpack_rows": ("hbm", 2 * R * 2 * row),
+        "gn_relu_fwd": ("hbm", 2 * 2 * R * 3 * row),                   # 2 passes x 2 layers: 2 reads + 1 write
+        "gn_relu_bwd": ("hbm", 2 * 2 * R * 7 * row),                   # 6 reads + 1 write
+        "add_relu_fwd": ("hbm", 2 * R * 3 * row),
+        "add_relu_bwd": ("hbm", 2 * R * 2 * row),
+        "condconv_fwd": ("hbm", 2 * R * (row + 4 * k) + R * 8),        # rows + K maps (+ labels on the source pass)
+        "condconv_bwd": ("hbm", 2 * R * (2 * row + 2 * 4 * k)),        # rows read, d_rows written, maps + map gradients
+        "gather_rows": ("hbm", ms * 2 * row),
+        "scatter_add_rows": ("hbm", ms * 2 * row + 0 * R),
+        "attn_fwd": ("tensor", 1024 * mm),                            # 4 chunks x (QK^T + PV) x 2 M^2 64
+        "attn_bwd": ("tensor", 2560 * mm),                            # 5 GEMMs of the same size
+        "qkv_fwd": ("tensor", 2 * ms * 256 * 768),
+        "qkv_bwd": ("tensor", 2 * 2 * ms * 256 * 768),
+        "attn_out_ln_fwd": ("tensor", 2 * ms * 256 * 256),
+        "attn_out_ln_bwd": ("tensor", 2 * 2 * ms * 256 * 256),
+        "node_cls_fwd": ("tensor", 2 * ms * 256 * 512 + 2 * ms * 512 * k),
+        "node_cls_bwd": ("tensor", 2 * 2 * ms * 256 * 512 + 2 * 2 * ms * 512 * k),
+        "dbscan_level": ("tensor", sum(256 * n * n for n in db_points)),   # n^2/2 pairs x 512 flops (symmetric Gram)
+    }
+
+
+def traffic_of(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    v = d.get("kernels", {}).get(kernel)
+    return None if v is None else v.get("dram_bytes_per_launch")
+
+
+# entry point -> the kernel that dominates it (the name the ncu capture and the roofline line report)
+DOMINANT_KERNEL = {"attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_level": "db_adj_tc_kernel",
+                   "condconv_fwd": "condconv_fwd_ts_kernel", "condconv_bwd": "condconv_bwd_rows_kernel", "gn_relu_bwd": "gn_bwd_apply_kernel",
+                   "gn_relu_fwd": "gn_apply_kernel", "qkv_fwd": "gemm3x_kernel", "qkv_bwd": "gemm3x_kernel"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    preset, num_fg = PRESETS[args.config]
+    k_cls = num_fg + 1
+    n = args.images
+    workload = {"c2f": "Cityscapes->Foggy VGG16 SCAN config, condgraph middle head fwd+bwd, %d source + %d target synthetic images per GPU "
+                       "per step, 800x1344 FPN features, 8 classes + bg" % (n, n),
+                "sim10k": "Sim10k->Cityscapes VGG16 SCAN config (K = 2, single-class node sampling + DBSCAN), middle head fwd+bwd, %d "
+                          "source + %d target synthetic images per GPU per step, 800x1344 FPN features" % (n, n),
+                "kitti-eval": "KITTI->Cityscapes VGG16 SCAN config (K = 2), middle-head inference + TEST.MODE map ensembling, %d synthetic "
+                              "images per GPU per step, 800x1344 FPN features; value = TEST.MODE 'precision'" % n}[args.config]
+    metric = "condgraph middle-head fwd+bwd images/s" if args.config != "kitti-eval" else "condgraph middle-head inference images/s"
 
     if args.impl == "reference":
         if rank != 0:
             return
         ips, t = cpu_reference_run(args, args.steps, args.warmup)
-        sample = "1 source + 1 target synthetic image (800x1344, K=9) per step, oracle port of the reference on host cores"
-        line = {"impl": "reference", "metric": "condgraph middle-head fwd+bwd images/s", "value": ips, "unit": "images/s",
+        sample = "1 source + 1 target synthetic image (800x1344, K=%d) per step, oracle port of the reference on host cores" % k_cls
+        if args.config == "kitti-eval":
+            sample = "1 synthetic image (800x1344, K=2) per step: inference + precision-mode ensembling, oracle port on host cores"
+        line = {"impl": "reference", "metric": metric, "value": ips, "unit": "images/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "Cityscapes->Foggy VGG16 SCAN config, condgraph middle head fwd+bwd, 800x1344 FPN features, "
-                                       "8 classes + bg; CPU arm runs 1+1 images per step", "settle_steps": args.settle},
+                "config": {"workload": workload + "; the CPU arm runs a bounded sample: 1 (+ 1) image per step", "settle_steps": args.settle},
                 "cpu_baseline": {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
                 "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -195,13 +364,13 @@ def main():
 
     if os.environ.get("SCAN_CUDNN_BENCHMARK", "1") == "1":
         torch.backends.cudnn.benchmark = True     # fixed shapes: let cuDNN pick the tower-convolution algorithms by measurement
-    cfg = scan_cfg("c2f")
+    tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
+    cfg = scan_cfg(preset)
     module = build_condgraph(cfg, 256)
     module.load_state_dict(fixture_state_dict(module, seed=99))
     module.to(dev)
     module.multihead_attn.p_drop = args.dropout
-    n = args.images
-    src_h, src_t, tgt_h = make_batches(n, pinned=True)
+    src_h, src_t, tgt_h = make_batches(n, num_fg, pinned=True)
     src_d = [f.to(dev) for f in src_h]
     tgt_d = [f.to(dev) for f in tgt_h]
     pretrain(module, src_d, src_t, args.settle)
@@ -211,13 +380,28 @@ def main():
         for p in module.parameters():
             dist.broadcast(p.data, 0)
         dist.broadcast(module.prototype, 0)
-    module.train()
+    state0 = {k_: v.detach().clone() for k_, v in module.state_dict().items()}
+    counter0 = module.counter_rnn.counter if hasattr(module, "counter_rnn") else None
     g = torch.Generator().manual_seed(5)
     # the module returns channels-last feature tensors; the FCOS head that consumes them hands back gradients in the same
     # memory format (cuDNN's backward-data follows its input), so the stand-in cotangents are channels-last as well
     cots = ([(torch.randn((n, 256, h, w), generator=g) / 1e5).to(dev).contiguous(memory_format=torch.channels_last)
              for h, w in FULL_SHAPES],
-            [(torch.randn((n, 9, h, w), generator=g) / 1e5).to(dev) for h, w in FULL_SHAPES])
+            [(torch.randn((n, k_cls, h, w), generator=g) / 1e5).to(dev) for h, w in FULL_SHAPES])
+    cls_logits = [torch.randn((n, num_fg, h, w), generator=g).to(dev) for h, w in FULL_SHAPES]
+    is_eval = args.config == "kitti-eval"
+    if is_eval:
+        module.eval()
+    else:
+        module.train()
+
+    def step_dev(feats_s, feats_t, ready=None, mode="precision"):
+        if is_eval:
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready[0])
+            _, probs = eval_step(module, feats_s, cls_logits, mode)
+            return [torch.stack([p_.reshape(-1)[0] for p_ in probs])]
+        return one_step(module, feats_s, src_t, feats_t, cots, ready=ready)
 
     def barrier():
         if world > 1:
@@ -226,7 +410,7 @@ def main():
 
     # ---------------- device-resident timing ----------------
     for _ in range(args.warmup):
-        one_step(module, [f.detach() for f in src_d], src_t, [f.detach() for f in tgt_d], cots)
+        step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -241,7 +425,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        one_step(module, [f.detach() for f in src_d], src_t, [f.detach() for f in tgt_d], cots)
+        step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
     e1.record()
     barrier()
     if profiling:
@@ -250,12 +434,31 @@ def main():
     launches = _lib.CALLS["launches"]
     ms = e0.elapsed_time(e1)
     kernel_ms = ops.timers_summary()
-    module.record = True      # one untimed recorded step: DBSCAN point counts and node counts of this workload
-    one_step(module, [f.detach() for f in src_d], src_t, [f.detach() for f in tgt_d], cots)
-    module.record = False
-    dbscan_info = module.last.get("dbscan_info")
-    n_nodes_t = module.last.get("sample_meta").n_nodes if module.last.get("sample_meta") is not None else 0
-    module.last = {}
+    ms_light = None
+    if is_eval:   # the second TEST.MODE of configs[3]
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(args.steps):
+            step_dev([f.detach() for f in src_d], None, mode="light")
+        l1.record()
+        barrier()
+        ms_light = l0.elapsed_time(l1)
+    # one untimed recorded step: node counts and DBSCAN point counts of this workload (they size the roofline table)
+    m_src = m_tgt = 0
+    db_points = []
+    if not is_eval:
+        module.record = True
+        one_pass(module, "source", [f.detach() for f in src_d], src_t, cots)
+        meta = module.last.get("sample_meta")
+        m_src = int(meta.n_nodes) if meta is not None else 0
+        one_pass(module, "target", [f.detach() for f in tgt_d], src_t, cots)
+        meta = module.last.get("sample_meta")
+        m_tgt = int(meta.n_nodes) if meta is not None else 0
+        info = module.last.get("dbscan_info")
+        db_points = info[:, 0].tolist() if info is not None else []
+        module.record = False
+        module.last = {}
 
     # ---------------- end-to-end timing: host inputs, H2D + D2H inside ----------------
     barrier()
@@ -266,7 +469,8 @@ def main():
     # fully exposed.
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
-    bufs = [([torch.empty(f.shape, device=dev) for f in src_h], [torch.empty(f.shape, device=dev) for f in tgt_h]) for _ in range(2)]
+    host_sets = (src_h,) if is_eval else (src_h, tgt_h)
+    bufs = [[[torch.empty(f.shape, device=dev) for f in hs] for hs in host_sets] for _ in range(2)]
     consumed = [None, None]   # event: the step that read buffer set b has finished
 
     def stage(b):
@@ -274,7 +478,7 @@ def main():
             if consumed[b] is not None:
                 copy_stream.wait_event(consumed[b])
             evs = []
-            for dst, src_ in ((bufs[b][0], src_h), (bufs[b][1], tgt_h)):     # the source pass can start before the target batch is in
+            for dst, src_ in zip(bufs[b], host_sets):     # the source pass can start before the target batch is in
                 for d_, h_ in zip(dst, src_):
                     d_.copy_(h_, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -290,7 +494,7 @@ def main():
         cur = ready
         if i + 1 < args.steps:
             ready = stage(b_ ^ 1)
-        res = one_step(module, [x.detach() for x in bufs[b_][0]], src_t, [x.detach() for x in bufs[b_][1]], cots, ready=cur)
+        res = step_dev([x.detach() for x in bufs[b_][0]], None if is_eval else [x.detach() for x in bufs[b_][1]], ready=cur)
         consumed[b_] = torch.cuda.Event()
         consumed[b_].record(main_stream)
         host = [r.cpu() for r in res if r is not None]
@@ -299,51 +503,76 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop_flag = True
-    h2d = sum(f.numel() * 4 for f in src_h) + sum(f.numel() * 4 for f in tgt_h)
+    h2d = sum(f.numel() * 4 for hs in host_sets for f in hs)
 
     t_all = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t_all[0]), float(t_all[1])
-    images = 2 * n * world * args.steps
+    images = (1 if is_eval else 2) * n * world * args.steps
     value = images / (ms / 1e3)
     e2e = images / (ms_e2e / 1e3)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        # roofline of the dominant hand-written kernel: conditional conv forward, 24.7 MB algorithmic per image
-        # (rows 22400*1024 B + K maps 22400*9*4 B + labels 22400*8 B); source launches carry labels
-        cc = kernel_ms.get("condconv_fwd", {"ms": 0.0, "calls": 0})
-        bytes_per_launch = n * L_PER_IMAGE * (1024 + 9 * 4) + n * L_PER_IMAGE * 8 * 0.5
-        ach = bytes_per_launch / (cc["ms"] / max(cc["calls"], 1) / 1e3) / 1e9 if cc["calls"] else None
-        roofline = {"kernel": "condconv_fwd_ts_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture at 8 images
-                    # (profiles/r01_hot_kernels_ncu_summary.txt: 185.3 + 9.3 MB), scaled to the images of this run
-                    "traffic": 194.6e6 * n / 8, "traffic_unit": "bytes/launch", "algorithmic_bytes": bytes_per_launch,
-                    "peak_source": peak_src}
+        hbm_peak, peak_src = peaks()
+        # ---- per-entry-point roofline table: algorithmic work of one step / CUDA-event time of the entry point in the step
+        table = []
+        if not is_eval:
+            work = work_model(n, k_cls, m_src, m_tgt, db_points)
+            for name, (bound, amount) in work.items():
+                t_ms = kernel_ms.get(name, {"ms": 0.0})["ms"] / args.steps
+                if t_ms <= 0:
+                    continue
+                if bound == "hbm":
+                    ach, peak, unit = amount / (t_ms * 1e-3) / 1e9, hbm_peak, "GB/s"
+                else:
+                    ach, peak, unit = amount / (t_ms * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
+                table.append({"entry": name, "bound": bound, "algorithmic": amount, "ms_per_step": t_ms, "achieved": ach, "peak": peak,
+                              "unit": unit, "frac": ach / peak})
+            table.sort(key=lambda r: -r["ms_per_step"])
+        roofline = None
+        if table:
+            top = table[0]
+            kern = DOMINANT_KERNEL.get(top["entry"], top["entry"])
+            roofline = {"kernel": kern, "entry": top["entry"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+                        "unit": top["unit"], "frac": top["frac"], "traffic": traffic_of(kern), "traffic_unit": "bytes/launch",
+                        "algorithmic_per_step": top["algorithmic"], "ms_per_step": top["ms_per_step"],
+                        "peak_source": ("cuBLAS tf32 8192^3 measured in this process (MEASURED_PEAKS recipe)" if top["bound"] == "tensor"
+                                        else peak_src),
+                        "note": "achieved = algorithmic flops (1x, not the 3x of 3xTF32) of the entry point per step / its CUDA-event time; "
+                                "the entry includes its small pre-pass kernels",
+                        "table": table}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             ips, t = cpu_reference_run(args, 3, 1)
             cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": "3 steps of 1 source + 1 target image (800x1344, K=9), oracle port on host cores"}
-        line = {"metric": "condgraph middle-head fwd+bwd images/s", "value": value, "unit": "images/s", "n_gpus": world,
+                   "sample": "3 steps of the bounded CPU sample (1 source + 1 target image, or 1 image for kitti-eval), oracle port on host cores"}
+        eager = None
+        if not args.no_eager_baseline and world == 1 and not is_eval:
+            try:
+                eager = eager_gpu_run(args, state0, counter0, src_d, src_t, tgt_d, cots)
+            except Exception as e:      # a baseline must never take the product's number down with it
+                eager = {"unavailable": repr(e)[:200]}
+        line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core conditional conv, fp32 accumulate)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core kernels, fp32 accumulate; tower convolutions cuDNN tf32)",
                 "data": "synthetic",
-                "config": {"workload": "Cityscapes->Foggy VGG16 SCAN config, condgraph middle head fwd+bwd, %d source + %d target "
-                                       "synthetic images per GPU per step, 800x1344 FPN features, 8 classes + bg" % (n, n),
+                "config": {"workload": workload, "name": args.config,
                            "parallelism": "dp%d (image shards, prototype all-reduce)" % world, "settle_steps": args.settle,
                            "attention_dropout": args.dropout,
-                           "towers": "3x3 convolutions = cuDNN NHWC tf32 implicit GEMM (torch's default allow_tf32), "
-                                     "cudnn.benchmark %s" % ("on" if torch.backends.cudnn.benchmark else "off"),
+                           "towers": "3x3 convolutions = cuDNN NHWC tf32 implicit GEMM (torch's default allow_tf32 = the reference's own GPU "
+                                     "arithmetic), cudnn.benchmark %s; parity runs force fp32 towers, the error at THESE flags is "
+                                     "recorded by tests/test_gpu_module.py::test_benchmark_flags_cudnn_tf32_error_is_reported"
+                                     % ("on" if torch.backends.cudnn.benchmark else "off"),
                            "e2e_input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i",
-                           "l2_note": "inputs 2x%d MB per step exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
+                           "l2_note": "inputs %d MB per pass exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-                "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kernel_ms.items()},
-                "dbscan_points_per_level": dbscan_info[:, 0].tolist() if dbscan_info is not None else None,
-                "target_nodes": n_nodes_t}
+                "eager_gpu_baseline": eager, "tf32_peak_tflops_measured": tf32_peak, "hbm_peak_gbs": hbm_peak,
+                "kernel_ms_per_step": {k_: v["ms"] / args.steps for k_, v in kernel_ms.items()},
+                "source_nodes": m_src, "target_nodes": m_tgt, "dbscan_points_per_level": db_points}
+        if ms_light is not None:
+            line["light_mode"] = {"value": images / (ms_light / 1e3), "unit": "images/s", "ms_per_step": ms_light / args.steps}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

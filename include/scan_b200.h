@@ -209,6 +209,42 @@ int scan_attn_bwd(const float* q, const float* k, const float* v, const float* c
                   float* dq, float* dk, float* dv, float* delta_ws, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* ---- K3a': the dense layers around the attention core and the node classifier, tcgen05 3xTF32 GEMMs (csrc/gemm.cu).
+ *      Replaces nn.Linear / nn.LayerNorm / nn.Dropout / F.cross_entropy of layers/transformer.py:43-49, 61-63, 84-88 and
+ *      condgraph.py:186-188, 400-402 (cuBLAS fp32 SIMT + ATen kernels in torch).  Channel width fixed at 256.
+ * scan_graph_workspace_bytes(m): workspace size accepted by every *_bwd entry point below for m nodes. */
+int64_t scan_graph_workspace_bytes(int32_t m);
+/* qkv [3, M, 256] (q | k | v, each a contiguous [M,256] matrix) = x [M,256] . w_qkv [768,256]^T + b_qkv [768] */
+int scan_qkv_fwd(const float* x, const float* w_qkv, const float* b_qkv, int32_t m, float* qkv, void* stream);
+/* d_x (+)= d_qkv . w_qkv (accumulate_dx != 0: added to the residual-branch gradient already in d_x);
+ * d_w_qkv [768,256] = d_qkv^T . x;  d_b_qkv [768] = column sums (deterministic). */
+int scan_qkv_bwd(const float* d_qkv, const float* x, const float* w_qkv, int32_t m, int32_t accumulate_dx, float* d_x,
+                 float* d_w_qkv, float* d_b_qkv, void* workspace, int64_t workspace_bytes, void* stream);
+/* y = LayerNorm(x + dropout(ctx . w_f^T + b_f)) * gamma + beta, fused in the GEMM epilogue (one TMEM lane = one node);
+ * the dropout mask is a counter hash of (seed, row, column); xhat [M,256] and rstd [M] are saved for the backward. */
+int scan_attn_out_ln_fwd(const float* ctx, const float* w_f, const float* b_f, const float* x, const float* gamma,
+                         const float* beta, int32_t m, float eps, float drop_p, uint64_t seed, float* y, float* xhat,
+                         float* rstd, void* stream);
+/* d_y -> d_x (residual branch), d_ctx, d_w_f [256,256], d_b_f [256], d_gamma_beta [512] = d_gamma | d_beta */
+int scan_attn_out_ln_bwd(const float* d_y, const float* xhat, const float* rstd, const float* gamma, const float* ctx,
+                         const float* w_f, int32_t m, float drop_p, uint64_t seed, float* d_x, float* d_ctx, float* d_w_f,
+                         float* d_b_f, float* d_gamma_beta, void* workspace, int64_t workspace_bytes, void* stream);
+/* loss (device scalar) = loss_weight * mean_m CE(relu(nodes . w1^T + b1) . w2^T + b2, labels - label_shift);
+ * hidden [M,512] and dlogits [M,16] (= softmax - onehot, columns >= K zero) are saved for the backward.
+ * workspace >= 8 * ceil(M / 128) + 256 bytes. */
+int scan_node_cls_fwd(const float* nodes, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const int64_t* labels, int32_t m, int32_t hidden_dim, int32_t num_classes, int32_t label_shift,
+                      float loss_weight, float* hidden, float* dlogits, float* loss, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+/* d_loss: device scalar d(total)/d(loss).  Outputs d_nodes [M,256], d_w1 [512,256], d_b1 [512], d_w2 [K,512], d_b2 [K]. */
+int scan_node_cls_bwd(const float* dlogits, const float* hidden, const float* nodes, const float* w1, const float* w2,
+                      int32_t m, int32_t hidden_dim, int32_t num_classes, float loss_weight, const float* d_loss,
+                      float* d_nodes, float* d_w1, float* d_b1, float* d_w2, float* d_b2, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+/* backward of the per-class node means (condgraph.py:395-398): d_nodes[m,:] = d_mean[label[m] - shift,:] / count */
+int scan_class_mean_bwd(const float* d_mean, const float* packed_sums, const int64_t* labels, int32_t m, int32_t channels,
+                        int32_t label_shift, float* d_nodes, void* stream);
+
 /* ---- K3b: per-class prototype sums + paradigm EMA (condgraph.py:395-398 class means;
  *      :558-617 update_prototype / _nx1 / _nx1_rnn) -------------------------------
  * scan_class_sums: sums[c, :] = sum of nodes with label c + label_shift... , sums[K*C + c] = count
@@ -258,10 +294,12 @@ int scan_sigmoid_focal_fwd(const float* logits, const int32_t* targets, int64_t 
 int scan_sigmoid_focal_bwd(const float* logits, const int32_t* targets, const float* d_losses,
                            int64_t n_rows, int32_t num_classes, float gamma, float alpha, float* d_logits,
                            void* stream);
-/* mode 0 'common': out = sigmoid(cls); 1 'light': out = act[:,1:]; 2 'precision': 0.5*sigmoid(cls)+0.5*act[:,1:]
- * cls [N, K-1, H, W] (may be NULL for light), act [N, K, H, W], out [N, K-1, H, W]; hw = H*W */
-int scan_ensemble(const float* cls_logits, const float* act, int32_t n_images, int32_t num_classes,
-                  int64_t hw, int32_t mode, float* out, void* stream);
+/* TEST.MODE ensembling of ALL levels in one launch.  mode 0 'common': out = sigmoid(cls); 1 'light': out = act[:,1:] (callers
+ * that can hand out a view do not need the kernel); 2 'precision': 0.5*sigmoid(cls)+0.5*act[:,1:].
+ * Per level l: cls [N, K-1, H_l, W_l] (array may be NULL for light), act [N, K, H_l, W_l], out [N, K-1, H_l, W_l];
+ * the three pointer arrays are HOST arrays of device pointers, like scan_pack_rows'. */
+int scan_ensemble_levels(const scan_levels_t* levels, const void* const* cls_logits_host, const void* const* act_host,
+                         int32_t num_classes, int32_t mode, void* const* out_host, void* stream);
 
 #ifdef __cplusplus
 }

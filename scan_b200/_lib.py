@@ -62,6 +62,14 @@ SIGNATURES = {
     "scan_attn_bwd_workspace_bytes": (c_int64, [c_int32]),
     "scan_attn_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P, _P, _P, c_int64,
                                 _P]),
+    "scan_graph_workspace_bytes": (c_int64, [c_int32]),
+    "scan_qkv_fwd": (c_int32, [_P, _P, _P, c_int32, _P, _P]),
+    "scan_qkv_bwd": (c_int32, [_P, _P, _P, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P]),
+    "scan_attn_out_ln_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_float, c_uint64, _P, _P, _P, _P]),
+    "scan_attn_out_ln_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_uint64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "scan_node_cls_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, c_int64, _P]),
+    "scan_node_cls_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "scan_class_mean_bwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
     "scan_class_sums": (c_int32, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "scan_proto_update": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P]),
     "scan_dbscan_workspace_bytes": (c_int64, [c_int64]),
@@ -70,7 +78,7 @@ SIGNATURES = {
     "scan_dbscan_points": (c_int32, [_P, c_int32, c_int32, c_double, c_int32, _P, _P, _P, c_int64, _P]),
     "scan_sigmoid_focal_fwd": (c_int32, [_P, _P, c_int64, c_int32, c_float, c_float, _P, _P]),
     "scan_sigmoid_focal_bwd": (c_int32, [_P, _P, _P, c_int64, c_int32, c_float, c_float, _P, _P]),
-    "scan_ensemble": (c_int32, [_P, _P, c_int32, c_int32, c_int64, c_int32, _P, _P]),
+    "scan_ensemble_levels": (c_int32, [_LV, _P, _P, c_int32, c_int32, _P, _P]),
 }
 
 _lib = None
@@ -78,7 +86,9 @@ _lib = None
 LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_fcos_assign": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
             "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_attn_fwd": 2, "scan_attn_bwd": 4,
             "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
-            "scan_sigmoid_focal_fwd": 1, "scan_sigmoid_focal_bwd": 1, "scan_ensemble": 1}
+            "scan_qkv_fwd": 1, "scan_qkv_bwd": 9, "scan_attn_out_ln_fwd": 1, "scan_attn_out_ln_bwd": 9, "scan_node_cls_fwd": 3,
+            "scan_node_cls_bwd": 9, "scan_class_mean_bwd": 1,
+            "scan_sigmoid_focal_fwd": 1, "scan_sigmoid_focal_bwd": 1, "scan_ensemble_levels": 1}
 CALLS = {"n": 0, "launches": 0}
 
 

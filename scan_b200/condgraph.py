@@ -106,7 +106,8 @@ class GRAPHHead(nn.Module):
 
 
 class MultiHeadAttention(nn.Module):
-    """Parameters of layers/transformer.py:36-90; the attention itself runs in scan_attn_fwd/bwd."""
+    """Parameters of layers/transformer.py:36-90; the arithmetic runs in scan_qkv_fwd / scan_attn_fwd / scan_attn_out_ln_fwd
+    and their backward entry points (no torch / cuBLAS op on this path)."""
 
     def __init__(self, model_dim=256, num_heads=4, dropout=0.1):
         super().__init__()
@@ -121,18 +122,14 @@ class MultiHeadAttention(nn.Module):
 
     def forward(self, x):
         """x [M,256] (the reference passes (key, value, query) = (x, x, x), condgraph.py:392)."""
-        q, k, v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
-        scale = float((self.dim_per_head // self.num_heads) ** -0.5)      # transformer.py:75 -> 0.25
         p = self.p_drop if self.training else 0.0
         seed = 0
         if p > 0:
             # one 63-bit draw per call from torch's default CPU generator: the masks follow torch.manual_seed / get_rng_state /
             # fork_rng and a checkpoint's RNG state like nn.Dropout does, and differ per rank when the ranks' generators do
             seed = int(torch.randint(0, 0x7FFFFFFFFFFFFFFF, (1,), dtype=torch.int64).item())
-        ctx = ops.chunked_attention(q, k, v, scale, p, seed)
-        out = self.linear_final(ctx)
-        out = F.dropout(out, p, self.training)
-        return self.layer_norm(x + out)
+        # projections, attention core, linear_final + dropout + residual LayerNorm: four tcgen05 launches, one autograd node
+        return ops.graph_attention(x, self, p, seed)
 
 
 def sim_matrix(a, b, eps=1e-8):
@@ -258,10 +255,10 @@ class GRAPHModule(nn.Module):
                 nodes = nodes + pos_points
         else:
             nodes = self._local_gcn(pos_points, pos_labels, shift)
-        packed = ops.class_sums(nodes, pos_labels, k, shift)
-        logits = self.proto_cls(torch.relu(self.proto_cls_hidden(nodes)))
-        node_loss = self.lamda1 * F.cross_entropy(logits, pos_labels - shift)
-        return node_loss, packed, nodes
+        # per-class means (differentiable: the target branch feeds them to the transfer losses) + the sum|count buffer
+        means, packed = ops.class_means(nodes, pos_labels, k, shift)
+        node_loss = ops.node_classifier_loss(nodes, self.proto_cls_hidden, self.proto_cls, pos_labels, shift, self.lamda1)
+        return node_loss, packed, nodes, means
 
     def _local_gcn(self, pos_points, pos_labels, shift):
         """Per-class GCN (condgraph.py:262-302, 404-414): Adj = softmax(affinity).detach(); two graph convolutions."""
@@ -347,7 +344,7 @@ class GRAPHModule(nn.Module):
         smp = ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels)
         self._record_nodes(geo, smp, labels=labels)
         pos_points = ops.gather_rows(rows, smp.node_rows)
-        node_loss, packed, _ = self._forward_gcns(pos_points, smp.node_labels)
+        node_loss, packed, _, _ = self._forward_gcns(pos_points, smp.node_labels)
         proto_batch = self.update_prototype_ensemble(packed)
         weight, bias = self._split_kernel(self.get_conded_weight())
         if self.record:
@@ -446,12 +443,9 @@ class GRAPHModule(nn.Module):
         out = self.features_post_processing(features, acts)
         if smp.n_nodes > 0 and (self.transfer_cfg[0] is not None or self.with_self_training):
             pos_points = ops.gather_rows(rows, smp.node_rows)
-            node_loss, packed, nodes = self._forward_gcns(pos_points, smp.node_labels)
-            node_loss = self.lamda4 * node_loss
-            cnt = packed[:, -1:]
-            tg_proto = torch.where(cnt > 0, packed[:, :-1] / cnt.clamp(min=1.0), torch.zeros_like(packed[:, :-1]))
             # the class means feed the transfer losses WITH gradient in the reference (condgraph.py:398, 526)
-            tg_proto = self._class_means_with_grad(nodes, smp.node_labels, tg_proto)
+            node_loss, packed, nodes, tg_proto = self._forward_gcns(pos_points, smp.node_labels)
+            node_loss = self.lamda4 * node_loss
             # with GLOBAL_GCN=False the reference has overwritten the sampled rows in place (condgraph.py:413)
             tl_nodes = pos_points if self.with_global_gcn else nodes
             transfer_loss = self.get_transfer_loss(tg_proto, tl_nodes, smp.node_labels)
@@ -461,15 +455,6 @@ class GRAPHModule(nn.Module):
                 return out, (node_loss, transfer_loss), None, acts
             return out, (None, transfer_loss), None, acts
         return out, None, None, acts
-
-    def _class_means_with_grad(self, nodes, labels, proto_values):
-        """prototype_batch[c] = nodes[labels == c].mean(0) as a differentiable function of `nodes`
-        (condgraph.py:395-398); values come from the scan_class_sums kernel, the gradient is the mean's."""
-        shift = 0 if self.with_bg_proto else 1
-        onehot = F.one_hot(labels - shift, self.used_num_classes).to(nodes.dtype)       # [M,K]
-        cnt = onehot.sum(0).clamp(min=1.0)
-        mean = (onehot / cnt).t() @ nodes
-        return mean + (proto_values - mean).detach()
 
     def _forward_inference(self, images, features, targets=None, return_maps=False):
         geo = ops.Geometry.of(features, self.fpn_strides)

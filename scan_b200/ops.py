@@ -530,6 +530,157 @@ def chunked_attention(q, k, v, scale=0.25, drop_p=0.0, seed=0):
 
 
 # ----------------------------------------------------------------------------------------------------
+# K3a': the dense layers around the attention core and the node classifier (tcgen05 3xTF32 GEMMs, csrc/gemm.cu)
+# ----------------------------------------------------------------------------------------------------
+def _graph_ws(m, device):
+    return torch.empty((_lib.lib().scan_graph_workspace_bytes(m),), device=device, dtype=torch.uint8)
+
+
+class _GraphAttention(torch.autograd.Function):
+    """MultiHeadAttention.forward (layers/transformer.py:53-90) for key = value = query = x [M,256]:
+    q,k,v projections -> chunked attention -> linear_final -> dropout -> LayerNorm(x + .), one autograd node."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, wf, bf, gamma, beta, scale, drop_p, seed, eps):
+        x = x.contiguous()
+        m = x.shape[0]
+        dev = x.device
+        w_qkv = torch.cat([wq, wk, wv]).contiguous()            # [768,256]: q | k | v output parts
+        b_qkv = torch.cat([bq, bk, bv]).contiguous()
+        wf, bf, gamma, beta = wf.contiguous(), bf.contiguous(), gamma.contiguous(), beta.contiguous()
+        qkv = torch.empty((3, m, C), device=dev, dtype=torch.float32)
+        call("scan_qkv_fwd", _ptr(x), _ptr(w_qkv), _ptr(b_qkv), m, _ptr(qkv), _stream())
+        att = torch.empty((m, C), device=dev, dtype=torch.float32)
+        lse = torch.empty((4 * m,), device=dev, dtype=torch.float32)
+        ws = torch.empty((_lib.lib().scan_attn_workspace_bytes(m),), device=dev, dtype=torch.uint8)
+        call("scan_attn_fwd", _ptr(qkv[0]), _ptr(qkv[1]), _ptr(qkv[2]), m, scale, drop_p, seed, _ptr(att), _ptr(lse), _ptr(ws),
+             ws.numel(), _stream())
+        y = torch.empty((m, C), device=dev, dtype=torch.float32)
+        xhat = torch.empty((m, C), device=dev, dtype=torch.float32)
+        rstd = torch.empty((m,), device=dev, dtype=torch.float32)
+        call("scan_attn_out_ln_fwd", _ptr(att), _ptr(wf), _ptr(bf), _ptr(x), _ptr(gamma), _ptr(beta), m, eps, drop_p,
+             seed ^ 0x5DEECE66D, _ptr(y), _ptr(xhat), _ptr(rstd), _stream())
+        ctx.save_for_backward(x, w_qkv, qkv, att, lse, wf, gamma, xhat, rstd)
+        ctx.cfg = (scale, drop_p, seed)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_y):
+        x, w_qkv, qkv, att, lse, wf, gamma, xhat, rstd = ctx.saved_tensors
+        scale, drop_p, seed = ctx.cfg
+        m = x.shape[0]
+        dev = x.device
+        d_y = d_y.contiguous()
+        ws = _graph_ws(m, dev)
+        d_x = torch.empty_like(x)
+        d_att = torch.empty_like(x)
+        d_wf = torch.empty_like(wf)
+        d_bf = torch.empty((C,), device=dev, dtype=torch.float32)
+        d_gb = torch.empty((2 * C,), device=dev, dtype=torch.float32)
+        call("scan_attn_out_ln_bwd", _ptr(d_y), _ptr(xhat), _ptr(rstd), _ptr(gamma), _ptr(att), _ptr(wf), m, drop_p,
+             seed ^ 0x5DEECE66D, _ptr(d_x), _ptr(d_att), _ptr(d_wf), _ptr(d_bf), _ptr(d_gb), _ptr(ws), ws.numel(), _stream())
+        d_qkv = torch.empty_like(qkv)
+        delta = torch.empty((4 * m,), device=dev, dtype=torch.float32)
+        ws2 = torch.empty((_lib.lib().scan_attn_bwd_workspace_bytes(m),), device=dev, dtype=torch.uint8)
+        call("scan_attn_bwd", _ptr(qkv[0]), _ptr(qkv[1]), _ptr(qkv[2]), _ptr(att), _ptr(lse), _ptr(d_att), m, scale, drop_p, seed,
+             _ptr(d_qkv[0]), _ptr(d_qkv[1]), _ptr(d_qkv[2]), _ptr(delta), _ptr(ws2), ws2.numel(), _stream())
+        d_w = torch.empty_like(w_qkv)
+        d_b = torch.empty((3 * C,), device=dev, dtype=torch.float32)
+        call("scan_qkv_bwd", _ptr(d_qkv), _ptr(x), _ptr(w_qkv), m, 1, _ptr(d_x), _ptr(d_w), _ptr(d_b), _ptr(ws), ws.numel(), _stream())
+        return (d_x, d_w[:C], d_b[:C], d_w[C:2 * C], d_b[C:2 * C], d_w[2 * C:], d_b[2 * C:], d_wf, d_bf, d_gb[:C], d_gb[C:],
+                None, None, None, None)
+
+
+def graph_attention(x, attn, drop_p, seed):
+    """attn: module holding linear_q/k/v/final + layer_norm (layers/transformer.py:36-52)."""
+    if x.shape[1] != C or not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("graph_attention expects CUDA fp32 [M,256] nodes (no CPU fallback)")
+    scale = float((attn.dim_per_head // attn.num_heads) ** -0.5)          # transformer.py:75 -> 0.25
+    return _GraphAttention.apply(x, attn.linear_q.weight, attn.linear_q.bias, attn.linear_k.weight, attn.linear_k.bias,
+                                 attn.linear_v.weight, attn.linear_v.bias, attn.linear_final.weight, attn.linear_final.bias,
+                                 attn.layer_norm.weight, attn.layer_norm.bias, scale, float(drop_p), int(seed),
+                                 float(attn.layer_norm.eps))
+
+
+class _NodeClassifier(torch.autograd.Function):
+    """loss_weight * CE(proto_cls(relu(proto_cls_hidden(nodes))), labels - shift) (condgraph.py:400-402)."""
+
+    @staticmethod
+    def forward(ctx, nodes, w1, b1, w2, b2, labels, shift, loss_weight):
+        nodes = nodes.contiguous()
+        w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+        m, dev = nodes.shape[0], nodes.device
+        k, h = w2.shape[0], w1.shape[0]
+        hidden = torch.empty((m, h), device=dev, dtype=torch.float32)
+        dlogits = torch.empty((m, 16), device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        ws = torch.empty((1024 + 8 * ((m + 127) // 128),), device=dev, dtype=torch.uint8)
+        call("scan_node_cls_fwd", _ptr(nodes), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(labels), m, h, k, shift, loss_weight,
+             _ptr(hidden), _ptr(dlogits), _ptr(loss), _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(nodes, w1, w2, hidden, dlogits)
+        ctx.cfg = (k, h, loss_weight)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_loss):
+        nodes, w1, w2, hidden, dlogits = ctx.saved_tensors
+        k, h, loss_weight = ctx.cfg
+        m, dev = nodes.shape[0], nodes.device
+        d_loss = d_loss.to(torch.float32).reshape(1).contiguous()
+        ws = _graph_ws(m, dev)
+        d_nodes = torch.empty_like(nodes)
+        d_w1, d_w2 = torch.empty_like(w1), torch.empty_like(w2)
+        d_b1 = torch.empty((h,), device=dev, dtype=torch.float32)
+        d_b2 = torch.empty((k,), device=dev, dtype=torch.float32)
+        call("scan_node_cls_bwd", _ptr(dlogits), _ptr(hidden), _ptr(nodes), _ptr(w1), _ptr(w2), m, h, k, loss_weight, _ptr(d_loss),
+             _ptr(d_nodes), _ptr(d_w1), _ptr(d_b1), _ptr(d_w2), _ptr(d_b2), _ptr(ws), ws.numel(), _stream())
+        return d_nodes, d_w1, d_b1, d_w2, d_b2, None, None, None
+
+
+def node_classifier_loss(nodes, hidden_layer, out_layer, labels, label_shift, loss_weight):
+    if nodes.shape[1] != C or hidden_layer.weight.shape != (512, C) or out_layer.weight.shape[0] > _lib.SCAN_MAX_CLASSES:
+        raise RuntimeError("node classifier kernel is built for Linear(256,512) -> Linear(512,K<=16)")
+    if not nodes.is_cuda:
+        raise RuntimeError("node_classifier_loss needs CUDA tensors (no CPU fallback)")
+    if nodes.shape[0] == 0:
+        raise RuntimeError("node_classifier_loss: no nodes")
+    return _NodeClassifier.apply(nodes, hidden_layer.weight, hidden_layer.bias, out_layer.weight, out_layer.bias, labels,
+                                 int(label_shift), float(loss_weight))
+
+
+class _ClassMeans(torch.autograd.Function):
+    """prototype_batch[c] = nodes[labels == c + shift].mean(0), zero for absent classes (condgraph.py:395-398), differentiable."""
+
+    @staticmethod
+    def forward(ctx, nodes, labels, num_classes, shift):
+        nodes = nodes.contiguous()
+        packed = class_sums(nodes, labels, num_classes, shift)
+        cnt = packed[:, -1:]
+        means = torch.where(cnt > 0, packed[:, :-1] / cnt.clamp(min=1.0), torch.zeros_like(packed[:, :-1]))
+        ctx.save_for_backward(packed, labels)
+        ctx.cfg = (nodes.shape[0], nodes.shape[1], shift)
+        ctx.mark_non_differentiable(packed)
+        return means, packed
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_means, _d_packed):
+        packed, labels = ctx.saved_tensors
+        m, c, shift = ctx.cfg
+        d_nodes = torch.empty((m, c), device=packed.device, dtype=torch.float32)
+        d_means = d_means.contiguous()
+        call("scan_class_mean_bwd", _ptr(d_means), _ptr(packed), _ptr(labels), m, c, shift, _ptr(d_nodes), _stream())
+        return d_nodes, None, None, None
+
+
+def class_means(nodes, labels, num_classes, label_shift):
+    """Returns (means [K,C] with gradient, packed [K,C+1] sum|count buffer)."""
+    return _ClassMeans.apply(nodes, labels, int(num_classes), int(label_shift))
+
+
+# ----------------------------------------------------------------------------------------------------
 # K3b: prototype sums + EMA
 # ----------------------------------------------------------------------------------------------------
 def class_sums(nodes, labels, num_classes, label_shift):
@@ -618,11 +769,20 @@ def sigmoid_focal_loss(logits, targets, gamma, alpha):
 _MODES = {"common": 0, "light": 1, "precision": 2}
 
 
+def ensemble_levels(mode, cls_logits, acts):
+    """TEST.MODE map ensembling of all levels (fcos.py:162-169 + inference.py:68): list of class-probability maps
+    [N,K-1,H_l,W_l].  One launch for every level; 'light' is a zero-copy view of the activation maps."""
+    if mode == "light":
+        return [a[:, 1:] for a in acts]
+    acts = [a.contiguous() for a in acts]
+    cls = [c.contiguous() for c in cls_logits]
+    n, k = acts[0].shape[:2]
+    geo = Geometry([tuple(a.shape[-2:]) for a in acts], [1] * len(acts), n)
+    outs = [torch.empty((n, k - 1) + tuple(a.shape[-2:]), device=a.device, dtype=torch.float32) for a in acts]
+    call("scan_ensemble_levels", geo.ref(), _ptr_array(cls), _ptr_array(acts), k, _MODES[mode], _ptr_array(outs), _stream())
+    return outs
+
+
 def ensemble(mode, cls_logits, act):
-    """TEST.MODE map ensembling of one level (fcos.py:162-169 + inference.py:68): class probabilities [N,K-1,H,W]."""
-    act = act.contiguous()
-    n, k, h, w = act.shape
-    out = torch.empty((n, k - 1, h, w), device=act.device, dtype=torch.float32)
-    cls = None if cls_logits is None else cls_logits.contiguous()
-    call("scan_ensemble", _ptr(cls), _ptr(act), n, k, h * w, _MODES[mode], _ptr(out), _stream())
-    return out
+    """One level (kept for callers that hold a single map)."""
+    return ensemble_levels(mode, None if cls_logits is None else [cls_logits], [act])[0]

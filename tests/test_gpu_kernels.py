@@ -441,11 +441,14 @@ def test_dbscan_threshold_band_is_rechecked_in_fp64():
     assert int(info.cpu()[5]) > 0   # the fp64 path was actually taken
 
 
-def test_sigmoid_focal_and_ensemble():
-    g = torch.Generator().manual_seed(2)
-    r, c = 5000, 8
+@pytest.mark.parametrize("r,c", [(5000, 8), (179200, 8), (4097, 2), (333, 1), (1000, 5), (64, 4)])
+def test_sigmoid_focal_rows_kernels(r, c):
+    """a17: thread-per-row kernels (C = 8 / 4 / 2 / 1 vectorised, generic C) vs the reference formulas, incl. ignored rows (t < 0),
+    background rows (t = 0) and out-of-range class ids."""
+    g = torch.Generator().manual_seed(2 + c)
     logits = torch.randn(r, c, generator=g) * 3
-    targets = torch.randint(-1, c + 1, (r,), generator=g).int()
+    logits[0, 0], logits[1, 0] = 95.0, -95.0           # p saturates / underflows: the reference's log(max(p, FLT_MIN)) clamp
+    targets = torch.randint(-1, c + 2, (r,), generator=g).int()
     lr = logits.clone().requires_grad_(True)
     want = orc.sigmoid_focal_loss_elementwise(lr, targets, 2.0, 0.25)
     cot = torch.randn(r, c, generator=g)
@@ -455,9 +458,128 @@ def test_sigmoid_focal_and_ensemble():
     (got * cot.to(DEV)).sum().backward()
     _close(got, want, 1e-5, "sigmoid focal fwd")
     _close(ld.grad, lr.grad, 1e-5, "sigmoid focal bwd")
-    act = torch.rand(2, 9, 13, 21, generator=g)
-    cls = torch.randn(2, 8, 13, 21, generator=g)
+    # a non-default gamma takes the powf branch
+    want15 = orc.sigmoid_focal_loss_elementwise(logits[:512], targets[:512], 1.5, 0.4)
+    got15 = ops.sigmoid_focal_loss(logits[:512].to(DEV), targets[:512].to(DEV), 1.5, 0.4)
+    _close(got15, want15, 2e-5, "sigmoid focal gamma 1.5")
+
+
+def test_ensemble_all_levels_one_launch():
+    g = torch.Generator().manual_seed(2)
+    acts = [torch.rand(2, 9, h, w, generator=g) for h, w in SHAPES]
+    cls = [torch.randn(2, 8, h, w, generator=g) for h, w in SHAPES]
     for mode in ("common", "light", "precision"):
-        want = orc.ensemble(mode, [cls], [act])[0]
-        got = ops.ensemble(mode, None if mode == "light" else cls.to(DEV), act.to(DEV))
-        _close(got, want, 1e-6, "ensemble " + mode)
+        want = orc.ensemble(mode, cls, acts)
+        got = ops.ensemble_levels(mode, None if mode == "light" else [c.to(DEV) for c in cls], [a.to(DEV) for a in acts])
+        for l in range(len(SHAPES)):
+            _close(got[l], want[l], 1e-6, "ensemble %s level %d" % (mode, l))
+    one = ops.ensemble("precision", cls[1].to(DEV), acts[1].to(DEV))
+    _close(one, orc.ensemble("precision", [cls[1]], [acts[1]])[0], 1e-6, "single level")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K3a': tcgen05 3xTF32 dense layers (csrc/gemm.cu) against float64 torch on the same GPU
+# ---------------------------------------------------------------------------------------------------------------------
+class _Mha(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.dim_per_head, self.num_heads = 64, 4
+        self.linear_k, self.linear_v, self.linear_q = [torch.nn.Linear(256, 256) for _ in range(3)]
+        self.linear_final = torch.nn.Linear(256, 256)
+        self.layer_norm = torch.nn.LayerNorm(256)
+
+
+def _mha_ref64(a, x):
+    m = x.shape[0]
+    q, k, v = a.linear_q(x), a.linear_k(x), a.linear_v(x)
+    att = torch.softmax(torch.bmm(q.reshape(4, m, 64), k.reshape(4, m, 64).transpose(1, 2)) * 0.25, dim=2)
+    ctx = torch.bmm(att, v.reshape(4, m, 64)).reshape(m, 256)
+    return a.layer_norm(x + a.linear_final(ctx))
+
+
+@pytest.mark.parametrize("m", [1, 10, 130, 1048, 3000])
+def test_graph_attention_block_matches_float64(m):
+    """q/k/v projections + attention + linear_final + residual LayerNorm as ONE op (four tcgen05 launches forward) vs float64
+    torch: output, d(x) and all ten parameter gradients."""
+    torch.manual_seed(m)
+    a = _Mha().to(DEV)
+    for p_ in a.parameters():
+        p_.data.mul_(1.5)
+    x = torch.randn(m, 256, device=DEV)
+    cot = torch.randn(m, 256, device=DEV)
+    a64 = _Mha().to(DEV).double()
+    a64.load_state_dict({k: v.double() for k, v in a.state_dict().items()})
+    x64 = x.double().requires_grad_(True)
+    y64 = _mha_ref64(a64, x64)
+    (y64 * cot.double()).sum().backward()
+    xd = x.clone().requires_grad_(True)
+    y = ops.graph_attention(xd, a, 0.0, 0)
+    (y * cot).sum().backward()
+    _close(y, y64, 2e-5, "y")
+    _close(xd.grad, x64.grad, 1e-4, "dx")
+    for (n, p_), (_, p64) in zip(a.named_parameters(), a64.named_parameters()):
+        _close(p_.grad, p64.grad, 1e-4, "d_" + n, atol=1e-5)
+
+
+def test_graph_attention_dropout_backward_is_consistent():
+    """Both dropouts on (attention probabilities + linear_final output): the backward must use the masks of the forward.
+    Directional finite difference of the op itself (smooth for a fixed mask)."""
+    torch.manual_seed(5)
+    m = 400
+    a = _Mha().to(DEV)
+    x = torch.randn(m, 256, device=DEV)
+    cot = torch.randn(m, 256, device=DEV)
+    d = torch.randn(m, 256, device=DEV)
+    xd = x.clone().requires_grad_(True)
+    y = ops.graph_attention(xd, a, 0.1, 777)
+    y2 = ops.graph_attention(x, a, 0.1, 777)
+    assert torch.equal(y, y2)
+    assert not torch.equal(y, ops.graph_attention(x, a, 0.1, 778))
+    (y * cot).sum().backward()
+    h = 1e-2
+    with torch.no_grad():
+        fp = (ops.graph_attention(x + h * d, a, 0.1, 777).double() * cot.double()).sum()
+        fm = (ops.graph_attention(x - h * d, a, 0.1, 777).double() * cot.double()).sum()
+    fd = float((fp - fm) / (2 * h))
+    an = float((xd.grad.double() * d.double()).sum())
+    assert abs(fd - an) <= 2e-2 * max(abs(an), 1.0), (fd, an)
+
+
+@pytest.mark.parametrize("m,k,shift", [(1, 9, 0), (77, 9, 0), (1000, 2, 0), (8888, 9, 0), (500, 8, 1)])
+def test_node_classifier_loss_matches_float64(m, k, shift):
+    torch.manual_seed(m + k)
+    hid, out = torch.nn.Linear(256, 512).to(DEV), torch.nn.Linear(512, k).to(DEV)
+    nodes = torch.randn(m, 256, device=DEV)
+    labels = torch.randint(shift, k + shift, (m,), device=DEV)
+    lam = 0.7
+    h64, o64 = torch.nn.Linear(256, 512).to(DEV).double(), torch.nn.Linear(512, k).to(DEV).double()
+    h64.load_state_dict({n: v.double() for n, v in hid.state_dict().items()})
+    o64.load_state_dict({n: v.double() for n, v in out.state_dict().items()})
+    n64 = nodes.double().requires_grad_(True)
+    want = lam * torch.nn.functional.cross_entropy(o64(torch.relu(h64(n64))), labels - shift)
+    (want * 1.7).backward()
+    nd = nodes.clone().requires_grad_(True)
+    got = ops.node_classifier_loss(nd, hid, out, labels, shift, lam)
+    (got * 1.7).backward()
+    _close(got, want, 2e-5, "loss")
+    _close(nd.grad, n64.grad, 1e-4, "d_nodes", atol=1e-7)
+    for name, a, b in (("w1", hid.weight, h64.weight), ("b1", hid.bias, h64.bias), ("w2", out.weight, o64.weight), ("b2", out.bias, o64.bias)):
+        _close(a.grad, b.grad, 1e-4, "d_" + name, atol=1e-7)
+
+
+def test_class_means_forward_and_backward():
+    g = torch.Generator().manual_seed(8)
+    m, k = 2000, 9
+    nodes = torch.randn(m, 256, generator=g)
+    labels = torch.randint(0, k, (m,), generator=g)
+    labels[labels == 5] = 6          # class 5 absent
+    cot = torch.randn(k, 256, generator=g)
+    nr = nodes.clone().requires_grad_(True)
+    want = torch.stack([nr[labels == c].mean(0) if (labels == c).any() else torch.zeros(256) for c in range(k)])
+    (want * cot).sum().backward()
+    nd = nodes.to(DEV).requires_grad_(True)
+    means, packed = ops.class_means(nd, labels.to(DEV), k, 0)
+    (means * cot.to(DEV)).sum().backward()
+    _close(means, want, 1e-5, "class means")
+    _close(nd.grad, nr.grad, 1e-6, "d_nodes")
+    assert float(packed[5, 256]) == 0.0
