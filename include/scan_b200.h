@@ -260,6 +260,34 @@ int scan_proto_update(const float* packed_sums, int32_t num_classes, int32_t cha
                       int32_t slot, int32_t shift, int32_t cosine_on, float momentum, float* prototype,
                       float* proto_batch_out, void* stream);
 
+/* ---- K4a': manifestation without the RNN (condgraph.py:320-334): tiny-batch dense layers over the K <= 16 paradigm rows ----
+ * y [K, O] = act(x [K, I] . w [O, I]^T + b); relu != 0 applies ReLU.  I % 4 == 0, K * I * 4 bytes <= 200 KB. */
+int scan_rows_linear_fwd(const float* x, const float* w, const float* b, int32_t k, int32_t in_dim, int32_t out_dim, int32_t relu,
+                         float* y, void* stream);
+/* y = the forward output (read only when relu != 0); d_b and d_x may be NULL */
+int scan_rows_linear_bwd(const float* x, const float* w, const float* dy, const float* y, int32_t k, int32_t in_dim, int32_t out_dim,
+                         int32_t relu, float* d_w, float* d_b, float* d_x, void* stream);
+/* y = relu(group_norm(x [K, C], groups)) per row (F.group_norm on a 2-D tensor, condgraph.py:326-327); stats [K, groups, 2] */
+int scan_rows_gn_relu_fwd(const float* x, const float* gamma, const float* beta, int32_t k, int32_t channels, int32_t groups, float eps,
+                          float* y, float* stats, void* stream);
+int scan_rows_gn_relu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* stats, int32_t k,
+                          int32_t channels, int32_t groups, float* d_x, float* d_gamma, float* d_beta, void* stream);
+
+/* ---- a14: transfer (graph-matching) losses of the target branch (condgraph.py:457-498, sim_matrix :35-43) ----------
+ * prototype: the module's paradigm buffer [K, 256, P] (P == 1: [K, 256]); sr_proto = prototype.mean(-1) is taken in-kernel.
+ * NODES: loss = KLDivLoss(reduction='mean')(softmax(nodes).log(), softmax(sr_proto[labels])); diff [M,256] = softmax(nodes) -
+ * target is saved and IS the gradient up to the scalar d_loss / (M * 256).  partials: scan_transfer_nodes_num_partials() doubles. */
+int32_t scan_transfer_nodes_num_partials(void);
+int scan_transfer_nodes_fwd(const float* nodes, const int64_t* labels, const float* prototype, int32_t proto_iter, int32_t m,
+                            int32_t num_classes, float* diff, double* partials, float* loss, void* stream);
+int scan_transfer_nodes_bwd(const float* diff, const float* d_loss, int32_t m, float* d_nodes, void* stream);
+/* flags bit 0 PROTOTYPE (KL over the classes present in the target batch), bit 1 ADJ, bit 2 ADJ_COMPLETE (1 - cosine of the
+ * flattened class-affinity matrices).  "present" = tg_proto row sum != 0, kept on the device (the reference's boolean-mask
+ * indexing synchronises).  losses4 = [PROTOTYPE, ADJ, ADJ_COMPLETE, total (+ *add_in if given)];
+ * d_tg_proto [K,256] = d(sum of the enabled losses)/d(tg_proto). */
+int scan_transfer_proto(const float* tg_proto, const float* prototype, int32_t proto_iter, int32_t num_classes, int32_t flags,
+                        const float* add_in, float* losses4, float* d_tg_proto, void* stream);
+
 /* ---- K2: DBSCAN target-node sampling (loss.py:397-423 DBSCAN_batch_cpu; sklearn.cluster.DBSCAN
  *      eps=DBSCAN_EPS, min_samples=5, euclidean, brute) ------------------------------------------------
  * One level per call.  act_nchw [N, K, H, W] (channel 0 = background), rows_level = first row of the

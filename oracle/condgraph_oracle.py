@@ -392,12 +392,29 @@ def sigmoid_focal_loss_elementwise(logits, targets, gamma, alpha):
     cls = torch.arange(1, c + 1, dtype=targets.dtype).unsqueeze(0)
     t = targets.unsqueeze(1)
     p = torch.sigmoid(logits)
-    term1 = (1 - p) ** gamma * torch.log(p)
+    # SigmoidFocalLoss_cuda.cu:45: logf(max(p, FLT_MIN)) -- the CUDA kernel (the one the reference trains with) clamps, the
+    # CPU mirror (layers/sigmoid_focal_loss.py:50) does not; they differ only where sigmoid(x) is subnormal (x < -87.3)
+    term1 = (1 - p) ** gamma * torch.log(p.clamp(min=1.17549435e-38))
     # CUDA kernel uses the stable form of log(1-p): -x*(x>=0) - log(1+exp(x-2x*(x>=0)))
     xs = logits
     log1mp = -xs * (xs >= 0).float() - torch.log1p(torch.exp(xs - 2 * xs * (xs >= 0).float()))
     term2 = p ** gamma * log1mp
     return -(t == cls).float() * term1 * alpha - ((t != cls) & (t >= 0)).float() * term2 * (1 - alpha)
+
+
+def sigmoid_focal_loss_backward_elementwise(logits, targets, d_losses, gamma, alpha):
+    """csrc/cuda/SigmoidFocalLoss_cuda.cu:61-101: the reference's ANALYTIC backward (what `_C.sigmoid_focalloss_backward`
+    returns).  It differentiates log(p) without the FLT_MIN clamp of the forward, so it differs from autograd of
+    `sigmoid_focal_loss_elementwise` where sigmoid(x) is subnormal (x < -87.3); everywhere else the two agree."""
+    c = logits.shape[1]
+    cls = torch.arange(1, c + 1, dtype=targets.dtype).unsqueeze(0)
+    t = targets.unsqueeze(1)
+    x = logits
+    p = torch.sigmoid(x)
+    ge = (x >= 0).float()
+    term1 = (1 - p) ** gamma * (1 - p - p * gamma * torch.log(p.clamp(min=1.17549435e-38)))
+    term2 = p ** gamma * ((-x * ge - torch.log1p(torch.exp(x - 2 * x * ge))) * (1 - p) * gamma - p)
+    return (-(t == cls).float() * term1 * alpha - ((t != cls) & (t >= 0)).float() * term2 * (1 - alpha)) * d_losses
 
 
 def ensemble(mode, cls_logits, act_maps):

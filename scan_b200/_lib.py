@@ -70,6 +70,14 @@ SIGNATURES = {
     "scan_node_cls_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, c_int64, _P]),
     "scan_node_cls_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "scan_class_mean_bwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
+    "scan_rows_linear_fwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "scan_rows_linear_bwd": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "scan_rows_gn_relu_fwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P]),
+    "scan_rows_gn_relu_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "scan_transfer_nodes_num_partials": (c_int32, []),
+    "scan_transfer_nodes_fwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
+    "scan_transfer_nodes_bwd": (c_int32, [_P, _P, c_int32, _P, _P]),
+    "scan_transfer_proto": (c_int32, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "scan_class_sums": (c_int32, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "scan_proto_update": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P]),
     "scan_dbscan_workspace_bytes": (c_int64, [c_int64]),
@@ -88,6 +96,8 @@ LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_rel
             "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
             "scan_qkv_fwd": 1, "scan_qkv_bwd": 9, "scan_attn_out_ln_fwd": 1, "scan_attn_out_ln_bwd": 9, "scan_node_cls_fwd": 3,
             "scan_node_cls_bwd": 9, "scan_class_mean_bwd": 1,
+            "scan_rows_linear_fwd": 1, "scan_rows_linear_bwd": 2, "scan_rows_gn_relu_fwd": 1, "scan_rows_gn_relu_bwd": 2,
+            "scan_transfer_nodes_fwd": 2, "scan_transfer_nodes_bwd": 1, "scan_transfer_proto": 1,
             "scan_sigmoid_focal_fwd": 1, "scan_sigmoid_focal_bwd": 1, "scan_ensemble_levels": 1}
 CALLS = {"n": 0, "launches": 0}
 

@@ -173,6 +173,8 @@ class GRAPHModule(nn.Module):
         # optional key MODEL.MIDDLE_HEAD.DBSCAN_MAX_POINTS only presets the initial size.
         self.dbscan_cap = int(getattr(mh, "DBSCAN_MAX_POINTS", 65536))
         self.dbscan_cap_limit = 700000   # 61 GB of adjacency bits: beyond this the O(n^2) clustering itself is hopeless
+        self.dbscan_streams = True       # one side stream per FPN level for the DBSCAN launch sequences (see _dbscan_levels)
+        self._side_streams = []
         self.record = False              # keep intermediate results of the last call in self.last (parity tests, bench stats)
         channel = mh.PROTO_CHANNEL
         hidden = mh.COND_HIDDEN_CHANNEL
@@ -231,11 +233,15 @@ class GRAPHModule(nn.Module):
             # h = cond_rnn(prototype.permute(2, 0, 1)); kernel = einsum("pkc,ocp->ko", h, cond_nx1.weight[..., 0]) + bias
             return ops.manifest_rnn(self.prototype, self.cond_rnn, self.cond_nx1)
         if self.prototype_iter > 1:
-            w = self.cond_nx1.weight[:, :, :, 0]
-            hcat = torch.einsum("kcp,ocp->ko", self.prototype, w) + self.cond_nx1.bias
-            hcat = F.group_norm(hcat, 32, self.cond_nx1_norm.weight, self.cond_nx1_norm.bias, 1e-5)
-            return self.cond_2(torch.relu(hcat))
-        return self.cond_2(torch.relu(self.cond_1(self.prototype)))
+            # cond_nx1 = Conv2d(256, hid, (P,1)) over [K,256,P,1] == Linear(256 P, hid) on the flattened paradigm rows; GroupNorm32
+            # over each row + ReLU; cond_2 (condgraph.py:322-328): three tiny-batch kernels (csrc/rowsmlp.cu)
+            k = self.prototype.shape[0]
+            hcat = ops.rows_linear(self.prototype.reshape(k, -1), self.cond_nx1.weight, self.cond_nx1.bias)
+            hcat = ops.rows_gn_relu(hcat, self.cond_nx1_norm.weight, self.cond_nx1_norm.bias, 32, self.cond_nx1_norm.eps)
+            return ops.rows_linear(hcat, self.cond_2.weight, self.cond_2.bias)
+        # PROTO_ITER == 1 (condgraph.py:330-334)
+        return ops.rows_linear(ops.rows_linear(self.prototype, self.cond_1.weight, self.cond_1.bias, relu=True),
+                               self.cond_2.weight, self.cond_2.bias)
 
     def _split_kernel(self, kernel_par):
         if self.with_bias_dc:
@@ -358,29 +364,9 @@ class GRAPHModule(nn.Module):
         return out, (node_loss, 0), act_loss, acts
 
     def get_transfer_loss(self, tg_prototype, tg_nodes, tg_labels):
-        """condgraph.py:457-498."""
-        losses = []
-        sr = self.prototype.mean(dim=-1).detach() if self.prototype_iter > 1 else self.prototype.detach()
-        cfgt = self.transfer_cfg
-        if "NODES" in cfgt or "NODE" in cfgt:
-            losses.append(F.kl_div(tg_nodes.softmax(-1).log(), sr[tg_labels].softmax(-1), reduction="mean"))
-        if "PROTOTYPE" in cfgt:
-            idx = tg_prototype.sum(-1).bool()
-            losses.append(F.kl_div(tg_prototype[idx].softmax(-1).log(), sr[idx].softmax(-1), reduction="mean"))
-        if "ADJ" in cfgt:
-            idx = tg_prototype.sum(dim=-1).bool()
-            a = sim_matrix(sr[idx], sr[idx]).view(1, -1)
-            b = sim_matrix(tg_prototype[idx], tg_prototype[idx]).view(1, -1)
-            losses.append(F.cosine_embedding_loss(a, b, a.new_ones(1), margin=0.0))
-        if "ADJ_COMPLETE" in cfgt:
-            idx = ~(tg_prototype.sum(dim=-1).bool())
-            comp = torch.where(idx[:, None], sr, tg_prototype)
-            a = sim_matrix(sr, sr).view(1, -1)
-            b = sim_matrix(comp, comp).view(1, -1)
-            losses.append(F.cosine_embedding_loss(a, b, a.new_ones(1), margin=0.0))
-        if losses:
-            return sum(losses)
-        return None
+        """condgraph.py:457-498: NODES / PROTOTYPE KL and ADJ / ADJ_COMPLETE cosine losses in the
+        scan_transfer_* kernels; the class-presence mask stays on the device (the reference's boolean indexing synchronises)."""
+        return ops.transfer_loss(self.transfer_cfg, tg_nodes, tg_labels, tg_prototype, self.prototype.detach())
 
     def _sample_target(self, geo, rows, acts):
         dev = rows.device
@@ -421,16 +407,38 @@ class GRAPHModule(nn.Module):
         return smp
 
     def _dbscan_levels(self, geo, rows, acts, pos_mask, plabel):
-        """scan_dbscan_level per FPN level into the shared pos_mask / plabel vectors; returns the per-level info records."""
+        """scan_dbscan_level per FPN level into the shared pos_mask / plabel vectors; returns the per-level info records.
+        The levels are independent (loss.py:464-518 loops over them), so each one is enqueued on its own side stream: the
+        ~20 small launches of the coarse levels (n = 100 .. 3 000 points: pure launch latency) overlap the P3 level's
+        tensor-core distance kernel instead of queueing behind it.  Fork / join with events; no host synchronisation."""
         k = self.used_num_classes
         caps = [min(geo.n_images * (k - 1) * h * w, self.dbscan_cap) for h, w in geo.shapes]
-        ws = ops.dbscan_workspace(max(caps), rows.device)
-        infos = []
-        for l in range(len(geo.shapes)):
+        n_levels = len(geo.shapes)
+        dev = rows.device
+        rows_d = rows.detach()
+        main = torch.cuda.current_stream(dev)
+        if self.dbscan_streams and n_levels > 1:
+            if len(self._side_streams) < n_levels - 1:
+                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_levels - 1)]
+            fork = torch.cuda.Event()
+            fork.record(main)
+        infos = [None] * n_levels
+        joins = []
+        for l in range(n_levels):
             a, b = geo.row_off[l], geo.row_off[l + 1]
-            _, info = ops.dbscan_level(rows.detach()[a:b], acts[l].detach(), self.dbscan_thr, self.dbscan_eps, caps[l],
-                                       pos_mask[a:b], plabel[a:b], ws)
-            infos.append(info)
+            side = self._side_streams[l - 1] if (self.dbscan_streams and l > 0) else None
+            if side is not None:
+                side.wait_event(fork)
+            with torch.cuda.stream(side if side is not None else main):
+                ws = ops.dbscan_workspace(caps[l], dev)      # allocated on (and recycled by) the stream that uses it
+                _, infos[l] = ops.dbscan_level(rows_d[a:b], acts[l].detach(), self.dbscan_thr, self.dbscan_eps, caps[l],
+                                               pos_mask[a:b], plabel[a:b], ws)
+                if side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
         return infos
 
     def _forward_train_target(self, images, features, targets=None, return_maps=False):

@@ -14,6 +14,8 @@
 // transposed V^T planes [chunk][hi d 0..63 | lo d 0..63][Mp] (keys contiguous), all loaded by TMA (128-byte swizzle).
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..19 softmax (lane quarter = w % 4, 16-key block = w / 4):
 // four softmax warps per scheduler hide the TMEM / MUFU / ALU latencies (one or two per scheduler run at IPC ~0.1).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -157,7 +159,9 @@ template <bool DROP>
 __global__ void __launch_bounds__(T5_THREADS, 1)
     attn_fwd_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, int m, float scale, float drop_p, uint64_t seed,
-                       float* __restrict__ ctx, float* __restrict__ lse) {
+                       float* __restrict__ ctx, float* __restrict__ lse, const int* __restrict__ run_flag) {
+  // fallback of the single-pass kernel below: runs only when that kernel flagged a row whose probabilities underflowed
+  if (run_flag && *run_flag == 0) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* q_s = smem;
@@ -465,11 +469,297 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------- forward, single pass (product)
+// The two-pass kernel above computes every score tile twice and its 16 elementwise warps execute ~35 instructions per score
+// (ncu, round 1: 47 % issue-slot utilisation next to a 48 % busy tensor pipe -- instruction issue, not the MMAs, bounds it).
+// This kernel visits every key tile ONCE:
+//   * softmax reference = an upper bound instead of the row maximum: s_ij <= |q_i| max_j |k_j| (Cauchy-Schwarz; the norms come
+//     from attn_norm_kernel), so p = 2^(s - bound) <= 1 never overflows and no statistics pass is needed; O accumulates the
+//     UN-normalised P~ V, the row sums l accumulate in registers, attn_finish_kernel divides and writes the log-sum-exp.
+//     A bound far above the true maximum only costs exponent range (fp32 and tf32 share the 8-bit exponent, the hi/lo split
+//     is relative); if a row sum drops below 2^-100 attn_finish_kernel raises a flag and the two-pass kernel re-runs.
+//   * the three 3xTF32 score products go into ONE 64-column accumulator (three N = 64 MMAs instead of the wide-N pair): the
+//     elementwise warps load 16 instead of 48 TMEM values per tile and skip two adds per score, and S shrinks from 192 to 64
+//     columns, which buys a THREE-deep S ring (the tensor pipe runs two tiles ahead of the softmax);
+//   * P.V keeps the wide-N form (its accumulator is only read at the drains).
+// TMEM: S ring [0,192) = 3 x 64   P operand slot [192,320) hi | lo   O [320,512) = Oa 128 + Ob 64.
+constexpr int T1_SBUF = 3;
+
+// |q_g| per sub-token row and max_j |k_j| per chunk (bits of a non-negative float order like unsigned integers)
+__global__ void __launch_bounds__(256) attn_norm_kernel(const float* __restrict__ q, const float* __restrict__ k, int m, float* __restrict__ qn,
+                                                        unsigned int* __restrict__ kmax_bits) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 4ll * m) return;
+  const float4* q4 = reinterpret_cast<const float4*>(q + r * 64);
+  const float4* k4 = reinterpret_cast<const float4*>(k + r * 64);
+  float sq = 0.f, sk = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 a = __ldg(q4 + i), b = __ldg(k4 + i);
+    sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    sk += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+  }
+  qn[r] = sqrtf(sq);
+  atomicMax(kmax_bits + (int)(r / m), __float_as_uint(sqrtf(sk)));
+}
+
+// ctx[g, :] /= l[g];  lse[g] = ln 2 * (bound2[g] + log2 l[g]);  flag |= (l[g] underflowed)
+__global__ void __launch_bounds__(256) attn_finish_kernel(float* __restrict__ ctx, const float* __restrict__ lsum, const float* __restrict__ qn,
+                                                          const unsigned int* __restrict__ kmax_bits, int m, float sl2,
+                                                          float* __restrict__ lse, int* __restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long g = i >> 4;
+  if (g >= 4ll * m) return;
+  const float l = __ldg(lsum + g);
+  const float inv = 1.f / l;
+  float4* c4 = reinterpret_cast<float4*>(ctx + g * 64) + (i & 15);
+  float4 v = *c4;
+  v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+  *c4 = v;
+  if ((i & 15) == 0) {
+    const float b2 = sl2 * __ldg(qn + g) * __uint_as_float(__ldg(kmax_bits + (int)(g / m))) * 1.000002f;
+    lse[g] = (b2 + log2f(l)) * 0.6931471805599453f;
+    if (!(l >= 7.9e-31f) || !(l <= 3.0e38f)) atomicOr(flag, 1);   // 2^-100; also catches NaN / inf
+  }
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(T5_THREADS, 1)
+    attn_fwd1_t5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                        const __grid_constant__ CUtensorMap map_v, int m, float scale, float drop_p, uint64_t seed,
+                        const float* __restrict__ qn, const unsigned int* __restrict__ kmax_bits, float* __restrict__ ctx,
+                        float* __restrict__ lsum) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + T5_Q_BYTES;
+  uint8_t* v_s = k_s + 2 * T5_STAGE;
+  uint64_t* bars = (uint64_t*)(v_s + 2 * T5_STAGE);
+  uint64_t* k_full = bars;          // [2]
+  uint64_t* k_empty = bars + 2;     // [2]
+  uint64_t* v_full = bars + 4;      // [2]
+  uint64_t* v_empty = bars + 6;     // [2]
+  uint64_t* s_full = bars + 8;      // [3]
+  uint64_t* s_empty = bars + 11;    // [3] (512 arrivals)
+  uint64_t* p_full = bars + 14;     // (512 arrivals)
+  uint64_t* p_empty = bars + 15;
+  uint64_t* o_full = bars + 16;
+  uint64_t* q_full = bars + 17;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+  float* stat_l = (float*)(bars + 20);      // [4][128] per-column-block row sums
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int chunk = blockIdx.y;
+  const long long base = (long long)chunk * m;
+  const int i0 = blockIdx.x * T5_BQ;
+  const int n_tiles = (m + T5_BK - 1) / T5_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(k_full + i), 1);
+      mbar_init(smem_u32(k_empty + i), 1);
+      mbar_init(smem_u32(v_full + i), 1);
+      mbar_init(smem_u32(v_empty + i), 1);
+    }
+    for (int i = 0; i < T1_SBUF; ++i) {
+      mbar_init(smem_u32(s_full + i), 1);
+      mbar_init(smem_u32(s_empty + i), 32 * T5_SM_WARPS);
+    }
+    mbar_init(smem_u32(p_full), 32 * T5_SM_WARPS);
+    mbar_init(smem_u32(p_empty), 1);
+    mbar_init(smem_u32(o_full), 1);
+    mbar_init(smem_u32(q_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: Q once, then the K ring =====
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(q_full), T5_Q_BYTES);
+      for (int part = 0; part < 2; ++part)      // hi, lo
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(smem_u32(q_s + (part * 2 + kb) * T5_QBOX), &map_q, smem_u32(q_full), part * 64 + kb * 32, (int)(base + i0));
+      int ks = 0;
+      uint32_t kph = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * T5_BK;
+        mbar_wait(smem_u32(k_empty + ks), kph ^ 1);
+        mbar_expect_tx(smem_u32(k_full + ks), T5_STAGE);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part)
+            tma_load_2d(smem_u32(k_s + ks * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_k, smem_u32(k_full + ks), part * 64 + kb * 32,
+                        (int)(base + j0));
+        if (++ks == 2) { ks = 0; kph ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== second TMA producer: the V^T ring =====
+    if (lane == 0) {
+      int vs = 0;
+      uint32_t vph = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = t * T5_BK;
+        mbar_wait(smem_u32(v_empty + vs), vph ^ 1);
+        mbar_expect_tx(smem_u32(v_full + vs), T5_STAGE);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < 2; ++part)
+            tma_load_2d(smem_u32(v_s + vs * T5_STAGE + (kb * 2 + part) * T5_KBOX), &map_v, smem_u32(v_full + vs), j0 + kb * 32,
+                        chunk * 128 + part * 64);
+        if (++vs == 2) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (converged warp, elected lane per instruction) =====
+    mbar_wait(smem_u32(q_full), 0);
+    tcgen05_fence_after();
+    const uint32_t q_addr = smem_u32(q_s);
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0, pf = 0;
+    // S(t) -> ring slot t % 3: Q_hi.K_hi + Q_hi.K_lo + Q_lo.K_hi, three N = 64 MMAs per k-step into the same 64 columns
+    auto issue_s = [&](int t) {
+      const int buf = t % T1_SBUF;
+      mbar_wait(smem_u32(s_empty + buf), (uint32_t)(((t / T1_SBUF) & 1) ^ 1));
+      mbar_wait(smem_u32(k_full + ks), kph);
+      tcgen05_fence_after();
+      const uint32_t kaddr = smem_u32(k_s + ks * T5_STAGE);
+      const uint32_t d = tmem_base + buf * 64;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t bh = umma_desc_sw128(kaddr + kb * 2 * T5_KBOX + k * 32);
+          const uint64_t bl = umma_desc_sw128(kaddr + (kb * 2 + 1) * T5_KBOX + k * 32);
+          const uint64_t ah = umma_desc_sw128(q_addr + kb * T5_QBOX + k * 32);
+          const uint64_t al = umma_desc_sw128(q_addr + (2 + kb) * T5_QBOX + k * 32);
+          t5_mma_ss(d, ah, bh, T5_IDESC_N64, (kb | k) != 0);
+          t5_mma_ss(d, ah, bl, T5_IDESC_N64, 1);
+          t5_mma_ss(d, al, bh, T5_IDESC_N64, 1);
+        }
+      t5_commit(smem_u32(k_empty + ks));
+      t5_commit(smem_u32(s_full + buf));
+      if (++ks == 2) { ks = 0; kph ^= 1; }
+    };
+    issue_s(0);
+    if (n_tiles > 1) issue_s(1);
+    for (int t = 0; t < n_tiles; ++t) {
+      if (t + 2 < n_tiles) issue_s(t + 2);
+      // O += P(t) . V(t)
+      mbar_wait(smem_u32(p_full), pf);
+      pf ^= 1;
+      mbar_wait(smem_u32(v_full + vs), vph);
+      tcgen05_fence_after();
+      const uint32_t vaddr = smem_u32(v_s + vs * T5_STAGE);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t b = umma_desc_sw128(vaddr + kb * 2 * T5_KBOX + k * 32);
+          const uint32_t acc = ((t % T5_FLUSH) | kb | k) != 0;   // restart after every drain
+          t5_mma_ts(tmem_base + T5_O_COL0, tmem_base + T5_P_COL0 + kb * 32 + k * 8, b, T5_IDESC_N128, acc);
+          t5_mma_ts(tmem_base + T5_O_COL0 + 128, tmem_base + T5_P_COL0 + 64 + kb * 32 + k * 8, b, T5_IDESC_N64, acc);
+        }
+      t5_commit(smem_u32(v_empty + vs));
+      t5_commit(smem_u32(p_empty));
+      if (++vs == 2) { vs = 0; vph ^= 1; }
+    }
+    t5_commit(smem_u32(o_full));
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===== softmax / epilogue warps: thread = query row (TMEM lane), 16-column block cq of the 64 key columns =====
+    const int w = warp - 4;
+    const int qd = w & 3, cq = w >> 2;
+    const int row = qd * 32 + lane;
+    const int grow = i0 + row;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const float sl2 = scale * 1.4426950408889634f;
+    // bound of the row's scores in the log2 domain (the SAME expression attn_finish_kernel uses for the log-sum-exp)
+    const float b2 = grow < m ? sl2 * __ldg(qn + base + grow) * __uint_as_float(__ldg(kmax_bits + chunk)) * 1.000002f : 0.f;
+    const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t drop_thr = DROP ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const uint32_t hrow = attn_drop_pre(seed, chunk) ^ ((uint32_t)grow * ATTN_DROP_CI);
+    float lrun = 0.f;
+    uint32_t pe = 0;
+    float s[16];
+    auto drain_o = [&](bool first) {
+      tmem_drain16<3>(tmem_base + lane_base + T5_O_COL0 + cq * 16, ctx + (base + grow) * T5_D + cq * 16, 1.f, first, grow < m);
+    };
+    auto prob_tile = [&](int t, auto last_c) {
+      constexpr bool LAST = decltype(last_c)::value;
+      const bool drain = t > 0 && t % T5_FLUSH == 0;
+      if (drain) {   // tiles [t - T5_FLUSH, t) are complete in O once the P.V MMAs of tile t-1 have retired
+        mbar_wait(smem_u32(p_empty), pe);
+        pe ^= 1;
+        tcgen05_fence_after();
+        drain_o(t == T5_FLUSH);
+        tcgen05_fence_before();
+      }
+      const int buf = t % T1_SBUF;
+      mbar_wait(smem_u32(s_full + buf), (uint32_t)((t / T1_SBUF) & 1));
+      tcgen05_fence_after();
+      t5_ld16(tmem_base + lane_base + buf * 64 + cq * 16, s);
+      t5_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(s_empty + buf));
+      const int j0 = t * T5_BK + cq * 16;
+      const int lim = m - j0;
+      [[maybe_unused]] const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float p = t5_ex2(fmaf(s[e], sl2, -b2));
+        if (LAST) p = e < lim ? p : 0.f;
+        lrun += p;                                   // the normaliser sums the UN-dropped probabilities
+        if constexpr (DROP) p = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? p * inv_keep : 0.f;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(p));
+        hi[e] = u;
+        lo[e] = __float_as_uint(p - __uint_as_float(u));
+      }
+      if (t > 0 && !drain) {   // the previous P must have been consumed by its P.V MMAs
+        mbar_wait(smem_u32(p_empty), pe);
+        pe ^= 1;
+      }
+      tcgen05_fence_after();
+      t5_st16(tmem_base + lane_base + T5_P_COL0 + cq * 16, hi);
+      t5_st16(tmem_base + lane_base + T5_P_COL0 + 64 + cq * 16, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(p_full));
+    };
+    for (int t = 0; t + 1 < n_tiles; ++t) prob_tile(t, std::false_type{});
+    prob_tile(n_tiles - 1, std::true_type{});
+    // row sums: combine the four column blocks
+    stat_l[cq * 128 + row] = lrun;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * T5_SM_WARPS) : "memory");
+    if (cq == 0 && grow < m) lsum[base + grow] = (stat_l[row] + stat_l[128 + row]) + (stat_l[256 + row] + stat_l[384 + row]);
+    // epilogue: the tiles since the last drain
+    mbar_wait(smem_u32(o_full), 0);
+    tcgen05_fence_after();
+    drain_o(n_tiles <= T5_FLUSH);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 static unsigned long long g_t5_attr = 0;
 
 int64_t attn_t5_workspace_bytes(int m) {
   const long long mp = ((long long)m + 63) / 64 * 64;
-  return (4ll * m * 128 * 2 + 4ll * 128 * mp) * 4 + 1024;
+  // q_hl, k_hl [4M,128] | V^T planes [4][128][Mp] | qn [4M] | lsum [4M] | kmax[4] + flag
+  return (4ll * m * 128 * 2 + 4ll * 128 * mp + 8ll * m + 64) * 4 + 1024;
 }
 
 int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, float scale, float drop_p, uint64_t seed, float* ctx,
@@ -478,8 +768,16 @@ int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, fl
   float* q_hl = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   float* k_hl = q_hl + 4ll * m * 128;
   float* vt = k_hl + 4ll * m * 128;
+  float* qn = vt + 4ll * 128 * mp;
+  float* lsum = qn + 4ll * m;
+  unsigned int* kmax_bits = (unsigned int*)(lsum + 4ll * m);   // [4] + flag at [8]
+  int* flag = (int*)(kmax_bits + 8);
+  static const int two_pass = getenv("SCAN_B200_ATTN_2PASS") ? atoi(getenv("SCAN_B200_ATTN_2PASS")) : 0;   // tests: force the fallback kernel
+  SCAN_CUDA_CHECK(cudaMemsetAsync(kmax_bits, 0, 16 * sizeof(int), st));
   attn_prep_kernel<<<2 * sm_count(), 256, 0, st>>>(q, k, v, m, mp, q_hl, k_hl, vt);
   SCAN_LAUNCH_CHECK("attn_prep_kernel");
+  attn_norm_kernel<<<(unsigned)ceil_div(4ll * m, 256), 256, 0, st>>>(q, k, m, qn, kmax_bits);
+  SCAN_LAUNCH_CHECK("attn_norm_kernel");
   CUtensorMap mq, mk, mv;
   int rc = make_rowmajor_map(&mq, q_hl, 4ull * m, 128, T5_BQ);
   if (rc) return rc;
@@ -490,12 +788,25 @@ int launch_attn_fwd_t5(const float* q, const float* k, const float* v, int m, fl
   if (first_use_on_device(&g_t5_attr)) {
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
     SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd1_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd1_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
   }
   dim3 grid((m + T5_BQ - 1) / T5_BQ, 4);
+  if (!two_pass) {
+    if (drop_p > 0.f)
+      attn_fwd1_t5_kernel<true><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, qn, kmax_bits, ctx, lsum);
+    else
+      attn_fwd1_t5_kernel<false><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, qn, kmax_bits, ctx, lsum);
+    SCAN_LAUNCH_CHECK("attn_fwd1_t5_kernel");
+    attn_finish_kernel<<<(unsigned)ceil_div(4ll * m * 16, 256), 256, 0, st>>>(ctx, lsum, qn, kmax_bits, m, scale * 1.4426950408889634f, lse, flag);
+    SCAN_LAUNCH_CHECK("attn_finish_kernel");
+  }
+  // two-pass kernel: exits at once unless the single-pass kernel flagged an underflowed row (or the test hook forces it)
+  const int* run_flag = two_pass ? nullptr : flag;
   if (drop_p > 0.f)
-    attn_fwd_t5_kernel<true><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse);
+    attn_fwd_t5_kernel<true><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse, run_flag);
   else
-    attn_fwd_t5_kernel<false><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse);
+    attn_fwd_t5_kernel<false><<<grid, T5_THREADS, T5_SMEM, st>>>(mq, mk, mv, m, scale, drop_p, seed, ctx, lse, run_flag);
   SCAN_LAUNCH_CHECK("attn_fwd_t5_kernel");
   return SCAN_OK;
 }

@@ -483,6 +483,72 @@ def manifest_rnn(proto, rnn, conv):
 
 
 # ----------------------------------------------------------------------------------------------------
+# K4a': manifestation without the RNN (tiny-batch dense layers over the K paradigm rows, csrc/rowsmlp.cu)
+# ----------------------------------------------------------------------------------------------------
+class _RowsLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x, w = x.contiguous(), w.contiguous()
+        b = None if b is None else b.contiguous()
+        k, i = x.shape
+        o = w.shape[0]
+        y = torch.empty((k, o), device=x.device, dtype=torch.float32)
+        call("scan_rows_linear_fwd", _ptr(x), _ptr(w), _ptr(b), k, i, o, int(relu), _ptr(y), _stream())
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (int(relu), b is not None, x.requires_grad)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        relu, has_b, need_dx = ctx.cfg
+        dy = dy.contiguous()
+        k, i = x.shape
+        o = w.shape[0]
+        d_w = torch.empty_like(w)
+        d_b = torch.empty((o,), device=x.device, dtype=torch.float32) if has_b else None
+        d_x = torch.empty_like(x) if need_dx else None
+        call("scan_rows_linear_bwd", _ptr(x), _ptr(w), _ptr(dy), _ptr(y), k, i, o, relu, _ptr(d_w), _ptr(d_b), _ptr(d_x), _stream())
+        return d_x, d_w, d_b, None
+
+
+def rows_linear(x, weight, bias, relu=False):
+    """act(x @ weight.T + bias) for a tiny batch x [K<=16, I] (weight may be a conv weight [O, I', P, 1] flattened to [O, I' P])."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.shape[0] > _lib.SCAN_MAX_CLASSES:
+        raise RuntimeError("rows_linear expects a CUDA fp32 [K<=16, I] input (no CPU fallback)")
+    return _RowsLinear.apply(x, weight.reshape(weight.shape[0], -1), bias, relu)
+
+
+class _RowsGnRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps):
+        x, gamma, beta = x.contiguous(), gamma.contiguous(), beta.contiguous()
+        k, c = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty((k, groups, 2), device=x.device, dtype=torch.float32)
+        call("scan_rows_gn_relu_fwd", _ptr(x), _ptr(gamma), _ptr(beta), k, c, groups, eps, _ptr(y), _ptr(stats), _stream())
+        ctx.save_for_backward(x, y, gamma, stats)
+        ctx.groups = groups
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, y, gamma, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        k, c = x.shape
+        d_x, d_g, d_b = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+        call("scan_rows_gn_relu_bwd", _ptr(x), _ptr(y), _ptr(dy), _ptr(gamma), _ptr(stats), k, c, ctx.groups, _ptr(d_x), _ptr(d_g), _ptr(d_b),
+             _stream())
+        return d_x, d_g, d_b, None, None
+
+
+def rows_gn_relu(x, gamma, beta, groups, eps):
+    return _RowsGnRelu.apply(x, gamma, beta, int(groups), float(eps))
+
+
+# ----------------------------------------------------------------------------------------------------
 # K3a: attention
 # ----------------------------------------------------------------------------------------------------
 # implementations: "t5" = tcgen05 kernels (product), "ffma" = fp32 verification kernels (SCAN_B200_ATTN_FWD/BWD=ffma)
@@ -678,6 +744,67 @@ class _ClassMeans(torch.autograd.Function):
 def class_means(nodes, labels, num_classes, label_shift):
     """Returns (means [K,C] with gradient, packed [K,C+1] sum|count buffer)."""
     return _ClassMeans.apply(nodes, labels, int(num_classes), int(label_shift))
+
+
+# ----------------------------------------------------------------------------------------------------
+# a14: transfer losses
+# ----------------------------------------------------------------------------------------------------
+TRANSFER_FLAGS = {"PROTOTYPE": 1, "ADJ": 2, "ADJ_COMPLETE": 4}
+
+
+class _TransferLoss(torch.autograd.Function):
+    """get_transfer_loss (condgraph.py:457-498): sum of the enabled NODES / PROTOTYPE / ADJ / ADJ_COMPLETE losses as one
+    autograd node (three launches forward); gradients flow to the target nodes and to the target class means."""
+
+    @staticmethod
+    def forward(ctx, nodes, labels, tg_proto, prototype, with_nodes, proto_flags):
+        dev = prototype.device
+        k, c = prototype.shape[0], prototype.shape[1]
+        p_iter = prototype.shape[2] if prototype.dim() == 3 else 1
+        prototype = prototype.contiguous()
+        loss_n = diff = None
+        if with_nodes:
+            nodes = nodes.contiguous()
+            m = nodes.shape[0]
+            diff = torch.empty_like(nodes)
+            partials = torch.empty((_lib.lib().scan_transfer_nodes_num_partials(),), device=dev, dtype=torch.float64)
+            loss_n = torch.empty((), device=dev, dtype=torch.float32)
+            call("scan_transfer_nodes_fwd", _ptr(nodes), _ptr(labels), _ptr(prototype), p_iter, m, k, _ptr(diff), _ptr(partials),
+                 _ptr(loss_n), _stream())
+        d_tg = None
+        out = loss_n
+        if proto_flags:
+            tg = tg_proto.contiguous()
+            losses = torch.empty((4,), device=dev, dtype=torch.float32)
+            d_tg = torch.empty((k, c), device=dev, dtype=torch.float32)
+            call("scan_transfer_proto", _ptr(tg), _ptr(prototype), p_iter, k, proto_flags, _ptr(loss_n), _ptr(losses), _ptr(d_tg), _stream())
+            out = losses[3]
+        ctx.save_for_backward(diff, d_tg)
+        ctx.m = nodes.shape[0] if with_nodes else 0
+        return out.clone() if proto_flags else out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_loss):
+        diff, d_tg = ctx.saved_tensors
+        d_loss = d_loss.to(torch.float32).reshape(1).contiguous()
+        d_nodes = None
+        if diff is not None:
+            d_nodes = torch.empty_like(diff)
+            call("scan_transfer_nodes_bwd", _ptr(diff), _ptr(d_loss), ctx.m, _ptr(d_nodes), _stream())
+        d_tgp = d_tg * d_loss if d_tg is not None else None
+        return d_nodes, None, d_tgp, None, None, None
+
+
+def transfer_loss(cfg_names, nodes, labels, tg_proto, prototype):
+    """cfg_names: MODEL.MIDDLE_HEAD.TRANSFER_CFG.  Returns the summed loss tensor or None when no term is enabled."""
+    with_nodes = ("NODES" in cfg_names) or ("NODE" in cfg_names)
+    flags = sum(v for n, v in TRANSFER_FLAGS.items() if n in cfg_names)
+    if not with_nodes and not flags:
+        return None
+    if prototype.shape[1] != C or prototype.shape[0] > _lib.SCAN_MAX_CLASSES or not prototype.is_cuda:
+        raise RuntimeError("transfer_loss expects a CUDA [K<=16, 256(, P)] prototype buffer (no CPU fallback)")
+    return _TransferLoss.apply(nodes, labels, tg_proto, prototype, with_nodes, flags)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -449,15 +449,19 @@ def test_sigmoid_focal_rows_kernels(r, c):
     logits = torch.randn(r, c, generator=g) * 3
     logits[0, 0], logits[1, 0] = 95.0, -95.0           # p saturates / underflows: the reference's log(max(p, FLT_MIN)) clamp
     targets = torch.randint(-1, c + 2, (r,), generator=g).int()
-    lr = logits.clone().requires_grad_(True)
-    want = orc.sigmoid_focal_loss_elementwise(lr, targets, 2.0, 0.25)
+    want = orc.sigmoid_focal_loss_elementwise(logits, targets, 2.0, 0.25)
     cot = torch.randn(r, c, generator=g)
-    (want * cot).sum().backward()
+    # the reference's backward is its own analytic kernel (SigmoidFocalLoss_cuda.cu:61-101), not autograd of the forward
+    want_grad = orc.sigmoid_focal_loss_backward_elementwise(logits, targets, cot, 2.0, 0.25)
     ld = logits.to(DEV).requires_grad_(True)
     got = ops.sigmoid_focal_loss(ld, targets.to(DEV), 2.0, 0.25)
     (got * cot.to(DEV)).sum().backward()
     _close(got, want, 1e-5, "sigmoid focal fwd")
-    _close(ld.grad, lr.grad, 1e-5, "sigmoid focal bwd")
+    _close(ld.grad, want_grad, 1e-5, "sigmoid focal bwd")
+    # away from the clamp the analytic backward equals autograd of the forward formula
+    lr = logits[2:].clone().requires_grad_(True)
+    (orc.sigmoid_focal_loss_elementwise(lr, targets[2:], 2.0, 0.25) * cot[2:]).sum().backward()
+    _close(ld.grad[2:], lr.grad, 1e-5, "sigmoid focal bwd vs autograd")
     # a non-default gamma takes the powf branch
     want15 = orc.sigmoid_focal_loss_elementwise(logits[:512], targets[:512], 1.5, 0.4)
     got15 = ops.sigmoid_focal_loss(logits[:512].to(DEV), targets[:512].to(DEV), 1.5, 0.4)
@@ -583,3 +587,103 @@ def test_class_means_forward_and_backward():
     _close(means, want, 1e-5, "class means")
     _close(nd.grad, nr.grad, 1e-6, "d_nodes")
     assert float(packed[5, 256]) == 0.0
+
+
+def test_attention_single_pass_underflow_falls_back_to_two_pass():
+    """The single-pass forward references every row to the Cauchy-Schwarz bound |q| max|k|; with huge, nearly orthogonal q and k the
+    bound sits > 2^100 above the true scores, every probability underflows, attn_finish_kernel raises its flag and the two-pass
+    kernel must take over (same stream, no host round trip)."""
+    torch.manual_seed(3)
+    m = 300
+    q = torch.randn(m, 256) * 0.05
+    k = torch.randn(m, 256) * 0.05
+    q.view(4 * m, 64)[:, 0] += 60.0          # every 64-d sub-token: q along e0, k along e1 -> q.k ~ 0, |q||k| = 3600
+    k.view(4 * m, 64)[:, 1] += 60.0
+    v = torch.randn(m, 256)
+    qr, kr, vr = [t.double().requires_grad_(True) for t in (q, k, v)]
+    att = torch.softmax(torch.bmm(qr.reshape(4, m, 64), kr.reshape(4, m, 64).transpose(1, 2)) * 0.25, dim=2)
+    want = torch.bmm(att, vr.reshape(4, m, 64)).reshape(m, 256)
+    cot = torch.randn(m, 256)
+    (want * cot.double()).sum().backward()
+    qd, kd, vd = [t.to(DEV).requires_grad_(True) for t in (q, k, v)]
+    got = ops.chunked_attention(qd, kd, vd, 0.25)
+    (got * cot.to(DEV)).sum().backward()
+    assert torch.isfinite(got).all()
+    _close(got, want, 5e-5, "ctx (fallback)")
+    _close(vd.grad, vr.grad, 5e-5, "dv (fallback)")
+    _close(qd.grad, qr.grad, 2e-4, "dq (fallback)", atol=1e-4)
+
+
+@pytest.mark.parametrize("cfg_names,p_iter,absent", [(("NODES", "ADJ"), 3, ()), (("NODES", "ADJ", "PROTOTYPE"), 3, (2, 5)),
+                                                     (("ADJ_COMPLETE",), 1, (0, 7)), (("NODE", "PROTOTYPE", "ADJ", "ADJ_COMPLETE"), 3, (4,)),
+                                                     (("PROTOTYPE",), 1, ())])
+def test_transfer_losses_match_reference_formulas(cfg_names, p_iter, absent):
+    """a14: scan_transfer_* vs the oracle's restatement of get_transfer_loss (condgraph.py:457-498), loss and both gradients."""
+    import types
+    torch.manual_seed(len(cfg_names) * 7 + p_iter)
+    k, m = 9, 700
+    proto = torch.randn(k, 256, p_iter) if p_iter > 1 else torch.randn(k, 256)
+    nodes = torch.randn(m, 256)
+    labels = torch.randint(0, k, (m,))
+    tg = torch.randn(k, 256) * 0.7
+    for c in absent:
+        tg[c] = 0.0                  # class absent from the target batch: zero mean row (condgraph.py:395-398)
+    fake = types.SimpleNamespace(mh=types.SimpleNamespace(TRANSFER_CFG=cfg_names), prototype=proto, P=p_iter)
+    nr, tr = nodes.clone().requires_grad_(True), tg.clone().requires_grad_(True)
+    want = orc.OracleCondGraph.transfer_loss(fake, tr * 1.0, nr, labels)      # (tr * 1.0: ADJ_COMPLETE writes in place)
+    (want * 1.3).backward()
+    nd, td = nodes.to(DEV).requires_grad_(True), tg.to(DEV).requires_grad_(True)
+    got = ops.transfer_loss(cfg_names, nd, labels.to(DEV), td, proto.to(DEV))
+    (got * 1.3).backward()
+    _close(got, want, 2e-5, "transfer loss")
+    if "NODES" in cfg_names or "NODE" in cfg_names:
+        _close(nd.grad, nr.grad, 2e-5, "d_nodes", atol=1e-9)
+    else:
+        assert nd.grad is None
+    if any(n in cfg_names for n in ("PROTOTYPE", "ADJ", "ADJ_COMPLETE")):
+        _close(td.grad, tr.grad, 5e-5, "d_tg_proto", atol=1e-8)
+
+
+@pytest.mark.parametrize("k,i,o,relu,bias", [(9, 256, 512, True, True), (9, 768, 512, False, True), (2, 512, 257, False, True),
+                                             (16, 512, 256, False, False), (1, 256, 512, True, True)])
+def test_rows_linear_matches_torch(k, i, o, relu, bias):
+    """a9 (no-RNN manifestation): tiny-batch dense layer, forward + d_w / d_b / d_x."""
+    torch.manual_seed(k * 1000 + o)
+    lin = torch.nn.Linear(i, o, bias=bias)
+    x = torch.randn(k, i)
+    cot = torch.randn(k, o)
+    xr = x.clone().requires_grad_(True)
+    yr = lin(xr)
+    yr = torch.relu(yr) if relu else yr
+    (yr * cot).sum().backward()
+    lind = torch.nn.Linear(i, o, bias=bias).to(DEV)
+    lind.load_state_dict(lin.state_dict())
+    xd = x.to(DEV).requires_grad_(True)
+    yd = ops.rows_linear(xd, lind.weight, lind.bias if bias else None, relu)
+    (yd * cot.to(DEV)).sum().backward()
+    _close(yd, yr, 1e-5, "y")
+    _close(xd.grad, xr.grad, 1e-5, "d_x")
+    _close(lind.weight.grad, lin.weight.grad, 1e-5, "d_w")
+    if bias:
+        _close(lind.bias.grad, lin.bias.grad, 1e-5, "d_b")
+    # the first layer of the manifestation takes the paradigm BUFFER: no d_x requested
+    y2 = ops.rows_linear(x.to(DEV), lind.weight, lind.bias if bias else None, relu)
+    assert torch.equal(y2, yd.detach())
+
+
+@pytest.mark.parametrize("k,c", [(9, 512), (2, 512), (16, 256)])
+def test_rows_gn_relu_matches_torch(k, c):
+    torch.manual_seed(k + c)
+    x = torch.randn(k, c) * 2 + 0.3
+    gamma, beta = torch.randn(c), torch.randn(c) * 0.2
+    cot = torch.randn(k, c)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.relu(torch.nn.functional.group_norm(xr, 32, gr, br, 1e-5))
+    (yr * cot).sum().backward()
+    xd, gd, bd = [t.to(DEV).requires_grad_(True) for t in (x, gamma, beta)]
+    yd = ops.rows_gn_relu(xd, gd, bd, 32, 1e-5)
+    (yd * cot.to(DEV)).sum().backward()
+    _close(yd, yr, 2e-5, "y")
+    _close(xd.grad, xr.grad, 5e-5, "d_x")
+    _close(gd.grad, gr.grad, 5e-5, "d_gamma")
+    _close(bd.grad, br.grad, 5e-5, "d_beta")
