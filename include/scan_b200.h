@@ -260,6 +260,28 @@ int scan_proto_update(const float* packed_sums, int32_t num_classes, int32_t cha
                       int32_t slot, int32_t shift, int32_t cosine_on, float momentum, float* prototype,
                       float* proto_batch_out, void* stream);
 
+/* ---- a6: building blocks of the per-class GCN (GLOBAL_GCN = False; condgraph.py:262-302, 404-414) -------------------
+ * All on the tcgen05 3xTF32 GEMM of csrc/gemm.cu; pitches in floats, multiples of 4; pointers 16-byte aligned.
+ * scan_gemm_nt: c [m,n] (+)= act(a [m,k] . b [n,k]^T + bias[n]); k > 512 is split and reduced in a fixed order
+ *   (workspace of scan_gemm_nt_workspace_bytes(m, n, k) bytes, may be NULL when k <= 512). */
+int64_t scan_gemm_nt_workspace_bytes(int32_t m, int32_t n, int32_t k);
+int scan_gemm_nt(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t m, int32_t n, int32_t k, const float* bias,
+                 int32_t relu, int32_t accumulate, float* c, int64_t ldc, void* workspace, int64_t workspace_bytes, void* stream);
+/* dst [n_cols, ld_dst] = src [n_rows, n_cols]^T, zero-padded to ld_dst columns */
+int scan_transpose(const float* src, int32_t n_rows, int32_t n_cols, int64_t ld_src, float* dst, int64_t ld_dst, void* stream);
+/* d_w [n_out,n_in] (+)= dz [m,n_out]^T . x [m,n_in]; d_b [n_out] (+)= column sums of dz (d_b may be NULL) */
+int64_t scan_linear_wgrad_workspace_bytes(int32_t m, int32_t n_out, int32_t n_in);
+int scan_linear_wgrad(const float* dz, const float* x, int32_t m, int32_t n_out, int32_t n_in, int32_t accumulate, float* d_w,
+                      float* d_b, void* workspace, int64_t workspace_bytes, void* stream);
+/* in-place softmax over the first n_cols entries of each of n_rows rows (pitch ld); the pad columns are zeroed (get_edge :284-302) */
+int scan_rows_softmax(float* x, int32_t n_rows, int32_t n_cols, int64_t ld, void* stream);
+/* y [m,256] = x / max(|x|_2, eps) row-wise (sim_matrix, condgraph.py:35-43) */
+int scan_rows_l2normalize(const float* x, int32_t m, float eps, float* y, void* stream);
+/* GCN output activation over [m,256] rows: mode 0 NO, 1 relu, 2 sigmoid, 3 tanh, 4 softmax(dim=-1) (condgraph.py:274-281);
+ * act_out = act(z) (saved for the backward), y = act_out + shortcut (shortcut may be NULL; y may alias act_out when it is) */
+int scan_gcn_act_fwd(const float* z, const float* shortcut, int32_t m, int32_t mode, float* act_out, float* y, void* stream);
+int scan_gcn_act_bwd(const float* act_out, const float* dy, int32_t m, int32_t mode, float* dz, void* stream);
+
 /* ---- K4a': manifestation without the RNN (condgraph.py:320-334): tiny-batch dense layers over the K <= 16 paradigm rows ----
  * y [K, O] = act(x [K, I] . w [O, I]^T + b); relu != 0 applies ReLU.  I % 4 == 0, K * I * 4 bytes <= 200 KB. */
 int scan_rows_linear_fwd(const float* x, const float* w, const float* b, int32_t k, int32_t in_dim, int32_t out_dim, int32_t relu,

@@ -70,6 +70,15 @@ SIGNATURES = {
     "scan_node_cls_fwd": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, c_int64, _P]),
     "scan_node_cls_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "scan_class_mean_bwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
+    "scan_gemm_nt_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "scan_gemm_nt": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int32, c_int32, _P, c_int32, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "scan_transpose": (c_int32, [_P, c_int32, c_int32, c_int64, _P, c_int64, _P]),
+    "scan_linear_wgrad_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "scan_linear_wgrad": (c_int32, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, c_int64, _P]),
+    "scan_rows_softmax": (c_int32, [_P, c_int32, c_int32, c_int64, _P]),
+    "scan_rows_l2normalize": (c_int32, [_P, c_int32, c_float, _P, _P]),
+    "scan_gcn_act_fwd": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P]),
+    "scan_gcn_act_bwd": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "scan_rows_linear_fwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "scan_rows_linear_bwd": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "scan_rows_gn_relu_fwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P]),
@@ -96,6 +105,8 @@ LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_rel
             "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
             "scan_qkv_fwd": 1, "scan_qkv_bwd": 9, "scan_attn_out_ln_fwd": 1, "scan_attn_out_ln_bwd": 9, "scan_node_cls_fwd": 3,
             "scan_node_cls_bwd": 9, "scan_class_mean_bwd": 1,
+            "scan_gemm_nt": 2, "scan_transpose": 1, "scan_linear_wgrad": 5, "scan_rows_softmax": 1, "scan_rows_l2normalize": 1,
+            "scan_gcn_act_fwd": 1, "scan_gcn_act_bwd": 1,
             "scan_rows_linear_fwd": 1, "scan_rows_linear_bwd": 2, "scan_rows_gn_relu_fwd": 1, "scan_rows_gn_relu_bwd": 2,
             "scan_transfer_nodes_fwd": 2, "scan_transfer_nodes_bwd": 1, "scan_transfer_proto": 1,
             "scan_sigmoid_focal_fwd": 1, "scan_sigmoid_focal_bwd": 1, "scan_ensemble_levels": 1}

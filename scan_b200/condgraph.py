@@ -267,36 +267,10 @@ class GRAPHModule(nn.Module):
         return node_loss, packed, nodes, means
 
     def _local_gcn(self, pos_points, pos_labels, shift):
-        """Per-class GCN (condgraph.py:262-302, 404-414): Adj = softmax(affinity).detach(); two graph convolutions."""
-        out = pos_points.clone()
-        labels_host = pos_labels.cpu()
-        for i in range(self.used_num_classes):
-            idx = torch.nonzero(labels_host == i + shift).reshape(-1)
-            if idx.numel() == 0:
-                continue
-            idx = idx.to(pos_points.device)
-            sub = pos_points[idx]
-            if self.GCN_norm_cfg == "NO":
-                adj = torch.mm(sub, sub.t()).softmax(-1).detach()
-            else:
-                adj = sim_matrix(sub, sub).softmax(-1).detach()
-            x = torch.relu(self.gcn_layer1(torch.mm(adj, sub)))
-            y = self.gcn_layer2(torch.mm(adj, x))
-            act = self.GCN_out_act_cfg
-            if act == "softmax":
-                y = y.softmax(dim=-1)
-            elif act == "sigmoid":
-                y = y.sigmoid()
-            elif act == "tanh":
-                y = y.tanh()
-            elif act == "relu":
-                y = torch.relu(y)
-            elif act != "NO":
-                raise KeyError("unknown gcn output activation")
-            if self.with_shortcut_GCNs:
-                y = y + sub
-            out = out.index_copy(0, idx, y)
-        return out
+        """Per-class GCN (condgraph.py:262-302, 404-414): Adj = softmax(affinity).detach(); two graph convolutions per class,
+        all on the scan_b200 GEMM / softmax / activation kernels (ops.local_gcn)."""
+        return ops.local_gcn(pos_points, pos_labels, self.gcn_layer1, self.gcn_layer2, self.used_num_classes, shift,
+                             self.GCN_norm_cfg, self.GCN_out_act_cfg, self.with_shortcut_GCNs)
 
     # ------------------------------------------------------------------ paradigm update (condgraph.py:304-311, 558-617)
     @torch.no_grad()

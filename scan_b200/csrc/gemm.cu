@@ -584,6 +584,144 @@ __global__ void __launch_bounds__(256) class_mean_bwd_kernel(const float* __rest
   *reinterpret_cast<float4*>(d_nodes + (long long)row * channels + c) = make_float4(d.x * inv, d.y * inv, d.z * inv, d.w * inv);
 }
 
+// ---------------------------------------------------------------------------- generic helpers of the per-class GCN (a6)
+// out[r, c] (+)= act(sum_s partial[s][r][c] + bias[c]) for c < n (fixed order over s)
+__global__ void __launch_bounds__(256) splitk_reduce_act_kernel(const float* __restrict__ partial, int splits, int m, int n, long long ld_part,
+                                                                const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ out,
+                                                                long long ldc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)m * n) return;
+  const int r = (int)(i / n), c = (int)(i % n);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += partial[((long long)s * m + r) * ld_part + c];
+  if (bias) acc += __ldg(bias + c);
+  if (relu) acc = fmaxf(acc, 0.f);
+  float* o = out + (long long)r * ldc + c;
+  *o = accumulate ? *o + acc : acc;
+}
+
+// in-place softmax over the first n_cols entries of every row (block per row); columns n_cols .. ld-1 are zeroed
+__global__ void __launch_bounds__(256) rows_softmax_kernel(float* __restrict__ x, int n_cols, long long ld) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  float* row = x + (long long)blockIdx.x * ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < n_cols; c += 256) mx = fmaxf(mx, row[c]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = red[0];
+    for (int i = 1; i < 8; ++i) v = fmaxf(v, red[i]);
+    bc = v;
+  }
+  __syncthreads();
+  mx = bc;
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < n_cols; c += 256) {
+    const float e = expf(row[c] - mx);
+    row[c] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += red[i];
+    bc = 1.f / v;
+  }
+  __syncthreads();
+  const float inv = bc;
+  for (int c = threadIdx.x; c < (int)ld; c += 256) row[c] = c < n_cols ? row[c] * inv : 0.f;
+}
+
+// y[r, :] = x[r, :] / max(|x[r, :]|, eps) (sim_matrix, condgraph.py:35-43); 256 channels, one warp per row
+__global__ void __launch_bounds__(256) rows_l2norm_kernel(const float* __restrict__ x, int m, float eps, float* __restrict__ y) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x + (long long)row * 256 + lane * 8);
+  const float4 a = __ldg(x4), b = __ldg(x4 + 1);
+  float q = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+  q = warp_sum(q);
+  const float inv = 1.f / fmaxf(sqrtf(q), eps);
+  float4* y4 = reinterpret_cast<float4*>(y + (long long)row * 256 + lane * 8);
+  y4[0] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  y4[1] = make_float4(b.x * inv, b.y * inv, b.z * inv, b.w * inv);
+}
+
+// GCN output activation (condgraph.py:274-281) over rows of 256 channels, one warp per row.
+// mode 0 NO, 1 relu, 2 sigmoid, 3 tanh, 4 softmax(dim=-1).  a = act(z); y = a (+ shortcut row).
+__global__ void __launch_bounds__(256) gcn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ shortcut, int m, int mode,
+                                                          float* __restrict__ a_out, float* __restrict__ y) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  float v[8];
+  {
+    const float4* z4 = reinterpret_cast<const float4*>(z + (long long)row * 256 + lane * 8);
+    const float4 p = __ldg(z4), q = __ldg(z4 + 1);
+    v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+  }
+  if (mode == 4) {
+    float mx = v[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) mx = fmaxf(mx, v[e]);
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { v[e] = expf(v[e] - mx); s += v[e]; }
+    s = 1.f / warp_sum(s);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= s;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      v[e] = mode == 1 ? fmaxf(v[e], 0.f) : mode == 2 ? 1.f / (1.f + expf(-v[e])) : mode == 3 ? tanhf(v[e]) : v[e];
+  }
+  float4* a4 = reinterpret_cast<float4*>(a_out + (long long)row * 256 + lane * 8);
+  a4[0] = make_float4(v[0], v[1], v[2], v[3]);
+  a4[1] = make_float4(v[4], v[5], v[6], v[7]);
+  if (shortcut) {
+    const float4* s4 = reinterpret_cast<const float4*>(shortcut + (long long)row * 256 + lane * 8);
+    const float4 p = __ldg(s4), q = __ldg(s4 + 1);
+    v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w; v[4] += q.x; v[5] += q.y; v[6] += q.z; v[7] += q.w;
+  }
+  float4* y4 = reinterpret_cast<float4*>(y + (long long)row * 256 + lane * 8);
+  y4[0] = make_float4(v[0], v[1], v[2], v[3]);
+  y4[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+// dz = dy * act'(z) expressed through a = act(z)
+__global__ void __launch_bounds__(256) gcn_act_bwd_kernel(const float* __restrict__ a, const float* __restrict__ dy, int m, int mode,
+                                                          float* __restrict__ dz) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  float av[8], g[8];
+  {
+    const float4* a4 = reinterpret_cast<const float4*>(a + (long long)row * 256 + lane * 8);
+    const float4* g4 = reinterpret_cast<const float4*>(dy + (long long)row * 256 + lane * 8);
+    const float4 p = __ldg(a4), q = __ldg(a4 + 1), r = __ldg(g4), t = __ldg(g4 + 1);
+    av[0] = p.x; av[1] = p.y; av[2] = p.z; av[3] = p.w; av[4] = q.x; av[5] = q.y; av[6] = q.z; av[7] = q.w;
+    g[0] = r.x; g[1] = r.y; g[2] = r.z; g[3] = r.w; g[4] = t.x; g[5] = t.y; g[6] = t.z; g[7] = t.w;
+  }
+  if (mode == 4) {
+    float dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dot = fmaf(g[e], av[e], dot);
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = av[e] * (g[e] - dot);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      g[e] = mode == 1 ? (av[e] > 0.f ? g[e] : 0.f) : mode == 2 ? g[e] * av[e] * (1.f - av[e]) : mode == 3 ? g[e] * (1.f - av[e] * av[e]) : g[e];
+  }
+  float4* o = reinterpret_cast<float4*>(dz + (long long)row * 256 + lane * 8);
+  o[0] = make_float4(g[0], g[1], g[2], g[3]);
+  o[1] = make_float4(g[4], g[5], g[6], g[7]);
+}
+
 // ---------------------------------------------------------------------------- host side
 static int make_map_pitch(CUtensorMap* m, const float* base, uint64_t n_rows, uint64_t n_cols, uint64_t pitch_floats, uint32_t box_rows) {
   EncodeTiledFn enc;
@@ -891,5 +1029,127 @@ extern "C" int scan_class_mean_bwd(const float* d_mean, const float* packed, con
   class_mean_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d_mean, packed, (const long long*)labels, m, channels,
                                                                                       label_shift, d_nodes);
   SCAN_LAUNCH_CHECK("class_mean_bwd_kernel");
+  return SCAN_OK;
+}
+
+// ---------------------------------------------------------------------------- generic entry points (per-class GCN, a6)
+static inline long long pad4ll(long long v) { return (v + 3) / 4 * 4; }
+
+extern "C" int64_t scan_gemm_nt_workspace_bytes(int32_t m, int32_t n, int32_t k) {
+  const long long splits = ceil_div(k > 0 ? k : 1, GM_SPLIT_K);
+  return splits > 1 ? splits * (long long)m * pad4ll(n) * 4 + 1024 : 1024;
+}
+
+// c [m, n] (pitch ldc) (+)= act(a [m, k] (pitch lda) . b [n, k]^T (pitch ldb) + bias); reductions longer than 512 are split and
+// summed in a fixed order (the tensor-core accumulator truncates)
+extern "C" int scan_gemm_nt(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t m, int32_t n, int32_t k, const float* bias,
+                            int32_t relu, int32_t accumulate, float* c, int64_t ldc, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (m == 0 || n == 0) return SCAN_OK;
+  if (!a || !b || !c || m < 0 || n < 0 || k < 1 || lda < k || ldb < k || ldc < n) return SCAN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map_pitch(&ma, a, (uint64_t)m, (uint64_t)k, (uint64_t)lda, GM_BM))) return rc;
+  if ((rc = make_map_pitch(&mb, b, (uint64_t)n, (uint64_t)k, (uint64_t)ldb, 128))) return rc;
+  const int splits = (int)ceil_div(k, GM_SPLIT_K);
+  if (splits == 1) {
+    GemmArgs g = base_args(m, n, (k + GM_BK - 1) / GM_BK * GM_BK);
+    g.c = c;
+    g.ldc = (int)ldc;
+    g.bias = bias;
+    g.relu = relu;
+    g.accumulate = accumulate;
+    if ((ldc % 4) || ((uintptr_t)c & 15)) return SCAN_EINVAL;
+    return launch_gemm<128, GM_EPI_STORE>(ma, mb, g, 1, st);
+  }
+  if (!workspace || workspace_bytes < scan_gemm_nt_workspace_bytes(m, n, k)) return SCAN_ECAPACITY;
+  float* part = (float*)align256((char*)workspace);
+  const long long ldp = pad4ll(n);
+  GemmArgs g = base_args(m, n, GM_SPLIT_K);
+  g.c = part;
+  g.ldc = (int)ldp;
+  g.c_split_stride = (long long)m * ldp;
+  if ((rc = launch_gemm<128, GM_EPI_STORE>(ma, mb, g, splits, st))) return rc;
+  const long long total = (long long)m * n;
+  splitk_reduce_act_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, splits, m, n, ldp, bias, relu, accumulate, c, ldc);
+  SCAN_LAUNCH_CHECK("splitk_reduce_act_kernel");
+  return SCAN_OK;
+}
+
+// dst [n_cols, ld_dst] = src [n_rows, n_cols]^T, zero in columns n_rows .. ld_dst-1
+extern "C" int scan_transpose(const float* src, int32_t n_rows, int32_t n_cols, int64_t ld_src, float* dst, int64_t ld_dst, void* stream) {
+  if (n_rows == 0 || n_cols == 0) return SCAN_OK;
+  if (!src || !dst || n_rows < 0 || n_cols < 0 || ld_src < n_cols || ld_dst < n_rows) return SCAN_EINVAL;
+  return transpose_pad(src, n_rows, n_cols, (int)ld_src, dst, (int)ld_dst, (cudaStream_t)stream);
+}
+
+extern "C" int64_t scan_linear_wgrad_workspace_bytes(int32_t m, int32_t n_out, int32_t n_in) {
+  const long long mp = pad32(m > 0 ? m : 1);
+  return ((long long)(n_out + n_in) * mp + ceil_div(mp, GM_SPLIT_K) * (long long)n_out * n_in + (long long)n_out * n_in + n_out) * 4 + 4096;
+}
+
+// d_w [n_out, n_in] (+)= dz [m, n_out]^T . x [m, n_in];  d_b [n_out] (+)= column sums of dz   (n_in % 4 == 0)
+extern "C" int scan_linear_wgrad(const float* dz, const float* x, int32_t m, int32_t n_out, int32_t n_in, int32_t accumulate, float* d_w,
+                                 float* d_b, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (m == 0) return SCAN_OK;
+  if (!dz || !x || !d_w || !workspace || m < 0 || n_out < 1 || n_in < 4 || n_in % 4 || n_out % 4) return SCAN_EINVAL;
+  if (workspace_bytes < scan_linear_wgrad_workspace_bytes(m, n_out, n_in)) return SCAN_ECAPACITY;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mp = pad32(m);
+  Bump ws(workspace, workspace_bytes);
+  float* dzt = ws.take((long long)n_out * mp);
+  float* xt = ws.take((long long)n_in * mp);
+  float* part = ws.take(ceil_div(m, GM_SPLIT_K) * (long long)n_out * n_in);
+  float* tmp_w = ws.take((long long)n_out * n_in);
+  float* tmp_b = ws.take(n_out);
+  if (!ws.ok()) return SCAN_ECAPACITY;
+  int rc;
+  if ((rc = transpose_pad(dz, m, n_out, n_out, dzt, mp, st))) return rc;
+  if ((rc = transpose_pad(x, m, n_in, n_in, xt, mp, st))) return rc;
+  if (!accumulate) {
+    if (d_b && (rc = rowsum(dzt, n_out, m, mp, d_b, st))) return rc;
+    return wgrad(dzt, xt, n_out, n_in, m, mp, part, d_w, st);
+  }
+  if ((rc = wgrad(dzt, xt, n_out, n_in, m, mp, part, tmp_w, st))) return rc;
+  const long long n = (long long)n_out * n_in;
+  splitk_reduce_act_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(tmp_w, 1, 1, (int)n, n, nullptr, 0, 1, d_w, n);
+  SCAN_LAUNCH_CHECK("splitk_reduce_act_kernel");
+  if (d_b) {
+    if ((rc = rowsum(dzt, n_out, m, mp, tmp_b, st))) return rc;
+    splitk_reduce_act_kernel<<<(unsigned)ceil_div(n_out, 256), 256, 0, st>>>(tmp_b, 1, 1, n_out, n_out, nullptr, 0, 1, d_b, n_out);
+    SCAN_LAUNCH_CHECK("splitk_reduce_act_kernel");
+  }
+  return SCAN_OK;
+}
+
+extern "C" int scan_rows_softmax(float* x, int32_t n_rows, int32_t n_cols, int64_t ld, void* stream) {
+  if (n_rows == 0) return SCAN_OK;
+  if (!x || n_rows < 0 || n_cols < 1 || ld < n_cols) return SCAN_EINVAL;
+  rows_softmax_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>(x, n_cols, ld);
+  SCAN_LAUNCH_CHECK("rows_softmax_kernel");
+  return SCAN_OK;
+}
+
+extern "C" int scan_rows_l2normalize(const float* x, int32_t m, float eps, float* y, void* stream) {
+  if (m == 0) return SCAN_OK;
+  if (!x || !y || m < 0) return SCAN_EINVAL;
+  rows_l2norm_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(x, m, eps, y);
+  SCAN_LAUNCH_CHECK("rows_l2norm_kernel");
+  return SCAN_OK;
+}
+
+extern "C" int scan_gcn_act_fwd(const float* z, const float* shortcut, int32_t m, int32_t mode, float* act_out, float* y, void* stream) {
+  if (m == 0) return SCAN_OK;
+  if (!z || !act_out || !y || m < 0 || mode < 0 || mode > 4) return SCAN_EINVAL;
+  gcn_act_fwd_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(z, shortcut, m, mode, act_out, y);
+  SCAN_LAUNCH_CHECK("gcn_act_fwd_kernel");
+  return SCAN_OK;
+}
+
+extern "C" int scan_gcn_act_bwd(const float* act_out, const float* dy, int32_t m, int32_t mode, float* dz, void* stream) {
+  if (m == 0) return SCAN_OK;
+  if (!act_out || !dy || !dz || m < 0 || mode < 0 || mode > 4) return SCAN_EINVAL;
+  gcn_act_bwd_kernel<<<(unsigned)ceil_div(m, 8), 256, 0, (cudaStream_t)stream>>>(act_out, dy, m, mode, dz);
+  SCAN_LAUNCH_CHECK("gcn_act_bwd_kernel");
   return SCAN_OK;
 }

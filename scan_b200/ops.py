@@ -747,6 +747,134 @@ def class_means(nodes, labels, num_classes, label_shift):
 
 
 # ----------------------------------------------------------------------------------------------------
+# a6: per-class GCN (GLOBAL_GCN = False)
+# ----------------------------------------------------------------------------------------------------
+def _pad(v, q):
+    return (v + q - 1) // q * q
+
+
+def gemm_nt(a, b, m, n, k, lda, ldb, out=None, ldc=None, bias=None, relu=False, accumulate=False):
+    """out [m, n] (+)= act(a [m, k] @ b [n, k].T + bias) on the tcgen05 3xTF32 GEMM (raw-pointer form: pitches in floats)."""
+    dev = a.device
+    if out is None:
+        ldc = _pad(n, 4)
+        out = torch.empty((m, ldc), device=dev, dtype=torch.float32)
+    ws_bytes = _lib.lib().scan_gemm_nt_workspace_bytes(m, n, k)
+    ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+    call("scan_gemm_nt", _ptr(a), lda, _ptr(b), ldb, m, n, k, _ptr(bias), int(relu), int(accumulate), _ptr(out), ldc, _ptr(ws), ws_bytes,
+         _stream())
+    return out
+
+
+def transpose_pad(x, n_rows, n_cols, ld_src, ld_dst):
+    out = torch.empty((n_cols, ld_dst), device=x.device, dtype=torch.float32)
+    call("scan_transpose", _ptr(x), n_rows, n_cols, ld_src, _ptr(out), ld_dst, _stream())
+    return out
+
+
+GCN_ACT = {"NO": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "softmax": 4}
+
+
+class _LocalGCN(torch.autograd.Function):
+    """The per-class graph convolution of condgraph.py:404-414 with GCNs (:262-282) and get_edge (:284-302):
+    for every class c with members idx_c:  Adj = softmax(affinity(X_c, X_c)).detach();  X1 = relu(W1 (Adj X_c) + b1);
+    Y = act(W2 (Adj X1) + b2) (+ X_c);  out[idx_c] = Y.  All products run on the tcgen05 3xTF32 GEMM (scan_gemm_nt), the
+    class blocks are gathered / scattered with the node kernels; gradients reach the nodes only through the second operand
+    of Adj . (the adjacency is detached in the reference)."""
+
+    @staticmethod
+    def forward(ctx, points, w1, b1, w2, b2, cosine, act_mode, shortcut, idx_list):
+        points = points.contiguous()
+        w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+        dev = points.device
+        out = torch.zeros_like(points)
+        saved = []
+        for idx in idx_list:
+            mc = idx.numel()
+            mp4, mp32 = _pad(mc, 4), _pad(mc, 32)
+            sub = torch.empty((mc, C), device=dev, dtype=torch.float32)
+            call("scan_gather_rows", _ptr(points), _ptr(idx), mc, C, _ptr(sub), _stream())
+            base = sub
+            if cosine:
+                base = torch.empty_like(sub)
+                call("scan_rows_l2normalize", _ptr(sub), mc, 1e-8, _ptr(base), _stream())
+            adj = gemm_nt(base, base, mc, mc, C, C, C)                       # [mc, mp4] affinity
+            call("scan_rows_softmax", _ptr(adj), mc, mc, mp4, _stream())
+            sub_t = transpose_pad(sub, mc, C, C, mp32)                       # [256, mp32]
+            h1 = gemm_nt(adj, sub_t, mc, C, mc, mp4, mp32)                   # Adj . X
+            x1 = gemm_nt(h1, w1, mc, C, C, C, C, bias=b1, relu=True)
+            x1_t = transpose_pad(x1, mc, C, C, mp32)
+            h2 = gemm_nt(adj, x1_t, mc, C, mc, mp4, mp32)
+            z2 = gemm_nt(h2, w2, mc, C, C, C, C, bias=b2)
+            act = torch.empty_like(sub)
+            y = torch.empty_like(sub) if shortcut else act
+            call("scan_gcn_act_fwd", _ptr(z2), _ptr(sub) if shortcut else None, mc, act_mode, _ptr(act), _ptr(y), _stream())
+            call("scan_scatter_add_rows", _ptr(y), _ptr(idx), mc, C, _ptr(out), _stream())
+            saved.append((idx, adj, h1, x1, h2, act))
+        ctx.saved = saved
+        ctx.cfg = (act_mode, shortcut)
+        ctx.save_for_backward(w1, w2)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_out):
+        w1, w2 = ctx.saved_tensors
+        act_mode, shortcut = ctx.cfg
+        d_out = d_out.contiguous()
+        dev = d_out.device
+        d_points = torch.zeros_like(d_out)
+        d_w1, d_w2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        d_b1 = torch.zeros((w1.shape[0],), device=dev, dtype=torch.float32)
+        d_b2 = torch.zeros((w2.shape[0],), device=dev, dtype=torch.float32)
+        w1_t = transpose_pad(w1, C, C, C, C)
+        w2_t = transpose_pad(w2, C, C, C, C)
+        for idx, adj, h1, x1, h2, act in ctx.saved:
+            mc = idx.numel()
+            mp4, mp32 = _pad(mc, 4), _pad(mc, 32)
+            dy = torch.empty((mc, C), device=dev, dtype=torch.float32)
+            call("scan_gather_rows", _ptr(d_out), _ptr(idx), mc, C, _ptr(dy), _stream())
+            dz2 = torch.empty_like(dy)
+            call("scan_gcn_act_bwd", _ptr(act), _ptr(dy), mc, act_mode, _ptr(dz2), _stream())
+            ws_bytes = _lib.lib().scan_linear_wgrad_workspace_bytes(mc, C, C)
+            ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+            call("scan_linear_wgrad", _ptr(dz2), _ptr(h2), mc, C, C, 1, _ptr(d_w2), _ptr(d_b2), _ptr(ws), ws_bytes, _stream())
+            dh2 = gemm_nt(dz2, w2_t, mc, C, C, C, C)
+            adj_t = transpose_pad(adj, mc, mc, mp4, mp4)
+            dh2_t = transpose_pad(dh2, mc, C, C, mp32)
+            dx1 = gemm_nt(adj_t, dh2_t, mc, C, mc, mp4, mp32)
+            dz1 = torch.empty_like(dy)
+            call("scan_gcn_act_bwd", _ptr(x1), _ptr(dx1), mc, 1, _ptr(dz1), _stream())
+            call("scan_linear_wgrad", _ptr(dz1), _ptr(h1), mc, C, C, 1, _ptr(d_w1), _ptr(d_b1), _ptr(ws), ws_bytes, _stream())
+            dh1 = gemm_nt(dz1, w1_t, mc, C, C, C, C)
+            dh1_t = transpose_pad(dh1, mc, C, C, mp32)
+            d_sub = dy if shortcut else torch.zeros_like(dy)
+            gemm_nt(adj_t, dh1_t, mc, C, mc, mp4, mp32, out=d_sub, ldc=C, accumulate=True)
+            call("scan_scatter_add_rows", _ptr(d_sub), _ptr(idx), mc, C, _ptr(d_points), _stream())
+        ctx.saved = None
+        return d_points, d_w1, d_b1, d_w2, d_b2, None, None, None, None
+
+
+def local_gcn(points, labels, layer1, layer2, num_classes, label_shift, edge_norm, out_act, shortcut):
+    """Per-class GCN over the sampled nodes.  The class membership lists are built on the host (one D2H of the label vector;
+    the reference synchronises once per class at `.any()`, condgraph.py:406-407)."""
+    if points.shape[1] != C or layer1.weight.shape != (C, C) or layer2.weight.shape != (C, C):
+        raise RuntimeError("local_gcn is built for 256 -> 256 -> 256 graph convolutions")
+    if not points.is_cuda:
+        raise RuntimeError("local_gcn needs CUDA tensors (no CPU fallback)")
+    if out_act not in GCN_ACT:
+        raise KeyError("unknown gcn output activation")
+    host = labels.cpu()
+    idx_list = []
+    for c in range(num_classes):
+        idx = torch.nonzero(host == c + label_shift).reshape(-1)
+        if idx.numel():
+            idx_list.append(idx.to(torch.int32).to(points.device, non_blocking=True))
+    return _LocalGCN.apply(points, layer1.weight, layer1.bias, layer2.weight, layer2.bias, edge_norm != "NO", GCN_ACT[out_act],
+                           bool(shortcut), idx_list)
+
+
+# ----------------------------------------------------------------------------------------------------
 # a14: transfer losses
 # ----------------------------------------------------------------------------------------------------
 TRANSFER_FLAGS = {"PROTOTYPE": 1, "ADJ": 2, "ADJ_COMPLETE": 4}
