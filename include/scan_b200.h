@@ -101,6 +101,27 @@ int scan_add_relu_bwd(const scan_levels_t* lv, const void* const* dy_levels_host
  * labels_out [R] int64, rows layout.  Bit-exact with the reference (fp32, no FMA contraction). */
 int scan_fcos_assign(const scan_levels_t* lv, const float* boxes, const int64_t* box_labels,
                      const int32_t* box_count, int32_t g_max, int64_t* labels_out, void* stream);
+/* The same assignment for FCOSLossComputation (loss.py:40-126), which also needs the regression targets:
+ * reg_targets_out [R, 4] = (l, t, r, b) of the chosen box (box 0 where no box matched, like the reference's argmin). */
+int scan_fcos_assign_reg(const scan_levels_t* lv, const float* boxes, const int64_t* box_labels,
+                         const int32_t* box_count, int32_t g_max, int64_t* labels_out, float* reg_targets_out,
+                         void* stream);
+
+/* ---- f2: FCOSLossComputation.__call__ fused (loss.py:168-230; layers/iou_loss.py:5-38; SigmoidFocalLoss_cuda.cu:36-98) ----
+ * Reads the FCOS head's NCHW maps in place (HOST arrays of per-level device pointers: cls [N,C,H,W] logits, reg [N,4,H,W],
+ * ctr [N,1,H,W] logits) with labels [R] / reg_targets [R,4] from scan_fcos_assign_reg.
+ * losses3 = (cls_loss, reg_loss, centerness_loss) device scalars; sums6 (fp64: focal sum, #pos, sum w, sum iou*w, sum iou,
+ * sum bce) is kept for the backward; partials: scan_fcos_loss_num_partials() doubles of scratch. */
+int32_t scan_fcos_loss_num_partials(void);
+int scan_fcos_loss_fwd(const scan_levels_t* lv, const void* const* cls_host, const void* const* reg_host, const void* const* ctr_host,
+                       const int64_t* labels, const float* reg_targets, int32_t num_classes, float gamma, float alpha,
+                       double* partials, double* sums6, float* losses3, void* stream);
+/* d_losses3: device vector of the three upstream gradients; writes d_cls / d_reg / d_ctr (same shapes as the maps) */
+int scan_fcos_loss_bwd(const scan_levels_t* lv, const void* const* cls_host, const void* const* reg_host, const void* const* ctr_host,
+                       const int64_t* labels, const float* reg_targets, int32_t num_classes, float gamma, float alpha,
+                       const double* sums6, const float* d_losses3, void* const* d_cls_host, void* const* d_reg_host,
+                       void* const* d_ctr_host, void* stream);
+
 
 /* ---- K1b: node sampling (loss.py:430-458 source branch; loss.py:497-516 target branch) ---------
  * mode 0 (source): positive <=> labels[g] > 0, node label = labels[g]; per level all negatives when

@@ -37,15 +37,17 @@ def level_locations(h, w, stride):
     return xs.repeat(h), ys.repeat_interleave(w)
 
 
-def fcos_assign(level_shapes, strides, boxes_per_image, labels_per_image):
+def fcos_assign(level_shapes, strides, boxes_per_image, labels_per_image, return_reg=False):
     """loss.py:262-343.  Returns a list (one per level) of int64 label vectors laid out
     image-major ([N*H_l*W_l], loss.py:289-294).  fp32 arithmetic; ranges inclusive on both
     ends; area uses the +1 convention (structures/bounding_box.py:229-230); ties resolved to
     the first minimum (torch.min); a location with no admissible box gets label 0."""
     out = []
+    regs = []
     for (h, w), s, (lo, hi) in zip(level_shapes, strides, SIZES_OF_INTEREST):
         xs, ys = level_locations(h, w, s)
         per_image = []
+        per_image_reg = []
         for boxes, labels in zip(boxes_per_image, labels_per_image):
             boxes = boxes.float()
             xs, ys = xs.to(boxes.device), ys.to(boxes.device)
@@ -64,7 +66,12 @@ def fcos_assign(level_shapes, strides, boxes_per_image, labels_per_image):
             lab = labels.long().to(boxes.device)[idx]
             lab = torch.where(best == INF_AREA, torch.zeros_like(lab), lab)
             per_image.append(lab)
+            # loss.py:111: regression targets (l, t, r, b) of the chosen box (index 0 where nothing matched)
+            per_image_reg.append(torch.stack([l, t, r, b], dim=2)[torch.arange(l.shape[0], device=l.device), idx])
         out.append(torch.cat(per_image))
+        regs.append(torch.cat(per_image_reg))
+    if return_reg:
+        return out, regs
     return out
 
 
@@ -415,6 +422,37 @@ def sigmoid_focal_loss_backward_elementwise(logits, targets, d_losses, gamma, al
     term1 = (1 - p) ** gamma * (1 - p - p * gamma * torch.log(p.clamp(min=1.17549435e-38)))
     term2 = p ** gamma * ((-x * ge - torch.log1p(torch.exp(x - 2 * x * ge))) * (1 - p) * gamma - p)
     return (-(t == cls).float() * term1 * alpha - ((t != cls) & (t >= 0)).float() * term2 * (1 - alpha)) * d_losses
+
+
+def fcos_loss_computation(level_shapes, strides, boxes_per_image, labels_per_image, box_cls, box_regression, centerness,
+                          gamma=2.0, alpha=0.25):
+    """FCOSLossComputation.__call__ (loss.py:168-230) with IOULoss (layers/iou_loss.py:5-38), compute_centerness_targets
+    (loss.py:128-133) and nn.BCEWithLogitsLoss: returns (cls_loss, reg_loss, centerness_loss)."""
+    n = box_cls[0].shape[0]
+    c = box_cls[0].shape[1]
+    labels, regs = fcos_assign(level_shapes, strides, boxes_per_image, labels_per_image, return_reg=True)
+    cls_flat = torch.cat([x.permute(0, 2, 3, 1).reshape(-1, c) for x in box_cls])
+    reg_flat = torch.cat([x.permute(0, 2, 3, 1).reshape(-1, 4) for x in box_regression])
+    ctr_flat = torch.cat([x.reshape(-1) for x in centerness])
+    lab = torch.cat(labels)
+    tgt = torch.cat(regs)
+    pos = torch.nonzero(lab > 0).squeeze(1)
+    cls_loss = sigmoid_focal_loss_elementwise(cls_flat, lab.int(), gamma, alpha).sum() / (pos.numel() + n)
+    reg_p, reg_t, ctr_p = reg_flat[pos], tgt[pos], ctr_flat[pos]
+    if pos.numel() == 0:
+        return cls_loss, reg_p.sum(), ctr_p.sum()
+    lr, tb = reg_t[:, [0, 2]], reg_t[:, [1, 3]]
+    ctr_t = torch.sqrt((lr.min(-1)[0] / lr.max(-1)[0]) * (tb.min(-1)[0] / tb.max(-1)[0]))
+    t_area = (reg_t[:, 0] + reg_t[:, 2]) * (reg_t[:, 1] + reg_t[:, 3])
+    p_area = (reg_p[:, 0] + reg_p[:, 2]) * (reg_p[:, 1] + reg_p[:, 3])
+    w_i = torch.min(reg_p[:, 0], reg_t[:, 0]) + torch.min(reg_p[:, 2], reg_t[:, 2])
+    h_i = torch.min(reg_p[:, 3], reg_t[:, 3]) + torch.min(reg_p[:, 1], reg_t[:, 1])
+    inter = w_i * h_i
+    union = t_area + p_area - inter
+    iou = -torch.log((inter + 1.0) / (union + 1.0))
+    reg_loss = (iou * ctr_t).sum() / ctr_t.sum() if bool(ctr_t.sum() > 0) else iou.mean()
+    ctr_loss = F.binary_cross_entropy_with_logits(ctr_p, ctr_t)
+    return cls_loss, reg_loss, ctr_loss
 
 
 def ensemble(mode, cls_logits, act_maps):

@@ -45,6 +45,10 @@ SIGNATURES = {
     "scan_add_relu_fwd": (c_int32, [_LV, _P, _P, _P, _P, _P]),
     "scan_add_relu_bwd": (c_int32, [_LV, _P, _P, _P, _P, _P, c_int64, _P]),
     "scan_fcos_assign": (c_int32, [_LV, _P, _P, _P, c_int32, _P, _P]),
+    "scan_fcos_assign_reg": (c_int32, [_LV, _P, _P, _P, c_int32, _P, _P, _P]),
+    "scan_fcos_loss_num_partials": (c_int32, []),
+    "scan_fcos_loss_fwd": (c_int32, [_LV, _P, _P, _P, _P, _P, c_int32, c_float, c_float, _P, _P, _P, _P]),
+    "scan_fcos_loss_bwd": (c_int32, [_LV, _P, _P, _P, _P, _P, c_int32, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "scan_sample_workspace_bytes": (c_int64, [c_int64]),
     "scan_sample_nodes": (c_int32, [_LV, c_int32, c_int32, _P, _P, _P, _P, _P, c_int32, _P, _P, c_int64, _P]),
     "scan_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
@@ -100,8 +104,8 @@ SIGNATURES = {
 
 _lib = None
 # kernels each entry point launches (memsets excluded): bench.py's gpu_launches is counted from this table
-LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_fcos_assign": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
-            "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_attn_fwd": 2, "scan_attn_bwd": 4,
+LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_fcos_assign": 1, "scan_fcos_assign_reg": 1, "scan_fcos_loss_fwd": 2, "scan_fcos_loss_bwd": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
+            "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_attn_fwd": 5, "scan_attn_bwd": 4,
             "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
             "scan_qkv_fwd": 1, "scan_qkv_bwd": 9, "scan_attn_out_ln_fwd": 1, "scan_attn_out_ln_bwd": 9, "scan_node_cls_fwd": 3,
             "scan_node_cls_bwd": 9, "scan_class_mean_bwd": 1,

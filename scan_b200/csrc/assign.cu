@@ -12,7 +12,7 @@ namespace scan {
 __global__ void __launch_bounds__(256) fcos_assign_kernel(Levels lv, const float* __restrict__ boxes,
                                                           const int64_t* __restrict__ box_labels,
                                                           const int32_t* __restrict__ box_count, int g_max,
-                                                          int64_t* __restrict__ labels_out) {
+                                                          int64_t* __restrict__ labels_out, float4* __restrict__ reg_out) {
   const long long R = lv.row_off[SCAN_MAX_LEVELS];
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= R) return;
@@ -58,6 +58,10 @@ __global__ void __launch_bounds__(256) fcos_assign_kernel(Levels lv, const float
   int64_t lab = 0;
   if (best != INF) lab = __ldg(box_labels + (long long)n * g_max + best_i);
   labels_out[g] = lab;
+  if (reg_out) {   // loss.py:111: reg_targets of the chosen box (box 0 when nothing matched: argmin of an all-INF row)
+    const float4 b = __ldg(b4 + best_i);
+    reg_out[g] = make_float4(__fsub_rn(x, b.x), __fsub_rn(y, b.y), __fsub_rn(b.z, x), __fsub_rn(b.w, y));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,7 +271,23 @@ extern "C" int scan_fcos_assign(const scan_levels_t* lvh, const float* boxes, co
   if (lv.n_levels > 5) return SCAN_ENOTSUP;  // the reference defines 5 size ranges (loss.py:263-269)
   const long long R = lv.row_off[SCAN_MAX_LEVELS];
   scan::fcos_assign_kernel<<<(unsigned)scan::ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(
-      lv, boxes, box_labels, box_count, g_max, labels_out);
+      lv, boxes, box_labels, box_count, g_max, labels_out, nullptr);
+  SCAN_LAUNCH_CHECK("fcos_assign_kernel");
+  return SCAN_OK;
+}
+
+// the same assignment for FCOSLossComputation (loss.py:40-126), which also needs the (l, t, r, b) regression targets [R, 4]
+extern "C" int scan_fcos_assign_reg(const scan_levels_t* lvh, const float* boxes, const int64_t* box_labels,
+                                    const int32_t* box_count, int32_t g_max, int64_t* labels_out, float* reg_targets_out,
+                                    void* stream) {
+  scan::Levels lv;
+  int rc = scan::make_levels(lvh, &lv);
+  if (rc) return rc;
+  if (!boxes || !box_labels || !box_count || !labels_out || !reg_targets_out || g_max < 1) return SCAN_EINVAL;
+  if (lv.n_levels > 5) return SCAN_ENOTSUP;
+  const long long R = lv.row_off[SCAN_MAX_LEVELS];
+  scan::fcos_assign_kernel<<<(unsigned)scan::ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(
+      lv, boxes, box_labels, box_count, g_max, labels_out, reinterpret_cast<float4*>(reg_targets_out));
   SCAN_LAUNCH_CHECK("fcos_assign_kernel");
   return SCAN_OK;
 }

@@ -322,6 +322,56 @@ def fcos_assign(geo, boxes, box_labels, box_count, g_max):
     return labels
 
 
+def fcos_assign_reg(geo, boxes, box_labels, box_count, g_max):
+    """Assignment + (l, t, r, b) regression targets [R,4] for FCOSLossComputation (loss.py:86-126)."""
+    labels = torch.empty((geo.R,), device=boxes.device, dtype=torch.int64)
+    reg = torch.empty((geo.R, 4), device=boxes.device, dtype=torch.float32)
+    call("scan_fcos_assign_reg", geo.ref(), _ptr(boxes), _ptr(box_labels), _ptr(box_count), g_max, _ptr(labels), _ptr(reg), _stream())
+    return labels, reg
+
+
+class _FcosLoss(torch.autograd.Function):
+    """(cls_loss, reg_loss, centerness_loss) of FCOSLossComputation.__call__ (loss.py:168-230) in one pass over the head's maps."""
+
+    @staticmethod
+    def forward(ctx, geo, labels, reg_targets, gamma, alpha, n_levels, *maps):
+        maps = [m.contiguous() for m in maps]
+        cls, reg, ctr = maps[:n_levels], maps[n_levels:2 * n_levels], maps[2 * n_levels:]
+        dev = cls[0].device
+        num_classes = cls[0].shape[1]
+        partials = torch.empty((_lib.lib().scan_fcos_loss_num_partials(),), device=dev, dtype=torch.float64)
+        sums = torch.empty((6,), device=dev, dtype=torch.float64)
+        losses = torch.empty((3,), device=dev, dtype=torch.float32)
+        call("scan_fcos_loss_fwd", geo.ref(), _ptr_array(cls), _ptr_array(reg), _ptr_array(ctr), _ptr(labels), _ptr(reg_targets), num_classes,
+             gamma, alpha, _ptr(partials), _ptr(sums), _ptr(losses), _stream())
+        ctx.geo, ctx.cfg = geo, (gamma, alpha, n_levels, num_classes)
+        ctx.save_for_backward(labels, reg_targets, sums, *maps)
+        return losses
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_losses):
+        labels, reg_targets, sums = ctx.saved_tensors[:3]
+        maps = ctx.saved_tensors[3:]
+        gamma, alpha, n_levels, num_classes = ctx.cfg
+        cls, reg, ctr = maps[:n_levels], maps[n_levels:2 * n_levels], maps[2 * n_levels:]
+        d_losses = d_losses.to(torch.float32).contiguous()
+        grads = [torch.empty_like(m) for m in maps]
+        call("scan_fcos_loss_bwd", ctx.geo.ref(), _ptr_array(cls), _ptr_array(reg), _ptr_array(ctr), _ptr(labels), _ptr(reg_targets),
+             num_classes, gamma, alpha, _ptr(sums), _ptr(d_losses), _ptr_array(grads[:n_levels]), _ptr_array(grads[n_levels:2 * n_levels]),
+             _ptr_array(grads[2 * n_levels:]), _stream())
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
+def fcos_loss(geo, labels, reg_targets, box_cls, box_regression, centerness, gamma, alpha):
+    """Returns a [3] tensor (cls_loss, reg_loss, centerness_loss)."""
+    for m in list(box_cls) + list(box_regression) + list(centerness):
+        if not m.is_cuda or m.dtype != torch.float32:
+            raise RuntimeError("fcos_loss expects CUDA fp32 maps (no CPU fallback)")
+    n_levels = len(box_cls)
+    return _FcosLoss.apply(geo, labels, reg_targets, float(gamma), float(alpha), n_levels, *box_cls, *box_regression, *centerness)
+
+
 class SampleResult(object):
     __slots__ = ("node_rows", "node_labels", "meta", "n_nodes")
 

@@ -723,3 +723,37 @@ def test_local_gcn_matches_float64(m, k, shift, norm, act, shortcut):
     _close(nd.grad, nr.grad, 2e-4, "d_nodes", atol=1e-7)
     for name, a, b in (("w1", l1g.weight, l1d.weight), ("b1", l1g.bias, l1d.bias), ("w2", l2g.weight, l2d.weight), ("b2", l2g.bias, l2d.bias)):
         _close(a.grad, b.grad, 2e-4, "d_" + name, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["c8", "car", "dense"])
+def test_fcos_loss_computation_matches_reference_golden(name, golden_dir):
+    """f2: scan_fcos_assign_reg + the fused loss pass against vectors generated from the UNMODIFIED reference
+    FCOSLossComputation (tests/tools/make_golden_fcos_loss.py): three losses and the gradients of all 15 head maps."""
+    import os
+    import fcos_loss_case
+    from scan_b200 import fcos_hooks
+    from scan_b200.config import scan_cfg
+    from scan_b200.structures import BoxList
+    gold = np.load(os.path.join(golden_dir, "fcos_loss.npz"))
+    shapes, strides, boxes, labels, cls, reg, ctr, hw = fcos_loss_case.build(name)
+    targets = []
+    for b, l in zip(boxes, labels):
+        t = BoxList(b, (hw[1], hw[0]), mode="xyxy")
+        t.add_field("labels", l)
+        targets.append(t)
+    maps = [m.to(DEV).requires_grad_(True) for m in cls + reg + ctr]
+    n = len(shapes)
+    ev = fcos_hooks.make_fcos_loss_evaluator(scan_cfg("c2f"))
+    losses = ev(None, maps[:n], maps[n:2 * n], maps[2 * n:], targets)
+    (losses[0] * 1.0 + losses[1] * 0.7 + losses[2] * 1.3).backward()
+    for i, v in enumerate(losses):
+        w = float(gold["%s/loss%d" % (name, i)])
+        assert abs(float(v) - w) <= 2e-5 * max(1.0, abs(w)), "loss %d: %r vs %r" % (i, float(v), w)
+    for i, m in enumerate(maps):
+        _close(m.grad, torch.from_numpy(gold["%s/grad%d" % (name, i)]), 2e-5, "grad %d" % i, atol=1e-9)
+    # regression targets / labels bit-exact with the oracle's assignment
+    geo = ops.Geometry(shapes, strides, len(boxes))
+    pb, pl, pc, gmax = ops.pad_targets(targets, DEV)
+    lab, rt = ops.fcos_assign_reg(geo, pb, pl, pc, gmax)
+    wl, wr = orc.fcos_assign(shapes, strides, boxes, labels, return_reg=True)
+    assert torch.equal(lab.cpu(), torch.cat(wl)) and torch.equal(rt.cpu(), torch.cat(wr))
