@@ -103,6 +103,34 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE the pinned host batches are allocated (first touch
+    places them on that node): at 8 ranks the end-to-end run streams 8 x 367 MB per step out of host memory, and remote-node
+    pinned buffers were the limiter of the round-1 e2e scaling (0.87 at 8 GPUs).  Best effort: returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus) > 12:
+            bus = bus[-12:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def make_batches(n_images, num_fg=8, pinned=False):
     from scan_b200.synthetic import make_workload
     src_f, src_t = make_workload(n_images, num_fg, seed=1234, dir_seed=77)
@@ -274,11 +302,13 @@ def measure_tf32_peak(dev):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def work_model(n_img, k, m_src, m_tgt, db_points):
+def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
     """Algorithmic work per STEP of every entry point (SURVEY 8d per-unit figures x the units one step processes):
     {entry: (bound, amount)}; bytes for HBM-bound entries, flops for tensor-bound ones.  R = rows of one pass."""
     R = n_img * L_PER_IMAGE
     row = 1024                                   # one fp32 row of 256 channels
+    if not tgt_graph:                            # no transfer loss / self-training: the target pass skips graph aggregation
+        m_tgt = 0
     mm = m_src * m_src + m_tgt * m_tgt
     ms = m_src + m_tgt
     return {
@@ -354,6 +384,7 @@ def main():
         return
 
     import torch.distributed as dist
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -488,6 +519,7 @@ def main():
         return evs
 
     barrier()
+    e2e_marks = [time.perf_counter()]
     f0.record()
     ready = stage(0)
     for i in range(args.steps):
@@ -500,6 +532,7 @@ def main():
         consumed[b_].record(main_stream)
         host = [r.cpu() for r in res if r is not None]
         d2h = sum(h.numel() * 4 for h in host)
+        e2e_marks.append(time.perf_counter())
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -519,7 +552,7 @@ def main():
         # ---- per-entry-point roofline table: algorithmic work of one step / CUDA-event time of the entry point in the step
         table = []
         if not is_eval:
-            work = work_model(n, k_cls, m_src, m_tgt, db_points)
+            work = work_model(n, k_cls, m_src, m_tgt, db_points, module.transfer_cfg[0] is not None or module.with_self_training)
             for name, (bound, amount) in work.items():
                 t_ms = kernel_ms.get(name, {"ms": 0.0})["ms"] / args.steps
                 if t_ms <= 0:
@@ -565,9 +598,11 @@ def main():
                                      "arithmetic), cudnn.benchmark %s; parity runs force fp32 towers, the error at THESE flags is "
                                      "recorded by tests/test_gpu_module.py::test_benchmark_flags_cudnn_tf32_error_is_reported"
                                      % ("on" if torch.backends.cudnn.benchmark else "off"),
-                           "e2e_input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i",
+                           "e2e_input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i"
+                                                 + ("; process bound to the GPU's NUMA node %s before pinning" % numa_node if numa_node is not None else ""),
                            "l2_note": "inputs %d MB per pass exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
-                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "host_ms_per_step": [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(e2e_marks[:-1], e2e_marks[1:])]},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
                 "eager_gpu_baseline": eager, "tf32_peak_tflops_measured": tf32_peak, "hbm_peak_gbs": hbm_peak,
                 "kernel_ms_per_step": {k_: v["ms"] / args.steps for k_, v in kernel_ms.items()},

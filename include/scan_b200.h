@@ -65,6 +65,10 @@ int scan_pack_rows(const scan_levels_t* lv, const void* const* nchw_host, int32_
 /* rows [R, C] -> nchw (overwrite when accumulate == 0, += otherwise): the backward of scan_pack_rows */
 int scan_unpack_rows(const scan_levels_t* lv, const float* rows, int32_t channels,
                      void* const* nchw_host, int32_t accumulate, void* stream);
+/* scan_unpack_levels: the same from one NHWC-dense [N*H_l*W_l, C] matrix PER LEVEL (HOST array of device pointers; the
+ * gradients cuDNN's backward-data hands back level by level), all levels in one launch. */
+int scan_unpack_levels(const scan_levels_t* lv, const void* const* rows_levels_host, int32_t channels,
+                       void* const* nchw_host, void* stream);
 
 /* ---- f1: GroupNorm(32) + ReLU of the head_in towers on the rows layout (condgraph.py:68-119: the
  *      nn.GroupNorm(32, C) + nn.ReLU that follow every tower convolution) ---------

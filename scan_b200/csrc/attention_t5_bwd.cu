@@ -142,14 +142,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(PrepArgs a, int m, i
 
 // ---------------------------------------------------------------------------- dQ
 // smem: Q hi/lo (4 x 16 KB) | dO hi/lo (4 x 16 KB) | K stage 32 KB | V stage 32 KB | K^T stage 32 KB
-// TMEM: two S/dP buffers [0,128) / [128,256): S [b*128, +64) and dP [b*128+64, +64), each the sum of its three 3xTF32
-//       products (three N = 64 MMAs per k-step into ONE accumulator)   dS operand slot hi [256,320) lo [320,384)
-//       dQ accumulator [384,512)
-// Pipeline (round 2): ncu showed the elementwise warps waiting 36 % of their time for S/dP while the tensor pipe was only half
-// busy -- with ONE S/dP buffer the MMA warp could not issue tile t+1 before every elementwise thread had pulled tile t into
-// registers (a barrier round trip per tile on the critical path).  Summing the three score products in the accumulator
-// shrinks S from 192 to 64 columns, which pays for a second S/dP buffer: the tensor pipe now runs one tile ahead, and the
-// elementwise warps load 32 instead of 64 TMEM values per tile and skip two adds per score.
+// TMEM: S [0,192) (wide: hi.hi | hi.lo | lo.hi)   dP [192,256) (three MMAs into one accumulator)
+//       dS operand slot hi [256,320) lo [320,384)   dQ accumulator [384,512)
+// Pipeline: the elementwise warps pull S/dP of tile t into registers and release the TMEM region at once, so the tensor
+// pipe computes S/dP of tile t+1 while they work; dQ MMAs of tile t follow as soon as dS(t) is in the operand slot.
 constexpr int DQ_SMEM = 1024 + 8 * B5_BOX128 + 3 * 4 * B5_BOX64 + 1024;
 constexpr float B5_LOG2E = 1.4426950408889634f;
 // The tensor core adds into its fp32 accumulator with truncation: the gradient accumulators are drained into the fp32
@@ -184,12 +180,12 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint64_t* v_empty = bars + 4;
   uint64_t* kt_full = bars + 5;
   uint64_t* kt_empty = bars + 6;
-  uint64_t* sp_full = bars + 7;   // [2] S and dP of a tile are in TMEM buffer t & 1
-  uint64_t* sp_free = bars + 9;   // [2] ... and have been pulled into registers (512 arrivals)
-  uint64_t* ds_full = bars + 11;  // dS operand written (512 arrivals)
-  uint64_t* dq_done = bars + 12;  // dQ MMAs of the tile retired: the dS slot may be overwritten
-  uint64_t* acc_full = bars + 13;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+  uint64_t* sp_full = bars + 7;   // S and dP of a tile are in TMEM
+  uint64_t* sp_free = bars + 8;   // ... and have been pulled into registers (512 arrivals)
+  uint64_t* ds_full = bars + 9;   // dS operand written (512 arrivals)
+  uint64_t* dq_done = bars + 10;  // dQ MMAs of the tile retired: the dS slot may be overwritten
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
@@ -204,7 +200,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const bool accum = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 14; ++i) mbar_init(smem_u32(bars + i), (i == 9 || i == 10 || i == 11) ? B5_EW : 1);
+    for (int i = 0; i < 12; ++i) mbar_init(smem_u32(bars + i), (i == 8 || i == 9) ? B5_EW : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -268,10 +264,6 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       // hide behind the dP MMAs and the dQ MMAs respectively
       auto issue_sdp = [&](int t) {
         const uint32_t ph = (uint32_t)(t & 1);
-        const int buf = t & 1;
-        const uint32_t sd = tmem_base + buf * 128, pd = sd + 64;
-        // the buffer was last used by tile t-2: its S/dP must have been pulled into registers
-        if (t >= 2) mbar_wait(smem_u32(sp_free + buf), (uint32_t)(((t - 2) >> 1) & 1));
         mbar_wait(smem_u32(k_full), ph);
         tcgen05_fence_after();
 #pragma unroll
@@ -279,13 +271,9 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            const uint64_t bkh = umma_desc_sw128(ka + kb * 2 * B5_BOX64 + k * 32);
-            const uint64_t bkl = umma_desc_sw128(ka + (kb * 2 + 1) * B5_BOX64 + k * 32);
-            const uint64_t aqh = umma_desc_sw128(qa + kb * B5_BOX128 + k * 32);
-            const uint64_t aql = umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32);
-            b5_mma_ss(sd, aqh, bkh, B5_ID64, acc);   // Q_hi . K_hi
-            b5_mma_ss(sd, aqh, bkl, B5_ID64, 1);     // Q_hi . K_lo
-            b5_mma_ss(sd, aql, bkh, B5_ID64, 1);     // Q_lo . K_hi
+            const uint64_t bk = umma_desc_sw128(ka + kb * 2 * B5_BOX64 + k * 32);
+            b5_mma_ss(tmem_base + 0, umma_desc_sw128(qa + kb * B5_BOX128 + k * 32), bk, B5_ID128, acc);         // Q_hi . [K_hi ; K_lo]
+            b5_mma_ss(tmem_base + 128, umma_desc_sw128(qa + (2 + kb) * B5_BOX128 + k * 32), bk, B5_ID64, acc);   // Q_lo . K_hi
           }
         b5_commit(smem_u32(k_empty));
         mbar_wait(smem_u32(v_full), ph);
@@ -299,15 +287,18 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
             const uint64_t bvl = umma_desc_sw128(va + (kb * 2 + 1) * B5_BOX64 + k * 32);
             const uint64_t adh = umma_desc_sw128(da + kb * B5_BOX128 + k * 32);
             const uint64_t adl = umma_desc_sw128(da + (2 + kb) * B5_BOX128 + k * 32);
-            b5_mma_ss(pd, adh, bvh, B5_ID64, acc);   // dO_hi . V_hi
-            b5_mma_ss(pd, adh, bvl, B5_ID64, 1);     // dO_hi . V_lo
-            b5_mma_ss(pd, adl, bvh, B5_ID64, 1);     // dO_lo . V_hi
+            b5_mma_ss(tmem_base + 192, adh, bvh, B5_ID64, acc);   // dO_hi . V_hi
+            b5_mma_ss(tmem_base + 192, adh, bvl, B5_ID64, 1);     // dO_hi . V_lo
+            b5_mma_ss(tmem_base + 192, adl, bvh, B5_ID64, 1);     // dO_lo . V_hi
           }
         b5_commit(smem_u32(v_empty));
-        b5_commit(smem_u32(sp_full + buf));
+        b5_commit(smem_u32(sp_full));
       };
       for (int tt = 0; tt <= n_tiles; ++tt) {
-        if (tt < n_tiles) issue_sdp(tt);   // runs one tile ahead of the dQ MMAs below (second S/dP buffer)
+        if (tt < n_tiles) {
+          if (tt > 0) mbar_wait(smem_u32(sp_free), (uint32_t)((tt - 1) & 1));   // S/dP of tile tt-1 now live in registers
+          issue_sdp(tt);
+        }
         if (tt == 0) continue;
         const int t = tt - 1;
         const uint32_t ph = (uint32_t)(t & 1);
@@ -342,7 +333,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const uint32_t drop_thr = DROP ? (uint32_t)fminf(drop_p * 4294967296.f, 4294967295.f) : 0u;
     const uint32_t hrow = attn_drop_pre(seed, chunk) ^ ((uint32_t)grow * ATTN_DROP_CI);
     const uint32_t tb = tmem_base + lb;
-    float a[16], x[16];
+    float a[16], b[16], c[16], x[16];
     auto drain_dq = [&](bool first) {
       tmem_drain16<2>(tb + 384 + cq * 16, dq + (base + grow) * 64 + cq * 16, scale, first, grow < m);
     };
@@ -359,21 +350,22 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
         drain_dq(!accum && t == DQ_FLUSH);
         tcgen05_fence_before();
       }
-      const int buf = t & 1;
-      mbar_wait(smem_u32(sp_full + buf), (uint32_t)((t >> 1) & 1));
+      mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
-      b5_ld16(tb + buf * 128 + cq * 16, a);
-      b5_ld16(tb + buf * 128 + 64 + cq * 16, x);
+      b5_ld16(tb + cq * 16, a);
+      b5_ld16(tb + 64 + cq * 16, b);
+      b5_ld16(tb + 128 + cq * 16, c);
+      b5_ld16(tb + 192 + cq * 16, x);
       b5_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(smem_u32(sp_free + buf));
+      mbar_arrive(smem_u32(sp_free));
       const int j0 = (t0 + t) * 64 + cq * 16;
       const int lim = m - j0;
       [[maybe_unused]] const uint32_t hcol = (uint32_t)j0 * ATTN_DROP_CJ;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float p = b5_ex2(fmaf(a[e], sl2, -lse2));
+        const float p = b5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse2));
         float dp = x[e];
         if constexpr (DROP) dp = (attn_drop_mix(hrow ^ (hcol + (uint32_t)e * ATTN_DROP_CJ)) >= drop_thr) ? dp * inv_keep : 0.f;
         float ds = p * (dp - dl_r);
@@ -406,10 +398,9 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 
 // ---------------------------------------------------------------------------- dK, dV
 // smem: K hi/lo (4 x 16 KB) | V hi/lo (4 x 16 KB) | 2 stages of (Q 16 KB + dO 16 KB) | dO^T stage 16 KB | Q^T stage 16 KB
-// TMEM: two S^T/dP^T buffers [0,64) / [64,128): S^T [b*64, +32) and dP^T [b*64+32, +32), each the sum of its three 3xTF32
-//       products   operand slots P~^T hi [128,160) lo [160,192), dS^T hi [192,224) lo [224,256)   dV accumulator [256,384)
-//       dK accumulator [384,512)
-// Same double-buffered S/dP pipeline as the dQ kernel (the tensor pipe runs one query tile ahead of the elementwise warps).
+// TMEM: S^T [0,96) (wide)   dP^T [96,128) (three MMAs)   operand slots P~^T hi [128,160) lo [160,192), dS^T hi [192,224)
+//       lo [224,256)   dV accumulator [256,384)   dK accumulator [384,512)
+// Same register-buffered pipeline as the dQ kernel.
 constexpr int DKV_QSTAGE = 8 * B5_BOX32;   // Q tile (16 KB) + dO tile (16 KB); two stages
 constexpr int DKV_SMEM = 1024 + 8 * B5_BOX128 + 2 * DKV_QSTAGE + 8 * B5_BOX32 + 1024;
 
@@ -433,12 +424,12 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   uint64_t* q_empty = bars + 3;    // [2]
   uint64_t* t_full = bars + 5;
   uint64_t* t_empty = bars + 6;    // dO^T and Q^T planes (accumulation operands)
-  uint64_t* sp_full = bars + 7;    // [2]
-  uint64_t* sp_free = bars + 9;    // [2] 512 arrivals
-  uint64_t* op_full = bars + 11;   // 512 arrivals
-  uint64_t* acc_done = bars + 12;
-  uint64_t* acc_full = bars + 13;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+  uint64_t* sp_full = bars + 7;
+  uint64_t* sp_free = bars + 8;    // 512 arrivals
+  uint64_t* op_full = bars + 9;    // 512 arrivals
+  uint64_t* acc_done = bars + 10;
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
@@ -450,7 +441,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
   const bool accum = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 14; ++i) mbar_init(smem_u32(bars + i), (i == 9 || i == 10 || i == 11) ? B5_EW : 1);
+    for (int i = 0; i < 12; ++i) mbar_init(smem_u32(bars + i), (i == 8 || i == 9) ? B5_EW : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -505,8 +496,6 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       auto issue_sdp = [&](int t) {
         const int st = t & 1;
         const uint32_t qa = smem_u32(q_s + st * DKV_QSTAGE), da = qa + 4 * B5_BOX32;
-        const uint32_t sd = tmem_base + st * 64, pd = sd + 32;
-        if (t >= 2) mbar_wait(smem_u32(sp_free + st), (uint32_t)(((t - 2) >> 1) & 1));   // buffer last used by tile t-2
         mbar_wait(smem_u32(q_full + st), (uint32_t)((t >> 1) & 1));
         tcgen05_fence_after();
 #pragma unroll
@@ -514,26 +503,27 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb | k) != 0;
-            const uint64_t bqh = umma_desc_sw128(qa + kb * 2 * B5_BOX32 + k * 32);
-            const uint64_t bql = umma_desc_sw128(qa + (kb * 2 + 1) * B5_BOX32 + k * 32);
+            const uint64_t bq = umma_desc_sw128(qa + kb * 2 * B5_BOX32 + k * 32);
             const uint64_t bdh = umma_desc_sw128(da + kb * 2 * B5_BOX32 + k * 32);
             const uint64_t bdl = umma_desc_sw128(da + (kb * 2 + 1) * B5_BOX32 + k * 32);
             const uint64_t akh = umma_desc_sw128(ka + kb * B5_BOX128 + k * 32);
             const uint64_t akl = umma_desc_sw128(ka + (2 + kb) * B5_BOX128 + k * 32);
             const uint64_t avh = umma_desc_sw128(va + kb * B5_BOX128 + k * 32);
             const uint64_t avl = umma_desc_sw128(va + (2 + kb) * B5_BOX128 + k * 32);
-            b5_mma_ss(sd, akh, bqh, B5_ID32, acc);    // S^T: K_hi . Q_hi
-            b5_mma_ss(pd, avh, bdh, B5_ID32, acc);    // dP^T: V_hi . dO_hi
-            b5_mma_ss(sd, akh, bql, B5_ID32, 1);      // S^T: K_hi . Q_lo
-            b5_mma_ss(pd, avh, bdl, B5_ID32, 1);      // dP^T: V_hi . dO_lo
-            b5_mma_ss(sd, akl, bqh, B5_ID32, 1);      // S^T: K_lo . Q_hi
-            b5_mma_ss(pd, avl, bdh, B5_ID32, 1);      // dP^T: V_lo . dO_hi
+            b5_mma_ss(tmem_base + 0, akh, bq, B5_ID64, acc);      // S^T: K_hi . [Q_hi ; Q_lo]
+            b5_mma_ss(tmem_base + 96, avh, bdh, B5_ID32, acc);    // dP^T: V_hi . dO_hi
+            b5_mma_ss(tmem_base + 64, akl, bq, B5_ID32, acc);     // S^T: K_lo . Q_hi
+            b5_mma_ss(tmem_base + 96, avh, bdl, B5_ID32, 1);      // dP^T: V_hi . dO_lo
+            b5_mma_ss(tmem_base + 96, avl, bdh, B5_ID32, 1);      // dP^T: V_lo . dO_hi
           }
         b5_commit(smem_u32(q_empty + st));
-        b5_commit(smem_u32(sp_full + st));
+        b5_commit(smem_u32(sp_full));
       };
       for (int tt = 0; tt <= n_tiles; ++tt) {
-        if (tt < n_tiles) issue_sdp(tt);   // one query tile ahead of the dV / dK MMAs below (second S/dP buffer)
+        if (tt < n_tiles) {
+          if (tt > 0) mbar_wait(smem_u32(sp_free), (uint32_t)((tt - 1) & 1));
+          issue_sdp(tt);
+        }
         if (tt == 0) continue;
         const int t = tt - 1;
         const uint32_t ph = (uint32_t)(t & 1);
@@ -568,7 +558,7 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
     const uint32_t tb = tmem_base + lb;
     const float4* lse4 = reinterpret_cast<const float4*>(lse2p + (long long)chunk * mp) + cq * 2;
     const float4* dl4 = reinterpret_cast<const float4*>(dlp + (long long)chunk * mp) + cq * 2;
-    float a[8], x[8];
+    float a[8], b[8], c[8], x[8];
     auto drain_one = [&](uint32_t col, float* out, float mul, bool first) {
       tmem_drain16<2>(tb + col + cq * 16, out + (base + gkey) * 64 + cq * 16, mul, first, gkey < m);
     };
@@ -586,19 +576,20 @@ __global__ void __launch_bounds__(B5_THREADS, 1)
       const float4 d0 = __ldg(dl4 + (t0 + t) * 8), d1 = __ldg(dl4 + (t0 + t) * 8 + 1);
       const float lse_c[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
       const float dl_c[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      const int buf = t & 1;
-      mbar_wait(smem_u32(sp_full + buf), (uint32_t)((t >> 1) & 1));
+      mbar_wait(smem_u32(sp_full), (uint32_t)(t & 1));
       tcgen05_fence_after();
-      b5_ld8(tb + buf * 64 + cq * 8, a);
-      b5_ld8(tb + buf * 64 + 32 + cq * 8, x);
+      b5_ld8(tb + cq * 8, a);
+      b5_ld8(tb + 32 + cq * 8, b);
+      b5_ld8(tb + 64 + cq * 8, c);
+      b5_ld8(tb + 96 + cq * 8, x);
       b5_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(smem_u32(sp_free + buf));
+      mbar_arrive(smem_u32(sp_free));
       const uint32_t hq = (uint32_t)((t0 + t) * 32 + cq * 8) * ATTN_DROP_CI;
       uint32_t ph_[8], pl_[8], sh_[8], sl_[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float p = b5_ex2(fmaf(a[e], sl2, -lse_c[e]));
+        const float p = b5_ex2(fmaf(a[e] + b[e] + c[e], sl2, -lse_c[e]));
         float pt = p, dp = x[e];
         if constexpr (DROP) {
           const bool keep = attn_drop_mix(hkey ^ (hq + (uint32_t)e * ATTN_DROP_CI)) >= drop_thr;

@@ -110,6 +110,17 @@ __device__ __forceinline__ void gm_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void gm_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]),
+      "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
+      "f"(v[31])
+      : "memory");
+}
+
 // Bernoulli source of the output dropout after linear_final (transformer.py:86): same counter hash as the attention mask,
 // keyed on (seed, row, column); forward and backward recompute it.
 __device__ __forceinline__ bool gm_keep(unsigned long long seed, uint32_t row, uint32_t col, uint32_t thr) {
@@ -283,25 +294,35 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         }
       }
     } else if constexpr (EPI == GM_EPI_LN) {
-      // full 256-wide row in this lane's TMEM columns: three passes (mean, variance, normalise); the residual row is read
-      // from global memory each pass (1 KB per thread, L1/L2 resident)
+      // full 256-wide row in this lane's TMEM columns.  Pass 1 forms v = resid + dropout(acc + bias) ONCE (residual row read with
+      // 128-bit loads, 1 KB per thread), accumulates the mean and writes v back into the accumulator columns (tcgen05.st);
+      // passes 2 and 3 (variance, normalise) read TMEM only.
       static_assert(EPI != GM_EPI_LN || BN == 256, "LayerNorm epilogue needs the whole row in one tile");
-      const float* xr = g.resid + (long long)(valid ? row : 0) * 256;
+      const float4* xr4 = reinterpret_cast<const float4*>(g.resid + (long long)(valid ? row : 0) * 256);
       const uint32_t thr = gm_drop_threshold(g.drop_p);
       const float inv_keep = g.drop_p > 0.f ? 1.f / (1.f - g.drop_p) : 1.f;
-      auto value = [&](const float (&v)[32], int c, int e) -> float {
-        float o = v[e] + __ldg(g.bias + c * 32 + e);
-        if (g.drop_p > 0.f) o = gm_keep(g.seed, (uint32_t)row, (uint32_t)(c * 32 + e), thr) ? o * inv_keep : 0.f;
-        return o + __ldg(xr + c * 32 + e);
-      };
       float sum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         float v[32];
         gm_ld32(tl + c * 32, v);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sum += value(v, c, e);
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c * 32) + e4);
+          const float4 x = __ldg(xr4 + c * 8 + e4);
+          const float bb[4] = {b.x, b.y, b.z, b.w}, xx[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e4 * 4 + j;
+            float o = v[e] + bb[j];
+            if (g.drop_p > 0.f) o = gm_keep(g.seed, (uint32_t)row, (uint32_t)(c * 32 + e), thr) ? o * inv_keep : 0.f;
+            v[e] = o + xx[j];
+            sum += v[e];
+          }
+        }
+        gm_st32(tl + c * 32, v);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       const float mean = sum * (1.f / 256.f);
       float sq = 0.f;
 #pragma unroll 1
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
         gm_ld32(tl + c * 32, v);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const float d = value(v, c, e) - mean;
+          const float d = v[e] - mean;
           sq = fmaf(d, d, sq);
         }
       }
@@ -324,10 +345,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           float4 xh, y;
-          xh.x = (value(v, c, e) - mean) * rs;
-          xh.y = (value(v, c, e + 1) - mean) * rs;
-          xh.z = (value(v, c, e + 2) - mean) * rs;
-          xh.w = (value(v, c, e + 3) - mean) * rs;
+          xh.x = (v[e] - mean) * rs;
+          xh.y = (v[e + 1] - mean) * rs;
+          xh.z = (v[e + 2] - mean) * rs;
+          xh.w = (v[e + 3] - mean) * rs;
           const float4 ga = __ldg(reinterpret_cast<const float4*>(g.gamma + c * 32 + e));
           const float4 be = __ldg(reinterpret_cast<const float4*>(g.beta + c * 32 + e));
           y.x = fmaf(xh.x, ga.x, be.x); y.y = fmaf(xh.y, ga.y, be.y); y.z = fmaf(xh.z, ga.z, be.z); y.w = fmaf(xh.w, ga.w, be.w);

@@ -9,6 +9,7 @@ struct PackArgs {
   const float* nchw[SCAN_MAX_LEVELS];
   long long tile_off[SCAN_MAX_LEVELS + 1];  // first tile index of each level
   int ptiles[SCAN_MAX_LEVELS];              // pixel tiles per image of the level
+  const float* rows_lv[SCAN_MAX_LEVELS];    // unpack only: per-level [N*H*W, C] inputs (null: one rows matrix in `rows_in`)
 };
 
 constexpr int TP = 64;  // pixels per tile
@@ -46,9 +47,11 @@ __global__ void __launch_bounds__(256) pack_kernel(Levels lv, PackArgs args, int
       if (p0 + pp < hw) rows_out[(row0 + pp) * channels + c0 + tx] = tile[tx][pp];
     }
   } else {
+    // separate per-level inputs (the gradients cuDNN hands back level by level): rebase so that the rows index still applies
+    const float* src = args.rows_lv[l] ? args.rows_lv[l] - lv.row_off[l] * channels : rows_in;
 #pragma unroll 4
     for (int pp = ty; pp < TP; pp += 4) {
-      tile[tx][pp] = (p0 + pp < hw) ? __ldg(rows_in + (row0 + pp) * channels + c0 + tx) : 0.f;
+      tile[tx][pp] = (p0 + pp < hw) ? __ldg(src + (row0 + pp) * channels + c0 + tx) : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
@@ -70,10 +73,12 @@ static int build_args(const Levels& lv, const void* const* ptrs, int channels, P
     if (l < lv.n_levels) {
       if (!ptrs[l]) return SCAN_EINVAL;
       a->nchw[l] = (const float*)ptrs[l];
+      a->rows_lv[l] = nullptr;
       a->ptiles[l] = (lv.h[l] * lv.w[l] + TP - 1) / TP;
       off += (long long)lv.n_images * a->ptiles[l] * (channels / TC);
     } else {
       a->nchw[l] = nullptr;
+      a->rows_lv[l] = nullptr;
       a->ptiles[l] = 1;
     }
   }
@@ -113,6 +118,26 @@ extern "C" int scan_unpack_rows(const scan_levels_t* lvh, const float* rows, int
     scan::pack_kernel<true, true><<<(unsigned)total, 256, 0, (cudaStream_t)stream>>>(lv, a, channels, nullptr, rows, nullptr);
   else
     scan::pack_kernel<true, false><<<(unsigned)total, 256, 0, (cudaStream_t)stream>>>(lv, a, channels, nullptr, rows, nullptr);
+  SCAN_LAUNCH_CHECK("unpack_kernel");
+  return SCAN_OK;
+}
+
+// the same with one NHWC-dense [N*H_l*W_l, C] input per level (HOST array of device pointers): one launch for all levels
+extern "C" int scan_unpack_levels(const scan_levels_t* lvh, const void* const* rows_levels_host, int32_t channels,
+                                  void* const* nchw_host, void* stream) {
+  scan::Levels lv;
+  int rc = scan::make_levels(lvh, &lv);
+  if (rc) return rc;
+  if (!nchw_host || !rows_levels_host) return SCAN_EINVAL;
+  scan::PackArgs a;
+  long long total;
+  rc = scan::build_args(lv, (const void* const*)nchw_host, channels, &a, &total);
+  if (rc) return rc;
+  for (int l = 0; l < lv.n_levels; ++l) {
+    if (!rows_levels_host[l]) return SCAN_EINVAL;
+    a.rows_lv[l] = (const float*)rows_levels_host[l];
+  }
+  scan::pack_kernel<true, false><<<(unsigned)total, 256, 0, (cudaStream_t)stream>>>(lv, a, channels, nullptr, nullptr, nullptr);
   SCAN_LAUNCH_CHECK("unpack_kernel");
   return SCAN_OK;
 }

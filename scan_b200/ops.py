@@ -156,16 +156,22 @@ class _PackLevels(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, *d_levels):
         geo = ctx.geo
-        grads = []
-        for l, (g, shape) in enumerate(zip(d_levels, ctx.shapes)):
-            if g is None:
-                grads.append(None)
-                continue
-            g_rows = _level_rows(nhwc_dense(g))
-            out = torch.empty(shape, device=g.device, dtype=torch.float32)
-            one = Geometry([geo.shapes[l]], [geo.strides[l]], geo.n_images)
-            call("scan_unpack_rows", one.ref(), _ptr(g_rows), C, _ptr_array([out]), 0, _stream())
-            grads.append(out)
+        if any(g is None for g in d_levels):     # a level without gradient: per-level launches for the others
+            grads = []
+            for l, (g, shape) in enumerate(zip(d_levels, ctx.shapes)):
+                if g is None:
+                    grads.append(None)
+                    continue
+                g_rows = _level_rows(nhwc_dense(g))
+                out = torch.empty(shape, device=g.device, dtype=torch.float32)
+                one = Geometry([geo.shapes[l]], [geo.strides[l]], geo.n_images)
+                call("scan_unpack_rows", one.ref(), _ptr(g_rows), C, _ptr_array([out]), 0, _stream())
+                grads.append(out)
+            return (None,) + tuple(grads)
+        # all five levels in ONE launch, straight from the per-level gradient tensors
+        g_rows = [_level_rows(nhwc_dense(g)) for g in d_levels]
+        grads = [torch.empty(shape, device=g_rows[0].device, dtype=torch.float32) for shape in ctx.shapes]
+        call("scan_unpack_levels", geo.ref(), _ptr_array(g_rows), C, _ptr_array(grads), _stream())
         return (None,) + tuple(grads)
 
 
@@ -901,7 +907,6 @@ class _LocalGCN(torch.autograd.Function):
             d_sub = dy if shortcut else torch.zeros_like(dy)
             gemm_nt(adj_t, dh1_t, mc, C, mc, mp4, mp32, out=d_sub, ldc=C, accumulate=True)
             call("scan_scatter_add_rows", _ptr(d_sub), _ptr(idx), mc, C, _ptr(d_points), _stream())
-        ctx.saved = None
         return d_points, d_w1, d_b1, d_w2, d_b2, None, None, None, None
 
 
