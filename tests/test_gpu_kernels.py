@@ -722,15 +722,20 @@ def test_local_gcn_matches_float64(m, k, shift, norm, act, shortcut):
     _close(got, want, 5e-5, "gcn out")
 
     def close_grad(a, b, what):
-        # a hidden unit whose pre-activation sits within fp32 rounding of zero takes the other ReLU branch than the float64
-        # reference (300 k units here: a handful do); through the nearly uniform adjacency every such flip moves the gradient of
-        # the whole class a little.  Same rule as tests/harness.py for ReLU paths: max-norm 5e-3, relative L2 3e-3 (measured
-        # 1.6e-3 with flips, < 2e-5 without)
+        # 2e-4 max-norm; or, like tests/harness.py for ReLU paths, sparse outliers: a hidden / output unit whose pre-activation sits
+        # within fp32 rounding of zero takes the other ReLU branch than the float64 reference (300 k units here: a handful do),
+        # which changes single weight-gradient entries by O(|dy| |h|) and, through the nearly uniform adjacency, moves the node
+        # gradients of the whole class a little: <= 2 % of the entries beyond the bound and relative L2 <= 3e-3
         a, b = a.detach().double().cpu(), b.detach().double().cpu()
         scale = max(float(b.abs().max()), 1e-30)
-        err = float((a - b).abs().max())
+        d = (a - b).abs()
+        err = float(d.max())
+        if err <= 2e-4 * scale + 1e-7:
+            return
+        frac = float((d > 2e-4 * scale).double().mean())
         l2 = float((a - b).norm() / max(float(b.norm()), 1e-30))
-        assert err <= 5e-3 * scale + 1e-7 and l2 <= 3e-3, "%s: max|d|=%.3e scale=%.3e relL2=%.3e" % (what, err, scale, l2)
+        assert l2 <= 3e-3 and (frac <= 0.02 or what == "d_nodes"), \
+            "%s: max|d|=%.3e scale=%.3e outliers=%.2f%% relL2=%.3e" % (what, err, scale, 100 * frac, l2)
 
     close_grad(nd.grad, nr.grad, "d_nodes")
     for name, a, b in (("w1", l1g.weight, l1d.weight), ("b1", l1g.bias, l1d.bias), ("w2", l2g.weight, l2d.weight), ("b2", l2g.bias, l2d.bias)):
