@@ -314,6 +314,7 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
     return {
         "pack_rows": ("hbm", 2 * R * 2 * row),                         # 2 passes: NCHW read + rows write
         "unpack_rows": ("hbm", 2 * R * 2 * row),
+        "unpack_levels": ("hbm", 2 * R * 2 * row),
         "gn_relu_fwd": ("hbm", 2 * 2 * R * 3 * row),                   # 2 passes x 2 layers: 2 reads + 1 write
         "gn_relu_bwd": ("hbm", 2 * 2 * R * 7 * row),                   # 6 reads + 1 write
         "add_relu_fwd": ("hbm", 2 * R * 3 * row),
@@ -456,8 +457,10 @@ def main():
     _lib.CALLS["launches"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_t0 = time.perf_counter()
     for _ in range(args.steps):
         step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host time to enqueue a step (incl. its two sync points)
     e1.record()
     barrier()
     if profiling:
@@ -614,7 +617,8 @@ def main():
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
                 "eager_gpu_baseline": eager, "tf32_peak_tflops_measured": tf32_peak, "hbm_peak_gbs": hbm_peak,
                 "kernel_ms_per_step": {k_: v["ms"] / args.steps for k_, v in kernel_ms.items()},
-                "source_nodes": m_src, "target_nodes": m_tgt, "dbscan_points_per_level": db_points}
+                "source_nodes": m_src, "target_nodes": m_tgt, "dbscan_points_per_level": db_points,
+                "host_enqueue_ms_per_step": host_enqueue_ms}
         if ms_light is not None:
             line["light_mode"] = {"value": images / (ms_light / 1e3), "unit": "images/s", "ms_per_step": ms_light / args.steps}
         print(json.dumps(line))

@@ -315,15 +315,19 @@ class GRAPHModule(nn.Module):
         return outs
 
     # ------------------------------------------------------------------ branches
-    def _forward_train_source(self, images, features, targets=None, return_maps=False):
+    def _forward_train_source(self, images, features, targets=None, return_maps=False, pre=None):
         geo = ops.Geometry.of(features, self.fpn_strides)
         dev = features[0].device
         rows = ops.join_rows(geo, features)
-        boxes, box_labels, box_count, g_max = ops.pad_targets(targets, dev)
-        labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
-        smp = ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels)
+        if pre is None:
+            boxes, box_labels, box_count, g_max = ops.pad_targets(targets, dev)
+            labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
+            pre = (labels, ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels))
+        labels, smp = pre
         self._record_nodes(geo, smp, labels=labels)
-        pos_points = ops.gather_rows(rows, smp.node_rows)
+        # `rows` continues as an alias handed through the gather: the conditional conv's d_rows then meets d_nodes inside ONE
+        # backward node (no zero-filled scatter target, no full-size gradient sum)
+        pos_points, rows = ops.gather_rows_through(rows, smp.node_rows)
         node_loss, packed, _, _ = self._forward_gcns(pos_points, smp.node_labels)
         proto_batch = self.update_prototype_ensemble(packed)
         weight, bias = self._split_kernel(self.get_conded_weight())
@@ -461,10 +465,20 @@ class GRAPHModule(nn.Module):
         if not features[0].is_cuda:
             raise RuntimeError("scan_b200.GRAPHModule runs on CUDA only (no CPU fallback)")
         geo = ops.Geometry.of(features, self.fpn_strides)
+        source = self.training and targets and mode == "source"
+        pre = None
+        if source:
+            # The FCOS assignment and the source node sampling depend on the targets and the level geometry only, not on the
+            # features: do them FIRST.  Their host read (the node count M sizes the graph tensors) then happens while the GPU
+            # is otherwise idle for ~50 us, and the rest of the source pass -- towers, graph aggregation, conditional conv --
+            # is enqueued without another synchronisation (before: the read sat after head_in and drained the queue).
+            boxes, box_labels, box_count, g_max = ops.pad_targets(targets, features[0].device)
+            labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
+            pre = (labels, ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels))
         features = self.head_in.forward_levels(geo, ops.pack_levels(geo, features))
         self.last = {"features_in": features} if self.record else {}
-        if self.training and targets and mode == "source":
-            return self._forward_train_source(images, features, targets, return_maps)
+        if source:
+            return self._forward_train_source(images, features, targets, return_maps, pre=pre)
         elif self.training and mode == "target" and forward_target:
             return self._forward_train_target(images, features, targets=None, return_maps=return_maps)
         return self._forward_inference(images, features, targets=None, return_maps=return_maps)

@@ -312,12 +312,23 @@ def pad_targets(targets, device):
     if min(counts) == 0:
         raise RuntimeError("an image without ground-truth boxes is unsupported (the reference's empty min, loss.py:333)")
     g = max(counts)
-    boxes = torch.zeros((n, g, 4), dtype=torch.float32)
-    labels = torch.zeros((n, g), dtype=torch.int64)
+    on_device = all(t.bbox.is_cuda for t in targets)
+    if on_device:
+        # targets already live on the GPU (the reference's trainer moves them there): pad with device copies, no D2H sync
+        boxes = torch.zeros((n, g, 4), device=device, dtype=torch.float32)
+        labels = torch.zeros((n, g), device=device, dtype=torch.int64)
+        for i, t in enumerate(targets):
+            boxes[i, :counts[i]] = t.bbox.detach().to(device, torch.float32)
+            labels[i, :counts[i]] = t.get_field("labels").detach().to(device, torch.int64)
+        cnt = torch.tensor(counts, dtype=torch.int32).pin_memory().to(device, non_blocking=True)
+        return boxes, labels, cnt, g
+    # host targets: stage through pinned memory (torch's caching host allocator) so that the three copies are truly asynchronous
+    boxes = torch.zeros((n, g, 4), dtype=torch.float32, pin_memory=True)
+    labels = torch.zeros((n, g), dtype=torch.int64, pin_memory=True)
     for i, t in enumerate(targets):
         boxes[i, :counts[i]] = t.bbox.detach().to("cpu", torch.float32)
         labels[i, :counts[i]] = t.get_field("labels").detach().to("cpu", torch.int64)
-    cnt = torch.tensor(counts, dtype=torch.int32)
+    cnt = torch.tensor(counts, dtype=torch.int32).pin_memory()
     return (boxes.to(device, non_blocking=True), labels.to(device, non_blocking=True),
             cnt.to(device, non_blocking=True), g)
 
@@ -427,6 +438,44 @@ class _GatherRows(torch.autograd.Function):
         call("scan_scatter_add_rows", _ptr(d_nodes), _ptr(node_rows), node_rows.numel(), d_nodes.shape[1],
              _ptr(d_rows), _stream())
         return d_rows, None
+
+
+class _GatherRowsThrough(torch.autograd.Function):
+    """gather_rows that also hands `rows` through: (nodes, rows_alias).  Consumers that come AFTER the gather in the forward
+    (the conditional convolution of the source branch) read rows_alias, so their dense d_rows arrives HERE together with
+    d_nodes and the node gradients are scatter-added straight into it -- instead of a zero-filled [R,256] scatter target plus
+    autograd's full-size gradient sum (one 183 MB fill and one 550 MB add per source pass at 8 images)."""
+
+    @staticmethod
+    def forward(ctx, rows, node_rows):
+        rows = rows.contiguous()
+        m = node_rows.numel()
+        out = torch.empty((m, rows.shape[1]), device=rows.device, dtype=torch.float32)
+        call("scan_gather_rows", _ptr(rows), _ptr(node_rows), m, rows.shape[1], _ptr(out), _stream())
+        ctx.save_for_backward(node_rows)
+        ctx.n_rows = rows.shape[0]
+        ctx.set_materialize_grads(False)
+        return out, rows
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_nodes, d_rows):
+        (node_rows,) = ctx.saved_tensors
+        if d_nodes is None:
+            return d_rows, None
+        d_nodes = d_nodes.contiguous()
+        if d_rows is None:
+            d_rows = torch.zeros((ctx.n_rows, d_nodes.shape[1]), device=d_nodes.device, dtype=torch.float32)
+        elif not d_rows.is_contiguous():
+            d_rows = d_rows.contiguous()
+        # d_rows is the fresh buffer the downstream backward just wrote (sole consumer of rows_alias): accumulate in place
+        call("scan_scatter_add_rows", _ptr(d_nodes), _ptr(node_rows), node_rows.numel(), d_nodes.shape[1], _ptr(d_rows), _stream())
+        return d_rows, None
+
+
+def gather_rows_through(rows, node_rows):
+    """Returns (nodes [M,C], rows_alias): use rows_alias for everything that reads `rows` after this call."""
+    return _GatherRowsThrough.apply(rows, node_rows)
 
 
 def gather_rows(rows, node_rows):

@@ -122,6 +122,25 @@ def test_benchmark_configuration_n8_every_element(bench_like):
     _report("bench_n8-twin")
 
 
+def test_benchmark_configuration_sim10k_n8():
+    """BASELINE.json configs[2] as `bench.py --config sim10k` runs it: Sim10k->Cityscapes (K = 2: single foreground class, no
+    transfer loss), 8 + 8 images at 800x1344, trained-like weights; DBSCAN over ~43 k single-class points at P3 (C oracle).
+    Integer results bit-exact, a strided sample of every float tensor at rtol 1e-3 (the c2f test above compares every element)."""
+    from scan_b200.condgraph import build_condgraph
+    oracle, prepared, counter = harness.prepare_bench_like(8, preset="sim10k", num_fg=1)
+    state = copy.deepcopy(oracle.state_dict())
+    want = harness.run_case("_bench_sim10k", oracle, "oracle", prepared=prepared)
+    m = build_condgraph(prepared[0], 256)
+    m.load_state_dict({k: v.clone() for k, v in state.items()})
+    if counter is not None:
+        m.counter_rnn.counter = counter
+    got = harness.run_case("_bench_sim10k", m, "product", device="cuda", prepared=prepared)
+    assert int(got["s1/dbscan_mask_l0"].sum()) > 0 and got["s0/node_rows"].shape[0] > 4000
+    bad = harness.compare(got, want, rtol=1e-3, device_run=True)
+    _report("bench_sim10k_n8")
+    assert not bad, "\n".join(bad[:25])
+
+
 def test_benchmark_flags_cudnn_tf32_error_is_reported(bench_like):
     """bench.py leaves torch's default cudnn.allow_tf32 = True for the tower convolutions (the reference's own GPU
     behaviour); parity runs force true fp32.  This run uses the BENCH flags: integer results must still be bit-exact
