@@ -346,14 +346,17 @@ class GRAPHModule(nn.Module):
         scan_transfer_* kernels; the class-presence mask stays on the device (the reference's boolean indexing synchronises)."""
         return ops.transfer_loss(self.transfer_cfg, tg_nodes, tg_labels, tg_prototype, self.prototype.detach())
 
-    def _sample_target(self, geo, rows, acts):
+    def _sample_target(self, geo, rows, acts, between=None):
+        """between: optional callable enqueued on the caller's stream after the per-level DBSCAN sequences have been forked
+        and before they are joined (the target pass puts head_out there: it does not depend on the sampling)."""
         dev = rows.device
         k = self.used_num_classes
         pos_mask = torch.empty((geo.R,), device=dev, dtype=torch.uint8)
         plabel = torch.empty((geo.R,), device=dev, dtype=torch.int64)
         infos = []
         if self.target_sampling == "dbscan":
-            infos = self._dbscan_levels(geo, rows, acts, pos_mask, plabel)
+            infos = self._dbscan_levels(geo, rows, acts, pos_mask, plabel, between=between)
+            between = None
         elif self.target_sampling == "score_threshold":
             # loss.py:479-481 (alternative sampler; torch ops, not a north-star kernel)
             for l, act in enumerate(acts):
@@ -363,6 +366,8 @@ class GRAPHModule(nn.Module):
                 plabel[a:b] = flat[:, 1:].argmax(dim=-1) + 1
         else:
             raise KeyError("unknown target labels!")   # 'mean_shift' / 'kmeans' samplers are out of scope
+        if between is not None:
+            between()
         smp = ops.sample_nodes(geo, 1, True, pos_mask=pos_mask, plabel=plabel)
         if infos:
             # ONE deferred status read for all levels (the sampling above already synchronised).  A level that selected more
@@ -384,50 +389,58 @@ class GRAPHModule(nn.Module):
                 self.last["dbscan_masks"] = [m.bool() for m in geo.split_rows(pos_mask)]
         return smp
 
-    def _dbscan_levels(self, geo, rows, acts, pos_mask, plabel):
+    def _dbscan_levels(self, geo, rows, acts, pos_mask, plabel, between=None):
         """scan_dbscan_level per FPN level into the shared pos_mask / plabel vectors; returns the per-level info records.
         The levels are independent (loss.py:464-518 loops over them), so each one is enqueued on its own side stream: the
         ~20 small launches of the coarse levels (n = 100 .. 3 000 points: pure launch latency) overlap the P3 level's
-        tensor-core distance kernel instead of queueing behind it.  Fork / join with events; no host synchronisation."""
+        tensor-core distance kernel instead of queueing behind it.  Fork / join with events; no host synchronisation.
+        `between()` is called between fork and join: with it every level (P3 too) goes to a side stream and the caller's
+        stream carries head_out meanwhile -- the sampling's host read then finds the GPU busy instead of draining it."""
         k = self.used_num_classes
         caps = [min(geo.n_images * (k - 1) * h * w, self.dbscan_cap) for h, w in geo.shapes]
         n_levels = len(geo.shapes)
         dev = rows.device
         rows_d = rows.detach()
         main = torch.cuda.current_stream(dev)
-        if self.dbscan_streams and n_levels > 1:
-            if len(self._side_streams) < n_levels - 1:
-                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_levels - 1)]
+        first_side = 0 if (between is not None and self.dbscan_streams) else 1     # level index from which side streams are used
+        if self.dbscan_streams:
+            if len(self._side_streams) < n_levels:
+                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n_levels)]
             fork = torch.cuda.Event()
             fork.record(main)
         infos = [None] * n_levels
         joins = []
-        # bench.py's per-entry timing: the levels overlap, so the fork -> join span on the main stream is what counts
+        # bench.py's per-entry timing: the levels overlap and the P3 level (the longest chain) bounds the fork -> join span:
+        # its own stream carries the two timing events
         timing = ops.TIMING["on"]
         if timing:
             ops.TIMING["on"] = False
-            span0 = torch.cuda.Event(enable_timing=True)
-            span0.record(main)
         for l in range(n_levels):
             a, b = geo.row_off[l], geo.row_off[l + 1]
-            side = self._side_streams[l - 1] if (self.dbscan_streams and l > 0) else None
+            side = self._side_streams[l] if (self.dbscan_streams and l >= first_side) else None
             if side is not None:
                 side.wait_event(fork)
             with torch.cuda.stream(side if side is not None else main):
+                if timing and l == 0:
+                    span0 = torch.cuda.Event(enable_timing=True)
+                    span0.record()
                 ws = ops.dbscan_workspace(caps[l], dev)      # allocated on (and recycled by) the stream that uses it
                 _, infos[l] = ops.dbscan_level(rows_d[a:b], acts[l].detach(), self.dbscan_thr, self.dbscan_eps, caps[l],
                                                pos_mask[a:b], plabel[a:b], ws)
+                if timing and l == 0:
+                    span1 = torch.cuda.Event(enable_timing=True)
+                    span1.record()
+                    ops.TIMERS.append(("scan_dbscan_levels_span", span0, span1))
                 if side is not None:
                     ev = torch.cuda.Event()
                     ev.record(side)
                     joins.append(ev)
+        if timing:
+            ops.TIMING["on"] = True
+        if between is not None:
+            between()
         for ev in joins:
             main.wait_event(ev)
-        if timing:
-            span1 = torch.cuda.Event(enable_timing=True)
-            span1.record(main)
-            ops.TIMERS.append(("scan_dbscan_levels_span", span0, span1))
-            ops.TIMING["on"] = True
         return infos
 
     def _forward_train_target(self, images, features, targets=None, return_maps=False):
@@ -435,9 +448,15 @@ class GRAPHModule(nn.Module):
         rows = ops.join_rows(geo, features)
         weight, bias = self._split_kernel(self.get_conded_weight())   # identical at every level (condgraph.py:507)
         acts, _, _ = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode())
-        smp = self._sample_target(geo, rows, acts)
+        # head_out needs the maps only: enqueue it between the fork and the join of the DBSCAN streams, ahead of the host read
+        held = {}
+
+        def head_out():
+            held["out"] = self.features_post_processing(features, acts)
+
+        smp = self._sample_target(geo, rows, acts, between=head_out)
         self._record_nodes(geo, smp)
-        out = self.features_post_processing(features, acts)
+        out = held["out"]
         if smp.n_nodes > 0 and (self.transfer_cfg[0] is not None or self.with_self_training):
             pos_points = ops.gather_rows(rows, smp.node_rows)
             # the class means feed the transfer losses WITH gradient in the reference (condgraph.py:398, 526)
