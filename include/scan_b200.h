@@ -48,6 +48,11 @@ const char* scan_strerror(int code);
 const char* scan_last_cuda_error(void);
 /* bytes of dynamic shared memory / SM count etc. are queried lazily; this forces it (returns 0 / SCAN_ECUDA) */
 int scan_init(int device);
+/* Copy a small (<= 4 MB, multiple of 4 bytes) buffer to the device with a kernel.  `src` may be PINNED HOST memory
+ * (device-accessible under unified addressing): per-call metadata such as the padded ground-truth boxes then bypasses the copy
+ * engine, where it would wait behind a training loop's input prefetch.  The host buffer must stay alive until the stream
+ * has passed this point (the Python shim keeps it referenced through a recorded event). */
+int scan_upload_small(const void* src, void* dst, int64_t bytes, void* stream);
 
 /* ---- geometry ------------------------------------------------------------------------------ */
 typedef struct {

@@ -1,6 +1,8 @@
 // ABI bookkeeping: version, error strings, device properties.
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace scan {
@@ -17,6 +19,12 @@ int sm_count() {
   int& slot = g_sm_count[dev & 63];
   if (slot == 0) slot = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   return slot;
+}
+// dst[i] = src[i] for a small buffer: `src` may be PINNED HOST memory (device-accessible under unified addressing), so tiny
+// per-call inputs (the padded GT boxes) reach the GPU through a kernel read instead of the copy engine, where they would queue
+// behind a training loop's multi-hundred-MB input prefetch
+__global__ void __launch_bounds__(256) upload_small_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long long n_words) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 }  // namespace scan
 
@@ -36,6 +44,17 @@ const char* scan_strerror(int code) {
 }
 
 const char* scan_last_cuda_error(void) { return scan::g_err; }
+
+int scan_upload_small(const void* pinned_host_or_device_src, void* dst, int64_t bytes, void* stream) {
+  if (bytes == 0) return SCAN_OK;
+  if (!pinned_host_or_device_src || !dst || bytes < 0 || (bytes & 3) || bytes > (1 << 22)) return SCAN_EINVAL;
+  if (((uintptr_t)pinned_host_or_device_src & 3) || ((uintptr_t)dst & 3)) return SCAN_EINVAL;
+  const long long n = bytes / 4;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 64);
+  scan::upload_small_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)pinned_host_or_device_src, (uint32_t*)dst, n);
+  SCAN_LAUNCH_CHECK("upload_small_kernel");
+  return SCAN_OK;
+}
 
 int scan_init(int device) {
   SCAN_CUDA_CHECK(cudaSetDevice(device));
