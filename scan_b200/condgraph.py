@@ -274,10 +274,18 @@ class GRAPHModule(nn.Module):
 
     # ------------------------------------------------------------------ paradigm update (condgraph.py:304-311, 558-617)
     @torch.no_grad()
-    def update_prototype_ensemble(self, packed):
+    def update_prototype_ensemble(self, packed, between=None):
+        """between: optional callable enqueued after the all-reduce has been STARTED and before its result is awaited (the
+        source pass puts the feature half of head_out there): the ranks are not in lockstep, so the collective is a
+        rendezvous, and independent work queued behind its start hides the wait for the slower rank."""
         if self.dist_group is not None:
             import torch.distributed as dist
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.dist_group)
+            work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.dist_group, async_op=True)
+            if between is not None:
+                between()
+            work.wait()        # stream-level wait on the collective's stream (no host block for NCCL)
+        elif between is not None:
+            between()
         shift = False
         if self.use_rnn:
             it = self.counter_rnn()
@@ -292,16 +300,23 @@ class GRAPHModule(nn.Module):
         return ops.proto_update(packed, self.prototype, slot, shift, self.cosine_update, 0.95)
 
     # ------------------------------------------------------------------ head_out (condgraph.py:379-384)
-    def features_post_processing(self, features, act_maps):
+    def head_out_feature_half(self, features):
+        """The 256 feature columns of head_out's first convolution (no dependence on the activation maps): can be enqueued early."""
+        conv = list(self.head_out.middle_tower)[0]
+        wf = conv.weight[:, :ops.C].contiguous(memory_format=torch.channels_last)
+        return [F.conv2d(ops.nhwc_dense(f), wf, None, padding=1) for f in features]
+
+    def features_post_processing(self, features, act_maps, us=None):
         """head_out(cat([features, act_maps], 1)) without materialising the concatenation: the first
-        convolution is split into its 256 feature columns (channels-last, NHWC kernels) and its K map columns."""
+        convolution is split into its 256 feature columns (channels-last, NHWC kernels) and its K map columns.
+        us: the feature half when the caller has already enqueued it (head_out_feature_half)."""
         if not self.with_concated_maps:
             return features
         layers = list(self.head_out.middle_tower)
         conv = layers[0]
-        wf = conv.weight[:, :ops.C].contiguous(memory_format=torch.channels_last)
         wa = conv.weight[:, ops.C:].contiguous(memory_format=torch.channels_last)
-        us = [F.conv2d(ops.nhwc_dense(f), wf, None, padding=1) for f in features]
+        if us is None:
+            us = self.head_out_feature_half(features)
         vs = [F.conv2d(a.contiguous(memory_format=torch.channels_last), wa, None, padding=1) for a in act_maps]
         if len(layers) == 2 and isinstance(layers[1], nn.ReLU):
             geo = ops.Geometry.of(features, self.fpn_strides)
@@ -329,7 +344,17 @@ class GRAPHModule(nn.Module):
         # backward node (no zero-filled scatter target, no full-size gradient sum)
         pos_points, rows = ops.gather_rows_through(rows, smp.node_rows)
         node_loss, packed, _, _ = self._forward_gcns(pos_points, smp.node_labels)
-        proto_batch = self.update_prototype_ensemble(packed)
+        # the feature half of head_out does not depend on the paradigm: it is enqueued between the start of the prototype
+        # all-reduce and the wait for its result (multi-GPU: hides the rendezvous with the slower rank)
+        held = {}
+        grad_on = torch.is_grad_enabled()
+
+        def early():
+            if self.with_concated_maps:
+                with torch.set_grad_enabled(grad_on):      # update_prototype_ensemble itself runs under no_grad
+                    held["us"] = self.head_out_feature_half(features)
+
+        proto_batch = self.update_prototype_ensemble(packed, between=early)
         weight, bias = self._split_kernel(self.get_conded_weight())
         if self.record:
             self.last["prototype_batch"], self.last["conded_weight"] = proto_batch, weight
@@ -338,7 +363,7 @@ class GRAPHModule(nn.Module):
                                              labels if with_loss else None, self.lamda2)
         if self.record:
             self.last["act_loss_flags"] = flags
-        out = self.features_post_processing(features, acts)
+        out = self.features_post_processing(features, acts, us=held.get("us"))
         return out, (node_loss, 0), act_loss, acts
 
     def get_transfer_loss(self, tg_prototype, tg_nodes, tg_labels):
