@@ -325,6 +325,20 @@ int scan_rows_gn_relu_fwd(const float* x, const float* gamma, const float* beta,
 int scan_rows_gn_relu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* stats, int32_t k,
                           int32_t channels, int32_t groups, float* d_x, float* d_gamma, float* d_beta, void* stream);
 
+/* ---- f4: FCOS post-processor (modeling/rpn/fcos/inference.py:54-194; boxlist_nms structures/boxlist_ops.py:9-31; IoU and
+ *      suppression rule csrc/cuda/nms.cu:13-67) on the probability maps of scan_ensemble_levels ----------------------------
+ * prob [N,C,H_l,W_l] probabilities, reg [N,4,H_l,W_l], ctr [N,1,H_l,W_l] logits (HOST arrays of device pointers), image_hw [N,2]
+ * int32 (h, w) on the device.  Per (image, level): candidates prob > pre_nms_thresh in (location, class) order, top
+ * pre_nms_top_n (<= 1024) by prob * sigmoid(ctr), decode + clip_to_image + min-size filter, score = sqrt(.); per image and class
+ * greedy NMS (IoU > nms_thresh, +1 pixel convention), then keep score >= the post_top_n-th largest.
+ * Outputs (capacity 8192 per image): out_box [N,8192,4], out_score [N,8192], out_label [N,8192] int32 (1-based), out_count [N]
+ * int32, ordered like the reference's result (class ascending, candidate order inside a class).  No host synchronisation. */
+int64_t scan_postprocess_workspace_bytes(int32_t n_images, int32_t n_levels);
+int scan_postprocess(const scan_levels_t* lv, const void* const* prob_host, const void* const* reg_host, const void* const* ctr_host,
+                     int32_t num_classes, const int32_t* image_hw, float pre_nms_thresh, int32_t pre_nms_top_n, float nms_thresh,
+                     int32_t post_top_n, float min_size, float* out_box, float* out_score, int32_t* out_label, int32_t* out_count,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- a14: transfer (graph-matching) losses of the target branch (condgraph.py:457-498, sim_matrix :35-43) ----------
  * prototype: the module's paradigm buffer [K, 256, P] (P == 1: [K, 256]); sr_proto = prototype.mean(-1) is taken in-kernel.
  * NODES: loss = KLDivLoss(reduction='mean')(softmax(nodes).log(), softmax(sr_proto[labels])); diff [M,256] = softmax(nodes) -

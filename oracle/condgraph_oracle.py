@@ -470,6 +470,96 @@ def ensemble(mode, cls_logits, act_maps):
 
 
 # --------------------------------------------------------------------------------------
+# f4: FCOS post-processor (inference.py:54-194)
+# --------------------------------------------------------------------------------------
+def nms_indices(boxes, scores, thresh):
+    """The reference's `_C.nms` on a GPU (csrc/cuda/nms.cu:13-129): greedy in score-descending order, a box is suppressed
+    when IoU (with the +1 pixel convention) is STRICTLY greater than `thresh`; returns the kept ORIGINAL indices in
+    ascending order (nms.cu:123-129 sorts them).  (The CPU twin csrc/cpu/nms_cpu.cpp uses >= and is not what inference runs.)"""
+    b = boxes.detach().cpu().double().numpy() if torch.is_tensor(boxes) else np.asarray(boxes, dtype=np.float64)
+    sc = scores.detach().cpu().numpy() if torch.is_tensor(scores) else np.asarray(scores)
+    n = b.shape[0]
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.int64)
+    b32 = b.astype(np.float32)
+    order = np.argsort(-sc, kind="stable")
+    area = (b32[:, 2] - b32[:, 0] + np.float32(1)) * (b32[:, 3] - b32[:, 1] + np.float32(1))
+    removed = np.zeros(n, dtype=bool)
+    keep = []
+    for oi, i in enumerate(order):
+        if removed[i]:
+            continue
+        keep.append(i)
+        rest = order[oi + 1:]
+        left = np.maximum(b32[i, 0], b32[rest, 0])
+        right = np.minimum(b32[i, 2], b32[rest, 2])
+        top = np.maximum(b32[i, 1], b32[rest, 1])
+        bottom = np.minimum(b32[i, 3], b32[rest, 3])
+        w = np.maximum(right - left + np.float32(1), np.float32(0))
+        h = np.maximum(bottom - top + np.float32(1), np.float32(0))
+        inter = w * h
+        iou = inter / (area[i] + area[rest] - inter)
+        removed[rest[iou > np.float32(thresh)]] = True
+    return torch.from_numpy(np.sort(np.asarray(keep, dtype=np.int64)))
+
+
+def fcos_postprocess(level_shapes, strides, probs, box_regression, centerness, image_sizes, pre_nms_thresh, pre_nms_top_n,
+                     nms_thresh, post_top_n, min_size=0):
+    """FCOSPostProcessor.forward (inference.py:54-194) on per-level class probability maps: forward_for_single_feature_map
+    (:54-121), cat over levels, select_over_all_levels (:148-194) with boxlist_nms (structures/boxlist_ops.py:9-31),
+    clip_to_image (structures/bounding_box.py:214-224) and remove_small_boxes (boxlist_ops.py:58-74).
+    Returns per image (boxes [D,4], scores [D], labels [D]).  When a level has more candidates than pre_nms_top_n the reference's
+    `topk(sorted=False)` leaves their order unspecified; this restatement keeps candidate order."""
+    n_img = probs[0].shape[0]
+    per_image = [[] for _ in range(n_img)]
+    for (h, w), s, p, r, c in zip(level_shapes, strides, probs, box_regression, centerness):
+        n, cdim = p.shape[0], p.shape[1]
+        xs, ys = level_locations(h, w, s)
+        box_cls = p.permute(0, 2, 3, 1).reshape(n, -1, cdim)
+        reg = r.permute(0, 2, 3, 1).reshape(n, -1, 4)
+        ctr = c.permute(0, 2, 3, 1).reshape(n, -1).sigmoid()
+        cand = box_cls > pre_nms_thresh
+        top_n = cand.reshape(n, -1).sum(1).clamp(max=pre_nms_top_n)
+        box_cls = box_cls * ctr[:, :, None]
+        for i in range(n):
+            nz = cand[i].nonzero()
+            loc, cls = nz[:, 0], nz[:, 1] + 1
+            sc = box_cls[i][cand[i]]
+            if int(cand[i].sum()) > int(top_n[i]):
+                _, idx = sc.topk(int(top_n[i]), sorted=False)
+                idx = idx.sort().values                        # candidate order (see docstring)
+                sc, loc, cls = sc[idx], loc[idx], cls[idx]
+            rg = reg[i][loc]
+            det = torch.stack([xs[loc] - rg[:, 0], ys[loc] - rg[:, 1], xs[loc] + rg[:, 2], ys[loc] + rg[:, 3]], dim=1)
+            ih, iw = image_sizes[i]
+            det[:, 0].clamp_(min=0, max=iw - 1)
+            det[:, 1].clamp_(min=0, max=ih - 1)
+            det[:, 2].clamp_(min=0, max=iw - 1)
+            det[:, 3].clamp_(min=0, max=ih - 1)
+            keep = ((det[:, 2] - det[:, 0] + 1 >= min_size) & (det[:, 3] - det[:, 1] + 1 >= min_size)).nonzero().squeeze(1)
+            per_image[i].append((det[keep], torch.sqrt(sc)[keep], cls[keep]))
+    out = []
+    for i in range(n_img):
+        boxes = torch.cat([t[0] for t in per_image[i]])
+        scores = torch.cat([t[1] for t in per_image[i]])
+        labels = torch.cat([t[2] for t in per_image[i]])
+        rb, rs, rl = [], [], []
+        for j in range(1, probs[0].shape[1] + 1):
+            inds = (labels == j).nonzero().view(-1)
+            keep = nms_indices(boxes[inds], scores[inds], nms_thresh)
+            rb.append(boxes[inds][keep])
+            rs.append(scores[inds][keep])
+            rl.append(torch.full((keep.numel(),), j, dtype=torch.int64))
+        boxes, scores, labels = torch.cat(rb), torch.cat(rs), torch.cat(rl)
+        if scores.numel() > post_top_n > 0:
+            thr, _ = torch.kthvalue(scores, scores.numel() - post_top_n + 1)
+            k = (scores >= thr.item()).nonzero().squeeze(1)
+            boxes, scores, labels = boxes[k], scores[k], labels[k]
+        out.append((boxes, scores, labels))
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # The module
 # --------------------------------------------------------------------------------------
 class _Counter(object):

@@ -1170,6 +1170,44 @@ def ensemble_levels(mode, cls_logits, acts):
     return outs
 
 
+def ensemble_levels_common(cls_logits):
+    """sigmoid of the classification logits of all levels in one launch (TEST.MODE 'common', inference.py:68)."""
+    cls = [c.contiguous() for c in cls_logits]
+    n, c = cls[0].shape[:2]
+    geo = Geometry([tuple(t.shape[-2:]) for t in cls], [1] * len(cls), n)
+    outs = [torch.empty_like(t) for t in cls]
+    call("scan_ensemble_levels", geo.ref(), _ptr_array(cls), None, c + 1, 0, _ptr_array(outs), _stream())
+    return outs
+
+
 def ensemble(mode, cls_logits, act):
     """One level (kept for callers that hold a single map)."""
     return ensemble_levels(mode, None if cls_logits is None else [cls_logits], [act])[0]
+
+
+# ----------------------------------------------------------------------------------------------------
+# f4: FCOS post-processor
+# ----------------------------------------------------------------------------------------------------
+PP_CAP = 8192
+
+
+def postprocess(geo, probs, box_regression, centerness, image_sizes, num_classes_fg, pre_nms_thresh, pre_nms_top_n, nms_thresh,
+                post_top_n, min_size=0.0):
+    """FCOSPostProcessor.forward (inference.py:54-194) on per-level class PROBABILITY maps [N,C,H,W].
+    Returns (boxes [N,8192,4], scores [N,8192], labels [N,8192] int32, counts [N] int32): device tensors, no host sync."""
+    probs = [p.contiguous() for p in probs]
+    regs = [r.contiguous() for r in box_regression]
+    ctrs = [c.contiguous() for c in centerness]
+    dev = probs[0].device
+    n = geo.n_images
+    hw = _upload_small(torch.tensor([[int(h), int(w)] for h, w in image_sizes], dtype=torch.int32), dev)
+    boxes = torch.empty((n, PP_CAP, 4), device=dev, dtype=torch.float32)
+    scores = torch.empty((n, PP_CAP), device=dev, dtype=torch.float32)
+    labels = torch.empty((n, PP_CAP), device=dev, dtype=torch.int32)
+    counts = torch.empty((n,), device=dev, dtype=torch.int32)
+    ws_bytes = _lib.lib().scan_postprocess_workspace_bytes(n, len(probs))
+    ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+    call("scan_postprocess", geo.ref(), _ptr_array(probs), _ptr_array(regs), _ptr_array(ctrs), num_classes_fg, _ptr(hw),
+         float(pre_nms_thresh), int(pre_nms_top_n), float(nms_thresh), int(post_top_n), float(min_size), _ptr(boxes), _ptr(scores),
+         _ptr(labels), _ptr(counts), _ptr(ws), ws_bytes, _stream())
+    return boxes, scores, labels, counts

@@ -794,3 +794,60 @@ def test_gather_rows_through_accumulates_into_the_downstream_gradient():
     n3, a3 = ops.gather_rows_through(rd3, idx.to(DEV).int())
     (a3 * c2.to(DEV)).sum().backward()
     _close(rd3.grad, c2, 1e-6, "d_rows (alias only)")
+
+
+@pytest.mark.parametrize("name", ["c8", "topk", "car_cap"])
+def test_fcos_postprocessor_matches_reference_golden(name, golden_dir):
+    """f4: candidate selection + top-k + decode + per-class NMS + detections cap (four launches) against vectors from the
+    unmodified reference FCOSPostProcessor; detections compared as sets (label exact, score / box 1e-5), and in the
+    reference's own order where that order is defined (no level above PRE_NMS_TOP_N)."""
+    import os
+    import postproc_case
+    from scan_b200 import fcos_hooks
+    gold = np.load(os.path.join(golden_dir, "postproc.npz"))
+    d = postproc_case.build(name)
+    pp = fcos_hooks.FCOSPostProcessor(pre_nms_thresh=d["thr"], pre_nms_top_n=d["top_n"], nms_thresh=d["nms_thr"],
+                                      fpn_post_nms_top_n=d["post_n"], min_size=0, num_classes=d["num_fg"] + 1, mode="precision",
+                                      fpn_strides=d["strides"])
+    res = pp(None, [p.to(DEV) for p in d["probs"]], [r.to(DEV) for r in d["regs"]], [c.to(DEV) for c in d["ctrs"]], d["sizes"])
+    assert len(res) == len(d["sizes"])
+    for i, bl in enumerate(res):
+        want = gold["%s/img%d" % (name, i)]
+        b, s, l = bl.bbox.cpu().numpy(), bl.get_field("scores").cpu().numpy(), bl.get_field("labels").cpu().numpy()
+        got = postproc_case.canonical(b, s, l)
+        assert got.shape == want.shape, "image %d: %d detections, reference %d" % (i, got.shape[0], want.shape[0])
+        assert np.array_equal(got[:, 0], want[:, 0])
+        assert np.abs(got[:, 1:] - want[:, 1:]).max() <= 1e-5 * max(1.0, np.abs(want[:, 1:]).max())
+        if name == "c8":
+            assert np.array_equal(l, gold["%s/img%d_labels_in_order" % (name, i)])
+            assert np.allclose(s, gold["%s/img%d_scores_in_order" % (name, i)], rtol=1e-6)
+    # 'common' mode: logits in, the sigmoid is applied inside (inference.py:68)
+    logits = [torch.logit(p.clamp(1e-6, 1 - 1e-6)).to(DEV) for p in d["probs"]]
+    pp.mode = "common"
+    res2 = pp(None, logits, [r.to(DEV) for r in d["regs"]], [c.to(DEV) for c in d["ctrs"]], d["sizes"])
+    assert [len(a) for a in res2] == [len(a) for a in res]
+
+
+def test_fcos_postprocessor_full_size_vs_oracle():
+    """Full Cityscapes geometry, 8 images, PRE_NMS_TOP_N = 1000 reached at P3: against the CPU oracle restatement."""
+    rs = np.random.RandomState(5)
+    shapes, strides, n, c = FULL, STRIDES, 8, 8
+    probs, regs, ctrs = [], [], []
+    for (h, w), s in zip(shapes, strides):
+        p = rs.uniform(0.0, 0.04, (n, c, h, w))
+        hot = rs.rand(n, c, h, w) < 0.02
+        p[hot] = rs.uniform(0.06, 0.99, int(hot.sum()))
+        probs.append(torch.from_numpy(p.astype(np.float32)))
+        regs.append(torch.from_numpy(np.exp(rs.standard_normal((n, 4, h, w)) * 0.5 + np.log(s * 2.0)).astype(np.float32)))
+        ctrs.append(torch.from_numpy(rs.standard_normal((n, 1, h, w)).astype(np.float32)))
+    sizes = [(800, 1344)] * n
+    import postproc_case
+    from scan_b200 import fcos_hooks
+    want = orc.fcos_postprocess(shapes, strides, probs, regs, ctrs, sizes, 0.05, 1000, 0.6, 100)
+    pp = fcos_hooks.FCOSPostProcessor(0.05, 1000, 0.6, 100, 0, c + 1, mode="light", fpn_strides=strides)
+    res = pp(None, [p.to(DEV) for p in probs], [r.to(DEV) for r in regs], [t.to(DEV) for t in ctrs], sizes)
+    for i, bl in enumerate(res):
+        g = postproc_case.canonical(bl.bbox.cpu().numpy(), bl.get_field("scores").cpu().numpy(), bl.get_field("labels").cpu().numpy())
+        w_ = postproc_case.canonical(want[i][0].numpy(), want[i][1].numpy(), want[i][2].numpy())
+        assert g.shape == w_.shape and np.array_equal(g[:, 0], w_[:, 0])
+        assert np.abs(g[:, 1:] - w_[:, 1:]).max() <= 1e-5 * max(1.0, np.abs(w_[:, 1:]).max())
