@@ -325,6 +325,31 @@ int scan_rows_gn_relu_fwd(const float* x, const float* gamma, const float* beta,
 int scan_rows_gn_relu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* stats, int32_t k,
                           int32_t channels, int32_t groups, float* d_x, float* d_gamma, float* d_beta, void* stream);
 
+/* ---- f1: the 3x3 convolutions of the GRAPHHead towers (condgraph.py:68-119; head_in :549, head_out :383) as a tcgen05 implicit
+ *      GEMM on the rows layout, all levels and images in one launch ---------------------------------------------------------
+ * scan_conv3x3_pack_weights: w[co][ci][ky][kx] (element strides s_*) -> packed[9][rows_pad][cols_pad] (rows padded to 256, columns
+ * to 32, zero filled; scan_conv3x3_packed_floats(rows, cols) floats).  transpose = 0: rows = co, cols = ci (forward);
+ * transpose = 1: rows = ci, cols = co and the taps rotated by 180 degrees (data gradient = the same convolution of dY).
+ * packed_lo (may be NULL) receives the 3xTF32 residual plane.  scan_tf32_residual: lo = rna_tf32(x - trunc_tf32(x)). */
+int64_t scan_conv3x3_packed_floats(int32_t rows, int32_t cols);
+int scan_conv3x3_pack_weights(const float* w, int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx, int32_t cout, int32_t cin,
+                              int32_t transpose, float* packed_hi, float* packed_lo, void* stream);
+int scan_tf32_residual(const float* x, int64_t n, float* lo, void* stream);
+/* y_rows [R, ldo] (first n_out columns) = act(conv3x3(x_rows [R, cin], padding 1) + bias + addend); cin % 32 == 0.  x_lo and
+ * packed_lo both non-NULL: 3xTF32 (fp32-accurate, the parity mode); both NULL: single-pass TF32 (what cuDNN runs under torch's
+ * default allow_tf32).  cta_group 2 = CTA pairs sharing the weight tile (the fast path), 1 = single CTAs. */
+int scan_conv3x3_rows(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* packed,
+                      const float* packed_lo, int32_t n_out, const float* bias, const float* addend, int32_t relu, float* y_rows,
+                      int32_t ldo, int32_t cta_group, void* stream);
+
+/* weight gradient of the same convolution: d_w[co][ci][ky][kx] (element strides s_*) = sum_p dy_rows[p, co] * x_rows[p + off, ci];
+ * cin and cout multiples of 256; both operands are read in place (MN-major tcgen05 operands, no transposed copy); x_lo / dy_lo
+ * both non-NULL: 3xTF32.  Deterministic (per-CTA-pair partial tiles summed in a fixed order); workspace from the _bytes query. */
+int64_t scan_conv3x3_wgrad_workspace_bytes(const scan_levels_t* lv, int32_t cin, int32_t cout, int32_t precise);
+int scan_conv3x3_wgrad(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* dy_rows,
+                       const float* dy_lo, int32_t cout, float* d_w, int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- f4: FCOS post-processor (modeling/rpn/fcos/inference.py:54-194; boxlist_nms structures/boxlist_ops.py:9-31; IoU and
  *      suppression rule csrc/cuda/nms.cu:13-67) on the probability maps of scan_ensemble_levels ----------------------------
  * prob [N,C,H_l,W_l] probabilities, reg [N,4,H_l,W_l], ctr [N,1,H_l,W_l] logits (HOST arrays of device pointers), image_hw [N,2]

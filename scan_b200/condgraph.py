@@ -20,6 +20,8 @@ behind the C ABI of include/scan_b200.h:
 
 There is no CPU path: features must be CUDA tensors and libscan_b200.so must be loadable.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -94,7 +96,7 @@ class GRAPHHead(nn.Module):
                 gn = layers[i]
                 i += 2
                 # bias-free convolution: the GroupNorm kernel adds the bias and returns its gradient as a by-product
-                outs = [F.conv2d(ops.nhwc_dense(x), w, None, padding=1) for x in h]
+                outs = _tower_conv(geo, conv.weight, w, h)
                 h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs, conv_bias=conv.bias)
             else:   # IN / BN variants and the norm-free head_out: torch modules (not used by the shipped configs' head_in)
                 outs = [F.conv2d(ops.nhwc_dense(x), w, conv.bias, padding=1) for x in h]
@@ -103,6 +105,20 @@ class GRAPHHead(nn.Module):
                     i += 1
                 h = outs
         return h
+
+
+TOWERS = {"impl": os.environ.get("SCAN_B200_TOWERS", "scan")}     # "scan" (csrc/tower.cu) | "cudnn"
+
+
+def _tower_conv(geo, weight, weight_cl, levels):
+    """Bias-free 3x3 tower convolution of all levels: the tcgen05 implicit GEMM of csrc/tower.cu (f1) for the 256 -> 256 layers of
+    every shipped config; other widths, and SCAN_B200_TOWERS=cudnn (the A/B switch of tools/ and bench.py), go to cuDNN's
+    channels-last kernels."""
+    if TOWERS["impl"] == "scan" and weight.shape[0] % 256 == 0 and weight.shape[1] % 256 == 0:
+        return ops.conv3x3_levels(geo, weight, list(levels))
+    if weight_cl is None:
+        weight_cl = weight.contiguous(memory_format=torch.channels_last)
+    return [F.conv2d(ops.nhwc_dense(x), weight_cl, None, padding=1) for x in levels]
 
 
 class MultiHeadAttention(nn.Module):
@@ -303,8 +319,9 @@ class GRAPHModule(nn.Module):
     def head_out_feature_half(self, features):
         """The 256 feature columns of head_out's first convolution (no dependence on the activation maps): can be enqueued early."""
         conv = list(self.head_out.middle_tower)[0]
-        wf = conv.weight[:, :ops.C].contiguous(memory_format=torch.channels_last)
-        return [F.conv2d(ops.nhwc_dense(f), wf, None, padding=1) for f in features]
+        wf = conv.weight[:, :ops.C]
+        geo = ops.Geometry.of(features, self.fpn_strides)
+        return _tower_conv(geo, wf, None, features)
 
     def features_post_processing(self, features, act_maps, us=None):
         """head_out(cat([features, act_maps], 1)) without materialising the concatenation: the first

@@ -257,6 +257,122 @@ def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None):
     return list(_GnReluLevels.apply(geo, gamma, beta, conv_bias, eps, *xs))
 
 
+# ----------------------------------------------------------------------------------------------------
+# f1: tower convolutions as a tcgen05 implicit GEMM on the rows layout (csrc/tower.cu)
+# ----------------------------------------------------------------------------------------------------
+CONV = {"cta_group": 2, "precise": False}     # precise = 3xTF32 (fp32-accurate; the parity runs), else single-pass TF32
+
+
+def conv3x3_pack(weight, transpose, precise):
+    """[Cout,Cin,3,3] weight (any strides) -> (packed_hi, packed_lo | None) for scan_conv3x3_rows."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    rows, cols = (cin, cout) if transpose else (cout, cin)
+    n = _lib.lib().scan_conv3x3_packed_floats(rows, cols)
+    hi = torch.empty((n,), device=weight.device, dtype=torch.float32)
+    lo = torch.empty_like(hi) if precise else None
+    s = weight.stride()
+    call("scan_conv3x3_pack_weights", _ptr(weight), s[0], s[1], s[2], s[3], cout, cin, int(bool(transpose)), _ptr(hi), _ptr(lo),
+         _stream())
+    return hi, lo
+
+
+def tf32_residual(x):
+    lo = torch.empty_like(x)
+    call("scan_tf32_residual", _ptr(x), x.numel(), _ptr(lo), _stream())
+    return lo
+
+
+def conv3x3_rows_raw(geo, x_rows, packed, n_out, bias=None, addend=None, relu=False, x_lo=None, packed_lo=None, out=None, cta_group=None):
+    """out[R, n_out] = act(conv3x3(x_rows[R, cin]) + bias + addend) with pre-packed weights (no autograd)."""
+    if not x_rows.is_cuda or x_rows.dtype != torch.float32 or not x_rows.is_contiguous() or x_rows.shape[0] != geo.R:
+        raise RuntimeError("conv3x3_rows expects a contiguous CUDA fp32 [R, Cin] rows matrix (no CPU fallback)")
+    if out is None:
+        out = torch.empty((geo.R, n_out), device=x_rows.device, dtype=torch.float32)
+    call("scan_conv3x3_rows", geo.ref(), _ptr(x_rows), _ptr(x_lo), x_rows.shape[1], _ptr(packed), _ptr(packed_lo), n_out, _ptr(bias),
+         _ptr(addend), int(bool(relu)), _ptr(out), out.shape[1], CONV["cta_group"] if cta_group is None else cta_group, _stream())
+    return out
+
+
+def conv3x3_wgrad_raw(geo, x_rows, dy_rows, x_lo=None, dy_lo=None, out=None):
+    """d_w [Cout,Cin,3,3] of the tower convolution from the rows matrices (no autograd)."""
+    cin, cout = x_rows.shape[1], dy_rows.shape[1]
+    if out is None:
+        out = torch.empty((cout, cin, 3, 3), device=x_rows.device, dtype=torch.float32)
+    nbytes = _lib.lib().scan_conv3x3_wgrad_workspace_bytes(geo.ref(), cin, cout, int(x_lo is not None))
+    if nbytes < 0:
+        raise RuntimeError("conv3x3_wgrad: channel counts must be multiples of 256")
+    ws = torch.empty((nbytes,), device=x_rows.device, dtype=torch.uint8)
+    s = out.stride()
+    call("scan_conv3x3_wgrad", geo.ref(), _ptr(x_rows), _ptr(x_lo), cin, _ptr(dy_rows), _ptr(dy_lo), cout, _ptr(out), s[0], s[1], s[2],
+         s[3], _ptr(ws), nbytes, _stream())
+    return out
+
+
+def _rows_of_levels(geo, levels):
+    """Per-level [N,C,H,W] tensors -> [R,C] rows; zero-copy when they are adjacent channels_last views of one buffer."""
+    base = levels[0]
+    c = base.shape[1]
+    for l, t in enumerate(levels):
+        if (not t.permute(0, 2, 3, 1).is_contiguous() or t.untyped_storage().data_ptr() != base.untyped_storage().data_ptr()
+                or t.data_ptr() != base.data_ptr() + geo.row_off[l] * c * 4):
+            return torch.cat([_level_rows(nhwc_dense(t)) for t in levels])
+    return torch.as_strided(base.detach(), (geo.R, c), (c, 1), base.storage_offset())
+
+
+def _level_views_c(geo, rows):
+    c = rows.shape[1]
+    return [rows[geo.row_off[l]:geo.row_off[l + 1]].view(geo.n_images, h, w, c).permute(0, 3, 1, 2) for l, (h, w) in enumerate(geo.shapes)]
+
+
+class _Conv3x3Levels(torch.autograd.Function):
+    """The bias-free 3x3 convolution (padding 1) of a tower layer over all levels: ONE scan_conv3x3_rows launch forward, one for
+    the data gradient (the same kernel on dY with the rotated, transposed weights) and scan_conv3x3_wgrad for the weights.
+    Inputs / outputs are per-level channels_last views of rows buffers."""
+
+    @staticmethod
+    def forward(ctx, geo, weight, *levels):
+        precise = CONV["precise"]
+        x_rows = _rows_of_levels(geo, levels)
+        hi, lo = conv3x3_pack(weight, False, precise)
+        x_lo = tf32_residual(x_rows) if precise else None
+        y_rows = conv3x3_rows_raw(geo, x_rows, hi, weight.shape[0], x_lo=x_lo, packed_lo=lo)
+        ctx.geo, ctx.precise = geo, precise
+        ctx.save_for_backward(x_rows, weight)
+        ctx.x_lo = x_lo
+        return tuple(_level_views_c(geo, y_rows))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *d_levels):
+        geo, precise = ctx.geo, ctx.precise
+        x_rows, weight = ctx.saved_tensors
+        d_levels = [g if g is not None else torch.zeros((geo.n_images, weight.shape[0], h, w), device=x_rows.device).contiguous(
+            memory_format=torch.channels_last) for g, (h, w) in zip(d_levels, geo.shapes)]
+        dy_rows = _rows_of_levels(geo, d_levels)
+        dy_lo = tf32_residual(dy_rows) if precise else None
+        d_w = None
+        if ctx.needs_input_grad[1]:
+            x_lo = ctx.x_lo if precise else None
+            d_w = torch.empty_like(weight)
+            conv3x3_wgrad_raw(geo, x_rows, dy_rows, x_lo=x_lo, dy_lo=dy_lo, out=d_w)
+        d_x = (None,) * len(d_levels)
+        if any(ctx.needs_input_grad[2:]):
+            hi, lo = conv3x3_pack(weight, True, precise)
+            dx_rows = conv3x3_rows_raw(geo, dy_rows, hi, weight.shape[1], x_lo=dy_lo, packed_lo=lo)
+            d_x = tuple(_level_views_c(geo, dx_rows))
+        return (None, d_w) + d_x
+
+
+def conv3x3_levels(geo, weight, levels):
+    """Tower convolution (no bias) of per-level [N,Cin,H,W] CUDA tensors -> per-level channels_last views of one rows buffer."""
+    if weight.shape[2:] != (3, 3) or weight.shape[0] % 256 or weight.shape[1] % 256:
+        raise RuntimeError("conv3x3_levels is built for 3x3 kernels with channel counts in multiples of 256")
+    for x in levels:
+        if not x.is_cuda or x.dtype != torch.float32 or x.shape[1] != weight.shape[1]:
+            raise RuntimeError("conv3x3_levels expects CUDA fp32 [N,%d,H,W] tensors (no CPU fallback)" % weight.shape[1])
+    return list(_Conv3x3Levels.apply(geo, weight, *levels))
+
+
 class _AddReluLevels(torch.autograd.Function):
     """relu(u + v + bias) per level (head_out without the concat), all levels per launch, output = views of one rows buffer."""
 

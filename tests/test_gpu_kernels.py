@@ -851,3 +851,65 @@ def test_fcos_postprocessor_full_size_vs_oracle():
         w_ = postproc_case.canonical(want[i][0].numpy(), want[i][1].numpy(), want[i][2].numpy())
         assert g.shape == w_.shape and np.array_equal(g[:, 0], w_[:, 0])
         assert np.abs(g[:, 1:] - w_[:, 1:]).max() <= 1e-5 * max(1.0, np.abs(w_[:, 1:]).max())
+
+
+def _conv_levels_ref(geo, x_rows, weight, bias):
+    outs = []
+    for l, (h, w) in enumerate(geo.shapes):
+        x = x_rows[geo.row_off[l]:geo.row_off[l + 1]].view(geo.n_images, h, w, -1).permute(0, 3, 1, 2).double()
+        y = torch.nn.functional.conv2d(x, weight.double(), None if bias is None else bias.double(), padding=1)
+        outs.append(y.permute(0, 2, 3, 1).reshape(-1, weight.shape[0]))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("shapes,n", [([(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 3), ([(100, 168), (50, 84)], 1), ([(9, 5)], 1)])
+def test_conv3x3_rows_matches_fp64_conv(shapes, n, cta_group):
+    """f1 forward / data-gradient kernel: 3xTF32 mode against an fp64 convolution at fp32 accuracy, single-pass TF32 mode at the
+    TF32 bound (inputs rounded to 11 bits: 2^-11 relative per product, 2304 products)."""
+    torch.manual_seed(3)
+    geo = ops.Geometry(shapes, STRIDES[:len(shapes)], n)
+    x = torch.randn(geo.R, 256, device=DEV)
+    w = torch.randn(256, 256, 3, 3, device=DEV) * 0.02
+    b = torch.randn(256, device=DEV)
+    ref = _conv_levels_ref(geo, x, w, b)
+    scale = float(ref.abs().max())
+    for transpose in (False, True):
+        wt = w if not transpose else w.flip(2, 3).transpose(0, 1)      # what the packed 'data gradient' weights compute
+        r = ref if not transpose else _conv_levels_ref(geo, x, wt.contiguous(), b)
+        hi, lo = ops.conv3x3_pack(w, transpose, True)
+        y3 = ops.conv3x3_rows_raw(geo, x, hi, 256, bias=b, x_lo=ops.tf32_residual(x), packed_lo=lo, cta_group=cta_group)
+        assert float((y3.double() - r).abs().max()) <= 5e-5 * scale, "3xTF32 %s" % transpose   # 864-step truncating accumulation
+        y1 = ops.conv3x3_rows_raw(geo, x, hi, 256, bias=b, cta_group=cta_group)
+        assert float((y1.double() - r).abs().max()) <= 2e-3 * scale, "TF32 %s" % transpose
+    # epilogue: addend + ReLU
+    add = torch.randn(geo.R, 256, device=DEV)
+    hi, lo = ops.conv3x3_pack(w, False, True)
+    y = ops.conv3x3_rows_raw(geo, x, hi, 256, bias=b, addend=add, relu=True, x_lo=ops.tf32_residual(x), packed_lo=lo, cta_group=cta_group)
+    assert float((y.double() - torch.relu(ref + add.double())).abs().max()) <= 5e-5 * scale
+
+
+@pytest.mark.parametrize("shapes,n", [([(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 3), ([(100, 168), (50, 84)], 2), ([(9, 5)], 1)])
+def test_conv3x3_wgrad_matches_fp64(shapes, n):
+    """f1 weight-gradient kernel (MN-major operands, CTA pairs, deterministic split over pixel segments) against the fp64
+    gradient of torch's convolution: 3xTF32 at fp32 accuracy, single-pass TF32 at the TF32 bound; bitwise repeatable."""
+    torch.manual_seed(4)
+    geo = ops.Geometry(shapes, STRIDES[:len(shapes)], n)
+    x = torch.randn(geo.R, 256, device=DEV)
+    dy = torch.randn(geo.R, 256, device=DEV)
+    w = torch.zeros(256, 256, 3, 3, device=DEV, dtype=torch.float64, requires_grad=True)
+    ys = []
+    for l, (h, wd) in enumerate(geo.shapes):
+        xl = x[geo.row_off[l]:geo.row_off[l + 1]].view(n, h, wd, 256).permute(0, 3, 1, 2).double()
+        ys.append(torch.nn.functional.conv2d(xl, w, None, padding=1).permute(0, 2, 3, 1).reshape(-1, 256))
+    (ref,) = torch.autograd.grad(torch.cat(ys), [w], dy.double())
+    scale = float(ref.abs().max())
+    g3 = ops.conv3x3_wgrad_raw(geo, x, dy, x_lo=ops.tf32_residual(x), dy_lo=ops.tf32_residual(dy))
+    assert float((g3.double() - ref).abs().max()) <= 2e-5 * scale
+    g1 = ops.conv3x3_wgrad_raw(geo, x, dy)
+    assert float((g1.double() - ref).abs().max()) <= 2e-3 * scale
+    assert torch.equal(g1, ops.conv3x3_wgrad_raw(geo, x, dy))
+    # a channels-last gradient tensor (what torch hands out for channels-last weights)
+    out = torch.empty(256, 256, 3, 3, device=DEV).contiguous(memory_format=torch.channels_last)
+    ops.conv3x3_wgrad_raw(geo, x, dy, out=out)
+    assert torch.equal(out, g1)
