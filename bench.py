@@ -444,6 +444,11 @@ def main():
     # ---------------- device-resident timing ----------------
     for _ in range(args.warmup):
         step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
+    # training-loop hygiene: the long-lived objects (module, buffers, torch itself) leave the cyclic collector's young
+    # generations, so a full collection (~100 ms with torch loaded) cannot land inside a step
+    import gc
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -452,22 +457,39 @@ def main():
     if profiling:
         torch.cuda.profiler.start()
     ops.TIMERS.clear()
-    ops.TIMING["on"] = not profiling
+    ops.TIMING["on"] = False
     _lib.CALLS["n"] = 0
     _lib.CALLS["launches"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     host_t0 = time.perf_counter()
+    host_prof = None
+    if os.environ.get("SCAN_HOST_PROFILE") == "1":      # diagnostics: where the host spends a step (never set for a reported number)
+        import cProfile
+        host_prof = cProfile.Profile()
+        host_prof.enable()
     for _ in range(args.steps):
         step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
-    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host time to enqueue a step (incl. its two sync points)
+    if host_prof is not None:
+        import pstats
+        host_prof.disable()
+        pstats.Stats(host_prof, stream=sys.stderr).sort_stats("tottime").print_stats(45)
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host time to enqueue a step (incl. its sync points)
     e1.record()
     barrier()
     if profiling:
         torch.cuda.profiler.stop()
-    ops.TIMING["on"] = False
     launches = _lib.CALLS["launches"]
     ms = e0.elapsed_time(e1)
+    # per-entry-point device times: the same steps once more with a CUDA event pair around every C-ABI call.  Kept OUT of the
+    # timed loop: ~540 event records per step cost the host about 2 ms, and the step is sensitive to host time
+    kernel_steps = args.steps if args.steps < 10 else 10
+    if not profiling:
+        ops.TIMERS.clear()
+        ops.TIMING["on"] = True
+        for _ in range(kernel_steps):
+            step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
+        ops.TIMING["on"] = False
     kernel_ms = ops.timers_summary()
     ms_light = None
     if is_eval:   # the second TEST.MODE of configs[3]
@@ -521,6 +543,17 @@ def main():
                 evs.append(ev)
         return evs
 
+    # the staging copy alone (no compute): the floor the end-to-end step cannot go below on this host / PCIe link
+    h2d_alone_ms = None
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(copy_stream):
+            c0.record(copy_stream)
+        stage(0)
+        with torch.cuda.stream(copy_stream):
+            c1.record(copy_stream)
+        c1.synchronize()
+        h2d_alone_ms = c0.elapsed_time(c1)
     # two untimed end-to-end steps: the e2e path has first-use costs of its own (copy stream, first touch of the staging
     # buffers; measured 60-110 ms on the first step), which a training loop pays once
     for _ in range(2):
@@ -531,7 +564,13 @@ def main():
     barrier()
     consumed = [None, None]
     e2e_marks = [time.perf_counter()]
+    # result read-back: every step's losses are copied to pinned host memory inside the timed region and READ one step later
+    # (after the next step has been enqueued), the way a training loop logs its loss without draining the queue every step
+    pinned_res = [None, None]
+    pending = None
+    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     f0.record()
+    step_evs[0].record()
     ready = stage(0)
     for i in range(args.steps):
         b_ = i & 1
@@ -541,12 +580,26 @@ def main():
         res = step_dev([x.detach() for x in bufs[b_][0]], None if is_eval else [x.detach() for x in bufs[b_][1]], ready=cur)
         consumed[b_] = torch.cuda.Event()
         consumed[b_].record(main_stream)
-        host = [r.cpu() for r in res if r is not None]
-        d2h = sum(h.numel() * 4 for h in host)
+        res = [r for r in res if r is not None]
+        if pinned_res[b_] is None:
+            pinned_res[b_] = [torch.empty(r.shape, dtype=r.dtype, pin_memory=True) for r in res]
+        for h_, r in zip(pinned_res[b_], res):
+            h_.copy_(r, non_blocking=True)
+        ev_res = torch.cuda.Event()
+        ev_res.record(main_stream)
+        step_evs[i + 1].record()
+        if pending is not None:
+            pending[0].synchronize()
+            host = [float(h_.sum()) for h_ in pending[1]]          # the previous step's losses, on the host
+        pending = (ev_res, pinned_res[b_])
+        d2h = sum(h_.numel() * 4 for h_ in pinned_res[b_])
         e2e_marks.append(time.perf_counter())
+    pending[0].synchronize()
+    host = [float(h_.sum()) for h_ in pending[1]]
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    e2e_dev_ms = [round(a_.elapsed_time(b2), 2) for a_, b2 in zip(step_evs[:-1], step_evs[1:])]
     sampler.stop_flag = True
     h2d = sum(f.numel() * 4 for hs in host_sets for f in hs)
 
@@ -565,7 +618,7 @@ def main():
         if not is_eval:
             work = work_model(n, k_cls, m_src, m_tgt, db_points, module.transfer_cfg[0] is not None or module.with_self_training)
             for name, (bound, amount) in work.items():
-                t_ms = kernel_ms.get(name, {"ms": 0.0})["ms"] / args.steps
+                t_ms = kernel_ms.get(name, {"ms": 0.0})["ms"] / kernel_steps
                 if t_ms <= 0:
                     continue
                 if bound == "hbm":
@@ -613,10 +666,13 @@ def main():
                                                  + ("; process bound to the GPU's NUMA node %s before pinning" % numa_node if numa_node is not None else ""),
                            "l2_note": "inputs %d MB per pass exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "host_ms_per_step": [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(e2e_marks[:-1], e2e_marks[1:])]},
+                        "host_ms_per_step": [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(e2e_marks[:-1], e2e_marks[1:])],
+                        "device_ms_per_step": e2e_dev_ms,
+                        "h2d_alone_ms_per_step": h2d_alone_ms,
+                        "result_read": "pinned, non-blocking, consumed one step later (every step's result is read inside the timed region)"},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
                 "eager_gpu_baseline": eager, "tf32_peak_tflops_measured": tf32_peak, "hbm_peak_gbs": hbm_peak,
-                "kernel_ms_per_step": {k_: v["ms"] / args.steps for k_, v in kernel_ms.items()},
+                "kernel_ms_per_step": {k_: v["ms"] / kernel_steps for k_, v in kernel_ms.items()},
                 "source_nodes": m_src, "target_nodes": m_tgt, "dbscan_points_per_level": db_points,
                 "host_enqueue_ms_per_step": host_enqueue_ms}
         if ms_light is not None:

@@ -533,9 +533,20 @@ class GRAPHModule(nn.Module):
             # features: do them FIRST.  Their host read (the node count M sizes the graph tensors) then happens while the GPU
             # is otherwise idle for ~50 us, and the rest of the source pass -- towers, graph aggregation, conditional conv --
             # is enqueued without another synchronisation (before: the read sat after head_in and drained the queue).
-            boxes, box_labels, box_count, g_max = ops.pad_targets(targets, features[0].device)
-            labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
-            pre = (labels, ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels))
+            # They run on a side stream: the read then waits for these three small launches only, NOT for whatever the main
+            # stream still holds (the previous step's backward), so the host keeps enqueueing ahead of the GPU across steps.
+            dev = features[0].device
+            main, side = torch.cuda.current_stream(dev), self._pre_stream(dev)
+            if any(t.bbox.is_cuda for t in targets):
+                side.wait_stream(main)          # device-resident targets may have been produced on the main stream
+            with torch.cuda.stream(side):
+                boxes, box_labels, box_count, g_max = ops.pad_targets(targets, dev)
+                labels = ops.fcos_assign(geo, boxes, box_labels, box_count, g_max)
+                smp = ops.sample_nodes(geo, 0, self.with_bg_proto, labels=labels)
+            main.wait_stream(side)
+            for t in (boxes, box_labels, box_count, labels, smp.node_rows, smp.node_labels):
+                t.record_stream(main)           # allocated on the side stream, consumed on the main one
+            pre = (labels, smp)
         features = self.head_in.forward_levels(geo, ops.pack_levels(geo, features))
         self.last = {"features_in": features} if self.record else {}
         if source:
@@ -543,6 +554,13 @@ class GRAPHModule(nn.Module):
         elif self.training and mode == "target" and forward_target:
             return self._forward_train_target(images, features, targets=None, return_maps=return_maps)
         return self._forward_inference(images, features, targets=None, return_maps=return_maps)
+
+    def _pre_stream(self, dev):
+        streams = self.__dict__.setdefault("_pre_streams", {})
+        key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=dev)
+        return streams[key]
 
     # ------------------------------------------------------------------ bookkeeping for tests
     def _record_nodes(self, geo, smp, labels=None):

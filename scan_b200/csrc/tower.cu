@@ -59,6 +59,7 @@ struct ConvArgs {
   int n_blocks;          // BN-wide blocks of output channels
   int k_chunks;          // Cin / 32
   int n_terms;           // 1: single-pass tf32, 3: 3xTF32
+  int seg_len;           // k-stages accumulated in tensor memory before the epilogue takes the partial sum (>= k_iters: one segment)
   int rows_per_tap;      // rows of one tap in the packed weight matrix (>= n_blocks * BN)
   float* out;            // [R, ldo]
   int ldo;
@@ -276,22 +277,24 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;
-      for (int w = pair; w < n_work; w += n_pairs, ++j) {
-        const int buf = j & 1;
-        mbar_wait(smem_u32(acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + buf * BN;
-        for (int i = 0; i < k_iters; ++i) {
-          mbar_wait(smem_u32(full_bar + stage), phase);
+      for (int w = pair; w < n_work; w += n_pairs) {
+        for (int i0 = 0; i0 < k_iters; i0 += g.seg_len, ++j) {
+          const int buf = j & 1, i1 = min(i0 + g.seg_len, k_iters);
+          mbar_wait(smem_u32(acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);
           tcgen05_fence_after();
-          const uint32_t a = smem_u32(stages + stage * Cfg::STAGE_BYTES), b = a + CV_A_BYTES;
+          const uint32_t d = tmem_base + buf * BN;
+          for (int i = i0; i < i1; ++i) {
+            mbar_wait(smem_u32(full_bar + stage), phase);
+            tcgen05_fence_after();
+            const uint32_t a = smem_u32(stages + stage * Cfg::STAGE_BYTES), b = a + CV_A_BYTES;
 #pragma unroll
-          for (int k = 0; k < CV_BK / 8; ++k)
-            cv_mma<CG>(d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), IDESC, (i | k) != 0);
-          cv_commit<CG>(smem_u32(empty_bar + stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < CV_BK / 8; ++k)
+              cv_mma<CG>(d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), IDESC, (i > i0) | (k != 0));
+            cv_commit<CG>(smem_u32(empty_bar + stage));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+          cv_commit<CG>(smem_u32(acc_full + buf));
         }
-        cv_commit<CG>(smem_u32(acc_full + buf));
       }
       __syncwarp();
     }
@@ -302,8 +305,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
     int j = 0;
     uint32_t ae = smem_u32(acc_empty);
     if constexpr (CG == 2) ae = mapa_shared(ae, 0);
-    for (int w = pair; w < n_work; w += n_pairs, ++j) {
-      const int buf = j & 1;
+    for (int w = pair; w < n_work; w += n_pairs) {
       const int tg = w / g.n_blocks, nb = w - tg * g.n_blocks;
       const int ti = tg * CG + (int)rank;
       const ConvTile t = conv_decode(g, min(ti, g.n_tiles - 1));
@@ -312,43 +314,60 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
       const long long row = t.row_base + (long long)(t.y0 + py) * t.w + (t.x0 + px);
       float* out = g.out + (valid ? row : 0) * g.ldo + nb * BN;
       const float* add = g.addend ? g.addend + (valid ? row : 0) * g.ldo + nb * BN : nullptr;
-      mbar_wait(smem_u32(acc_full + buf), (uint32_t)(j >> 1) & 1u);
-      tcgen05_fence_after();
-      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      // one pass per accumulation segment: the partial sums of a tile are combined in its output row with round-to-nearest adds
+      // (this thread re-reads what it wrote), bias / addend / ReLU go on with the last one
+      for (int i0 = 0; i0 < k_iters; i0 += g.seg_len, ++j) {
+        const int buf = j & 1;
+        const bool first = i0 == 0, last = i0 + g.seg_len >= k_iters;
+        mbar_wait(smem_u32(acc_full + buf), (uint32_t)(j >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        cv_ld32(tl + c * 32, v);
-        const int col = nb * BN + c * 32;
-        if (!valid || col >= g.n_valid) continue;
-        if (col + 32 <= g.n_valid) {
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          cv_ld32(tl + c * 32, v);
+          const int col = nb * BN + c * 32;
+          if (!valid || col >= g.n_valid) continue;
+          if (col + 32 <= g.n_valid) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            if (g.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + e));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            for (int e = 0; e < 32; e += 4) {
+              float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              float4* dst = reinterpret_cast<float4*>(out + c * 32 + e);
+              if (!first) {
+                const float4 p = *dst;
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              if (last) {
+                if (g.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + e));
+                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if (add) {
+                  const float4 p = __ldg(reinterpret_cast<const float4*>(add + c * 32 + e));
+                  o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                }
+                if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              }
+              *dst = o;
             }
-            if (add) {
-              const float4 p = __ldg(reinterpret_cast<const float4*>(add + c * 32 + e));
-              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-            }
-            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(out + c * 32 + e) = o;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col + e < g.n_valid) {
+                float o = v[e] + (first ? 0.f : out[c * 32 + e]);
+                if (last) {
+                  o += (g.bias ? __ldg(g.bias + col + e) : 0.f) + (add ? __ldg(add + c * 32 + e) : 0.f);
+                  o = g.relu ? fmaxf(o, 0.f) : o;
+                }
+                out[c * 32 + e] = o;
+              }
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col + e < g.n_valid) {
-              float o = v[e] + (g.bias ? __ldg(g.bias + col + e) : 0.f) + (add ? __ldg(add + c * 32 + e) : 0.f);
-              out[c * 32 + e] = g.relu ? fmaxf(o, 0.f) : o;
-            }
         }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(ae + buf * 8); else mbar_arrive(ae + buf * 8);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(ae + buf * 8); else mbar_arrive(ae + buf * 8);
+        }
       }
     }
   }
@@ -795,6 +814,10 @@ extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_row
   g.n_blocks = rows_per_tap / 256;
   g.k_chunks = cin / 32;
   g.n_terms = x_lo ? 3 : 1;
+  // single-pass TF32: one accumulation per tile (what cuDNN does).  3xTF32: the tensor core TRUNCATES when it adds into its
+  // accumulator, so the fp32-accurate mode hands the partial sum to the epilogue every 4 k-stages (16 MMAs:
+  // a bias of at most 16 x 2^-24, below the rounding noise of an fp32 FFMA convolution; epilogue-bound, ~4x slower, parity only)
+  g.seg_len = x_lo ? 4 : 9 * g.k_chunks;
   g.rows_per_tap = rows_per_tap;
   g.out = y_rows;
   g.ldo = ldo;
@@ -860,9 +883,9 @@ static int wg_plan(const Levels& lv, int cin, int cout, int precise, WgArgs* g, 
   const int kinds = 9 * g->m_blocks * g->n_blocks;
   int pairs = sm_count() / 2;
   if (pairs < 1) pairs = 1;
-  // segments: accumulation chains of at most 512 k-chunks (32 when three terms are chained: the tensor core truncates when it
-  // adds into the accumulator), and a segment count that fills the last wave of pairs
-  const int max_chain = precise ? 32 : 512;
+  // segments: accumulation chains of at most 512 k-chunks (8 x 3 terms = 96 MMAs in the fp32-accurate mode: the tensor core
+  // truncates when it adds into the accumulator), and a segment count that fills the last wave of pairs
+  const int max_chain = precise ? 8 : 512;
   const int n_min = (int)ceil_div(chunks, max_chain);
   int best_n = n_min;
   double best_eff = -1.0;

@@ -144,6 +144,11 @@ def run_case(name, module, impl, device="cpu", boxlist_cls=BoxList, load_fixture
         # parity runs compare against an fp32 CPU reference: keep torch's own conv / matmul kernels (the towers,
         # which stay on cuDNN/cuBLAS) in true fp32; the only tf32 arithmetic left is the tcgen05 conditional conv
         torch.backends.cudnn.allow_tf32 = bool(tf32)
+        if impl == "product":
+            # the product's own tower convolutions (csrc/tower.cu): 3xTF32 (fp32-accurate) for the parity runs, single-pass TF32
+            # (= what cuDNN runs under torch's default) at the benchmark's flags
+            from scan_b200 import ops as _ops
+            _ops.CONV["precise"] = not bool(tf32)
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.deterministic = True
         torch.backends.cudnn.benchmark = False
@@ -271,14 +276,14 @@ def is_torch_only(k):
     return any(t in k for t in TORCH_ONLY) and "dfin_direct" not in k
 
 
-def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, only=None, cudnn_l2=1e-2, flip_frac=0.02):
+def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, only=None, cudnn_l2=1e-2, flip_frac=0.02, flip_l2=3e-3):
     """Bit-exact for integer results, rtol (relative to the tensor's max magnitude) for floats.
     only: optional predicate on the key (compare a subset).  Returns list of human-readable mismatches.
 
     Relaxed rules (each use is appended to REPORT):
       * tensors downstream of a tower ReLU (d(features), d(features_in) totals, tower / classifier-hidden gradients) may hold a
         FEW entries whose ReLU mask flipped (pre-activation within ~1e-6 of zero on one side): pass if <= 2 % of the entries
-        exceed the bound and the relative L2 error is <= 3 rtol.  `dfin_direct` (the hot path's own backward, no tower ReLU in
+        exceed the bound and the relative L2 error is <= flip_l2 (3e-3).  `dfin_direct` (the hot path's own backward, no tower ReLU in
         it) is NOT in this class: it must meet the max-norm bound.
       * device runs against the CPU oracle only: TORCH_ONLY tensors are produced by cuDNN's backward-data / backward-filter,
         whose result differs from the CPU convolution on identical inputs (tests/tools/diag_grad2.py); they get the relative-L2
@@ -312,7 +317,7 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, on
             frac = float((d > rtol * scale).mean())
             rel_l2 = float(np.linalg.norm(d) / max(np.linalg.norm(w.astype(np.float64)), 1e-30))
             relu_path = is_torch_only(k) or ("proto_cls_hidden" in k)
-            if relu_path and frac <= flip_frac and rel_l2 <= 3 * rtol:
+            if relu_path and frac <= flip_frac and rel_l2 <= flip_l2:
                 REPORT.append((k, err, scale, frac, rel_l2, "relu-flip rule"))
                 continue
             if device_run and cudnn_l2 and is_torch_only(k) and rel_l2 <= cudnn_l2:
@@ -331,6 +336,14 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, on
 # by torch's own GPU ops around the SAME cuDNN convolution calls.  TEST CODE: the product never takes this path.
 # ----------------------------------------------------------------------------------------------------------------------
 class torch_tower_twin(object):
+    """convs="scan": the twin keeps the product's own tower convolutions (csrc/tower.cu, checked against fp64 convolutions in
+    tests/test_gpu_kernels.py) and swaps only GroupNorm+ReLU / add+ReLU / pack for torch ops, so the strict bound isolates
+    those kernels; convs="cudnn": torch's convolutions as well (two fp32-accurate convolution implementations then differ
+    through ReLU flips, like cuDNN against the CPU)."""
+
+    def __init__(self, convs="scan"):
+        self.convs = convs
+
     def __enter__(self):
         import torch.nn.functional as F
         from scan_b200 import ops
@@ -358,10 +371,15 @@ class torch_tower_twin(object):
             return [f.contiguous(memory_format=torch.channels_last) for f in feats]
 
         ops.gn_relu_levels, ops.add_relu_levels, ops.pack_levels = gn_relu_levels, add_relu_levels, pack_levels
+        from scan_b200 import condgraph
+        self.towers = condgraph.TOWERS
+        self.saved_impl = self.towers["impl"]
+        self.towers["impl"] = self.convs
         return self
 
     def __exit__(self, *exc):
         self.ops.gn_relu_levels, self.ops.add_relu_levels, self.ops.pack_levels = self.saved
+        self.towers["impl"] = self.saved_impl
         return False
 
 

@@ -879,14 +879,14 @@ def test_conv3x3_rows_matches_fp64_conv(shapes, n, cta_group):
         r = ref if not transpose else _conv_levels_ref(geo, x, wt.contiguous(), b)
         hi, lo = ops.conv3x3_pack(w, transpose, True)
         y3 = ops.conv3x3_rows_raw(geo, x, hi, 256, bias=b, x_lo=ops.tf32_residual(x), packed_lo=lo, cta_group=cta_group)
-        assert float((y3.double() - r).abs().max()) <= 5e-5 * scale, "3xTF32 %s" % transpose   # 864-step truncating accumulation
+        assert float((y3.double() - r).abs().max()) <= 5e-6 * scale, "3xTF32 %s" % transpose   # partial sums leave the truncating accumulator every 96 MMAs
         y1 = ops.conv3x3_rows_raw(geo, x, hi, 256, bias=b, cta_group=cta_group)
         assert float((y1.double() - r).abs().max()) <= 2e-3 * scale, "TF32 %s" % transpose
     # epilogue: addend + ReLU
     add = torch.randn(geo.R, 256, device=DEV)
     hi, lo = ops.conv3x3_pack(w, False, True)
     y = ops.conv3x3_rows_raw(geo, x, hi, 256, bias=b, addend=add, relu=True, x_lo=ops.tf32_residual(x), packed_lo=lo, cta_group=cta_group)
-    assert float((y.double() - torch.relu(ref + add.double())).abs().max()) <= 5e-5 * scale
+    assert float((y.double() - torch.relu(ref + add.double())).abs().max()) <= 5e-6 * scale
 
 
 @pytest.mark.parametrize("shapes,n", [([(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 3), ([(100, 168), (50, 84)], 2), ([(9, 5)], 1)])
@@ -905,7 +905,7 @@ def test_conv3x3_wgrad_matches_fp64(shapes, n):
     (ref,) = torch.autograd.grad(torch.cat(ys), [w], dy.double())
     scale = float(ref.abs().max())
     g3 = ops.conv3x3_wgrad_raw(geo, x, dy, x_lo=ops.tf32_residual(x), dy_lo=ops.tf32_residual(dy))
-    assert float((g3.double() - ref).abs().max()) <= 2e-5 * scale
+    assert float((g3.double() - ref).abs().max()) <= 5e-6 * scale
     g1 = ops.conv3x3_wgrad_raw(geo, x, dy)
     assert float((g1.double() - ref).abs().max()) <= 2e-3 * scale
     assert torch.equal(g1, ops.conv3x3_wgrad_raw(geo, x, dy))
