@@ -319,6 +319,10 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         "gn_relu_bwd": ("hbm", 2 * 2 * R * 7 * row),                   # 6 reads + 1 write
         "add_relu_fwd": ("hbm", 2 * R * 3 * row),
         "add_relu_bwd": ("hbm", 2 * R * 2 * row),
+        # tower convolutions (csrc/tower.cu): 3 layers (2 head_in + the feature half of head_out) on R rows per pass; forward and
+        # data gradient share scan_conv3x3_rows, the weight gradient is scan_conv3x3_wgrad
+        "conv3x3_rows": ("tensor", 2 * 3 * 2 * (2 * R * 256 * 256 * 9)),     # passes x layers x (fprop + dgrad) x flops
+        "conv3x3_wgrad": ("tensor", 2 * 3 * (2 * R * 256 * 256 * 9)),
         "condconv_fwd": ("hbm", 2 * R * (row + 4 * k) + R * 8),        # rows + K maps (+ labels on the source pass)
         "condconv_bwd": ("hbm", 2 * R * (2 * row + 2 * 4 * k)),        # rows read, d_rows written, maps + map gradients
         "gather_rows": ("hbm", ms * 2 * row),
@@ -347,7 +351,7 @@ def traffic_of(kernel):
 
 
 # entry point -> the kernel that dominates it (the name the ncu capture and the roofline line report)
-DOMINANT_KERNEL = {"attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_levels_span": "db_adj_tc_kernel",
+DOMINANT_KERNEL = {"conv3x3_rows": "conv3x3_kernel", "conv3x3_wgrad": "conv_wgrad_kernel", "attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_levels_span": "db_adj_tc_kernel",
                    "condconv_fwd": "condconv_fwd_ts_kernel", "condconv_bwd": "condconv_bwd_rows_kernel", "gn_relu_bwd": "gn_bwd_apply_kernel",
                    "gn_relu_fwd": "gn_apply_kernel", "qkv_fwd": "gemm3x_kernel", "qkv_bwd": "gemm3x_kernel"}
 

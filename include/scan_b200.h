@@ -341,6 +341,13 @@ int scan_tf32_residual(const float* x, int64_t n, float* lo, void* stream);
 int scan_conv3x3_rows(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* packed,
                       const float* packed_lo, int32_t n_out, const float* bias, const float* addend, int32_t relu, float* y_rows,
                       int32_t ldo, int32_t cta_group, void* stream);
+/* the same with an optional SECOND input tensor x2_rows [R, cin2] whose channels follow x_rows' in the weight columns (the
+ * concatenation [features | activation maps] of head_out, condgraph.py:379-384, and of the CKA discriminator's class-conditional
+ * maps, fcos_head_discriminator_con.py:104-105, without materialising it), and an optional mask [R, ldo]: out = mask > 0 ? out : 0
+ * (data gradient through the ReLU of a saved forward output). */
+int scan_conv3x3_rows2(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* x2_rows,
+                       const float* x2_lo, int32_t cin2, const float* packed, const float* packed_lo, int32_t n_out, const float* bias,
+                       const float* addend, const float* mask, int32_t relu, float* y_rows, int32_t ldo, int32_t cta_group, void* stream);
 
 /* weight gradient of the same convolution: d_w[co][ci][ky][kx] (element strides s_*) = sum_p dy_rows[p, co] * x_rows[p + off, ci];
  * cin and cout multiples of 256; both operands are read in place (MN-major tcgen05 operands, no transposed copy); x_lo / dy_lo
@@ -349,6 +356,28 @@ int64_t scan_conv3x3_wgrad_workspace_bytes(const scan_levels_t* lv, int32_t cin,
 int scan_conv3x3_wgrad(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* dy_rows,
                        const float* dy_lo, int32_t cout, float* d_w, int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx,
                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- f3: thin kernels of the CKA discriminator FCOSDiscriminator_con (modeling/discriminator/fcos_head_discriminator_con.py:88-127,
+ *      layer.py:6-24); its convolutions are scan_conv3x3_rows2 / scan_conv3x3_wgrad ---------------------------------------------
+ * scan_thin_pack: channels [c0, c0 + k) of per-level NCHW maps [N, k_total, H_l, W_l] (HOST array of device pointers) -> rows
+ * [R, ld] columns [0, k), the remaining columns zero.  scan_thin_unpack: the inverse, times `scale` (the other channels of the
+ * NCHW tensors are left untouched).  scan_scale: y = scale * x (gradient reversal).  scan_colsum: out[c] = sum_r x[r, c]. */
+int scan_thin_pack(const scan_levels_t* lv, const void* const* nchw_host, int32_t k_total, int32_t c0, int32_t k, float* rows, int32_t ld,
+                   void* stream);
+int scan_thin_unpack(const scan_levels_t* lv, const float* rows, int32_t ld, int32_t k_total, int32_t c0, int32_t k, float scale,
+                     void* const* nchw_host, void* stream);
+int scan_scale(const float* x, int64_t n, float scale, float* y, void* stream);
+int64_t scan_colsum_workspace_bytes(int64_t n_rows, int32_t n_cols);
+int scan_colsum(const float* x, int64_t n_rows, int32_t n_cols, int32_t ld, float* out, void* workspace, int64_t workspace_bytes,
+                void* stream);
+/* class-weighted BCE with logits (:113-121): n_cls > 1: loss = sum_c [sum_p w_c bce(x_c, t) / sum_p w_c] / n_cls with w = the class
+ * maps (detached); n_cls == 1: the plain mean.  inv [16] receives the per-class gradient factors; scan_cka_bce_bwd writes
+ * d_logits = d_loss * (sigmoid(x) - t) * w * inv[c] to dl32 [R, 32] (zero padded) and, if non-NULL, to dl_wide [R, ld_wide]. */
+int64_t scan_cka_bce_workspace_bytes(void);
+int scan_cka_bce_fwd(const float* logits, int32_t ldl, const float* weights, int32_t ldw, int64_t n_rows, int32_t n_cls, float target,
+                     float* loss, float* inv, void* workspace, int64_t workspace_bytes, void* stream);
+int scan_cka_bce_bwd(const float* logits, int32_t ldl, const float* weights, int32_t ldw, int64_t n_rows, int32_t n_cls, float target,
+                     const float* inv, const float* d_loss, float* dl32, float* dl_wide, int32_t ld_wide, void* stream);
 
 /* ---- f4: FCOS post-processor (modeling/rpn/fcos/inference.py:54-194; boxlist_nms structures/boxlist_ops.py:9-31; IoU and
  *      suppression rule csrc/cuda/nms.cu:13-67) on the probability maps of scan_ensemble_levels ----------------------------

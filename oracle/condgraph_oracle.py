@@ -880,3 +880,32 @@ class OracleCondGraph(nn.Module):
 
 def build_oracle(cfg, in_channels=256):
     return OracleCondGraph(cfg, in_channels)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# f3: CKA discriminator (modeling/discriminator/fcos_head_discriminator_con.py:88-127, layer.py:6-24), restated with plain
+# torch ops.  TEST INFRASTRUCTURE (pinned by tests/golden/cka.npz, generated from the unmodified reference module).
+# ----------------------------------------------------------------------------------------------------------------------
+def cka_discriminator_loss(state, feature, act_maps, target, num_classes_fg, num_convs, fusion_cfg="concat"):
+    """state: the module's state dict (dis_tower.{3i}.weight/bias, dis_tower.{3i+1}.weight/bias, classifier_cls_{c}.{0,2}.*).
+    Forward only (the gradient reversal is the identity forward, layer.py:15-17); gradients come from autograd on the inputs,
+    with the reversal applied by the caller (d = -lambda * d, layer.py:19-24)."""
+    x = feature
+    for i in range(num_convs):                                                      # :20-33, :98
+        x = F.conv2d(x, state["dis_tower.%d.weight" % (3 * i)], state["dis_tower.%d.bias" % (3 * i)], padding=1)
+        x = F.relu(F.group_norm(x, 32, state["dis_tower.%d.weight" % (3 * i + 1)], state["dis_tower.%d.bias" % (3 * i + 1)], 1e-5))
+    loss = 0
+    for c in range(num_classes_fg):                                                 # :101-123 (use_bg = False: map index c + 1)
+        m = act_maps[:, c + 1:c + 2]
+        if fusion_cfg != "concat":
+            raise KeyError("only 'concat' is restated")
+        x_cls = torch.cat((x, m), dim=1)                                            # :104-105
+        hcls = F.relu(F.conv2d(x_cls, state["classifier_cls_%d.0.weight" % c], state["classifier_cls_%d.0.bias" % c], padding=1))
+        logits = F.conv2d(hcls, state["classifier_cls_%d.2.weight" % c], state["classifier_cls_%d.2.bias" % c], padding=1)
+        targets = torch.full(logits.shape, float(target), dtype=torch.float, device=x.device)
+        if num_classes_fg > 1:                                                      # :115-118
+            loss_cls = F.binary_cross_entropy_with_logits(logits, targets, weight=m.detach(), reduction="sum") / m.sum().detach()
+        else:                                                                       # :119-120
+            loss_cls = F.binary_cross_entropy_with_logits(logits, targets)
+        loss = loss + loss_cls / num_classes_fg                                     # :121
+    return loss

@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 OBJS=()
 mkdir -p "$HERE/build"
 pids=()
-for f in core layout gn manifest assign losses proto condconv gemm transfer rowsmlp fcosloss postproc tower attention attention_t5 attention_t5_bwd dbscan dbscan_tc; do
+for f in core layout gn manifest assign losses proto condconv gemm transfer rowsmlp fcosloss postproc tower cka attention attention_t5 attention_t5_bwd dbscan dbscan_tc; do
   "$NVCC" $FLAGS ${SCAN_PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
   pids+=($!)
   OBJS+=("$HERE/build/$f.o")

@@ -41,7 +41,8 @@ struct ConvCfg {
 
 struct alignas(64) ConvMaps {
   CUtensorMap a[2][SCAN_MAX_LEVELS];   // [hi | lo plane][level]: 4-D (C, W, H, N), box (32, tw, th, 1)
-  CUtensorMap b[2];                    // [hi | lo plane]: 2-D [9 * rows_per_tap, Cin], box (32, B_ROWS)
+  CUtensorMap a2[2][SCAN_MAX_LEVELS];  // optional second input tensor (its channels follow the first one's in the weight columns)
+  CUtensorMap b[2];                    // [hi | lo plane]: 2-D [9 * rows_per_tap, Cin + Cin2], box (32, B_ROWS)
 };
 
 struct ConvLevel {
@@ -58,6 +59,7 @@ struct ConvArgs {
   int n_tiles;           // pixel tiles over all levels and images
   int n_blocks;          // BN-wide blocks of output channels
   int k_chunks;          // Cin / 32
+  int k_chunks2;         // 32-channel chunks of the second input (0: none)
   int n_terms;           // 1: single-pass tf32, 3: 3xTF32
   int seg_len;           // k-stages accumulated in tensor memory before the epilogue takes the partial sum (>= k_iters: one segment)
   int rows_per_tap;      // rows of one tap in the packed weight matrix (>= n_blocks * BN)
@@ -66,6 +68,7 @@ struct ConvArgs {
   int n_valid;           // valid output channels (<= n_blocks * BN)
   const float* bias;     // [n_valid] or null
   const float* addend;   // [R, ldo] or null: out = act(acc + bias + addend)
+  const float* mask;     // [R, ldo] or null: out = mask > 0 ? out : 0 (the ReLU of a saved forward output, for data gradients)
   int relu;
 };
 
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
   const int pair = blockIdx.x / CG, n_pairs = gridDim.x / CG;
   const int n_tile_groups = (g.n_tiles + CG - 1) / CG;
   const int n_work = n_tile_groups * g.n_blocks;
-  const int k_iters = g.n_terms * 9 * g.k_chunks;
+  const int kc_all = g.k_chunks + g.k_chunks2;
+  const int k_iters = g.n_terms * 9 * kc_all;
   constexpr uint32_t IDESC = umma_idesc_tf32(CV_BM * CG, BN);
 
   if (threadIdx.x == 0) {
@@ -254,16 +258,20 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
         const int b_row0 = nb * BN + (int)rank * Cfg::B_ROWS;
         for (int term = 0; term < g.n_terms; ++term) {
           const CUtensorMap* ma = &maps.a[term == 2 ? 1 : 0][t.l];
+          const CUtensorMap* ma2 = &maps.a2[term == 2 ? 1 : 0][t.l];
           const CUtensorMap* mb = &maps.b[term == 1 ? 1 : 0];
           for (int tap = 0; tap < 9; ++tap) {
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            for (int kc = 0; kc < g.k_chunks; ++kc) {
+            for (int kc = 0; kc < kc_all; ++kc) {
               mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
               uint32_t fb = smem_u32(full_bar + stage);
               if (rank == 0) mbar_expect_tx(fb, bytes);
               if constexpr (CG == 2) fb = mapa_shared(fb, 0);
               const uint32_t dst = smem_u32(stages + stage * Cfg::STAGE_BYTES);
-              cv_tma_4d<CG>(dst, ma, fb, kc * CV_BK, t.x0 + dx, t.y0 + dy, t.n);
+              if (kc < g.k_chunks)
+                cv_tma_4d<CG>(dst, ma, fb, kc * CV_BK, t.x0 + dx, t.y0 + dy, t.n);
+              else
+                cv_tma_4d<CG>(dst, ma2, fb, (kc - g.k_chunks) * CV_BK, t.x0 + dx, t.y0 + dy, t.n);
               cv_tma_2d<CG>(dst + CV_A_BYTES, mb, fb, kc * CV_BK, tap * g.rows_per_tap + b_row0);
               if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -314,6 +322,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
       const long long row = t.row_base + (long long)(t.y0 + py) * t.w + (t.x0 + px);
       float* out = g.out + (valid ? row : 0) * g.ldo + nb * BN;
       const float* add = g.addend ? g.addend + (valid ? row : 0) * g.ldo + nb * BN : nullptr;
+      const float* msk = g.mask ? g.mask + (valid ? row : 0) * g.ldo + nb * BN : nullptr;
       // one pass per accumulation segment: the partial sums of a tile are combined in its output row with round-to-nearest adds
       // (this thread re-reads what it wrote), bias / addend / ReLU go on with the last one
       for (int i0 = 0; i0 < k_iters; i0 += g.seg_len, ++j) {
@@ -347,6 +356,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
                   o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
                 }
                 if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (msk) {
+                  const float4 q4 = __ldg(reinterpret_cast<const float4*>(msk + c * 32 + e));
+                  o.x = q4.x > 0.f ? o.x : 0.f; o.y = q4.y > 0.f ? o.y : 0.f; o.z = q4.z > 0.f ? o.z : 0.f; o.w = q4.w > 0.f ? o.w : 0.f;
+                }
               }
               *dst = o;
             }
@@ -358,6 +371,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
                 if (last) {
                   o += (g.bias ? __ldg(g.bias + col + e) : 0.f) + (add ? __ldg(add + c * 32 + e) : 0.f);
                   o = g.relu ? fmaxf(o, 0.f) : o;
+                  if (msk) o = __ldg(msk + c * 32 + e) > 0.f ? o : 0.f;
                 }
                 out[c * 32 + e] = o;
               }
@@ -765,20 +779,22 @@ extern "C" int scan_tf32_residual(const float* x, int64_t n, float* lo, void* st
   return SCAN_OK;
 }
 
-// y_rows[R, ldo] = act(conv3x3(x_rows[R, cin]; packed weights) + bias + addend).  `packed` is scan_conv3x3_pack_weights'
-// output for n_out output channels (rows padded to 256) and cin (a multiple of 32) input channels.  x_lo / packed_lo non-null
-// selects 3xTF32.  cta_group = 1 or 2.
-extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* packed,
-                                 const float* packed_lo, int n_out, const float* bias, const float* addend, int relu, float* y_rows, int ldo,
-                                 int cta_group, void* stream) {
+// y_rows[R, ldo] = act(conv3x3([x_rows[R, cin] | x2_rows[R, cin2]]; packed weights) + bias + addend), optionally masked.
+// `packed` is scan_conv3x3_pack_weights' output for n_out output channels (rows padded to 256) and cin + cin2 input channels
+// (cin, cin2 multiples of 32; x2_rows may be NULL).  x_lo / packed_lo (and x2_lo) non-null selects 3xTF32.  cta_group = 1 or 2.
+extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* x2_rows,
+                                  const float* x2_lo, int cin2, const float* packed, const float* packed_lo, int n_out, const float* bias,
+                                  const float* addend, const float* mask, int relu, float* y_rows, int ldo, int cta_group, void* stream) {
   Levels lv;
   int rc = make_levels(levels, &lv);
   if (rc) return rc;
   if (!x_rows || !packed || !y_rows || cin < 32 || (cin % 32) || n_out < 1 || ldo < n_out || (ldo % 4) || ((uintptr_t)y_rows & 15))
     return SCAN_EINVAL;
   if ((x_lo == nullptr) != (packed_lo == nullptr)) return SCAN_EINVAL;
+  if (x2_rows && (cin2 < 32 || (cin2 % 32) || (x_lo == nullptr) != (x2_lo == nullptr))) return SCAN_EINVAL;
+  if (!x2_rows) cin2 = 0;
   if (cta_group != 1 && cta_group != 2) return SCAN_EINVAL;
-  if ((bias && ((uintptr_t)bias & 15)) || (addend && ((uintptr_t)addend & 15))) return SCAN_EINVAL;
+  if ((bias && ((uintptr_t)bias & 15)) || (addend && ((uintptr_t)addend & 15)) || (mask && ((uintptr_t)mask & 15))) return SCAN_EINVAL;
   ConvMaps maps;
   ConvArgs g = {};
   g.n_levels = lv.n_levels;
@@ -796,11 +812,21 @@ extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_row
     tiles += lv.n_images * L.tiles_x * L.tiles_y;
     rc = conv_make_a_map(&maps.a[0][l], x_rows + lv.row_off[l] * cin, cin, L.w, L.h, lv.n_images, L.tw, L.th);
     if (rc) return rc;
+    maps.a[1][l] = maps.a[0][l];
     if (x_lo) {
       rc = conv_make_a_map(&maps.a[1][l], x_lo + lv.row_off[l] * cin, cin, L.w, L.h, lv.n_images, L.tw, L.th);
       if (rc) return rc;
-    } else {
-      maps.a[1][l] = maps.a[0][l];
+    }
+    maps.a2[0][l] = maps.a[0][l];
+    maps.a2[1][l] = maps.a[1][l];
+    if (x2_rows) {
+      rc = conv_make_a_map(&maps.a2[0][l], x2_rows + lv.row_off[l] * cin2, cin2, L.w, L.h, lv.n_images, L.tw, L.th);
+      if (rc) return rc;
+      maps.a2[1][l] = maps.a2[0][l];
+      if (x2_lo) {
+        rc = conv_make_a_map(&maps.a2[1][l], x2_lo + lv.row_off[l] * cin2, cin2, L.w, L.h, lv.n_images, L.tw, L.th);
+        if (rc) return rc;
+      }
     }
   }
   for (int l = lv.n_levels; l < SCAN_MAX_LEVELS; ++l) {
@@ -808,32 +834,42 @@ extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_row
     g.lv[l].tile_off = 0x7fffffff;
     maps.a[0][l] = maps.a[0][0];
     maps.a[1][l] = maps.a[1][0];
+    maps.a2[0][l] = maps.a2[0][0];
+    maps.a2[1][l] = maps.a2[1][0];
   }
   const int rows_per_tap = (n_out + 255) / 256 * 256;
   g.n_tiles = tiles;
   g.n_blocks = rows_per_tap / 256;
   g.k_chunks = cin / 32;
+  g.k_chunks2 = cin2 / 32;
   g.n_terms = x_lo ? 3 : 1;
   // single-pass TF32: one accumulation per tile (what cuDNN does).  3xTF32: the tensor core TRUNCATES when it adds into its
   // accumulator, so the fp32-accurate mode hands the partial sum to the epilogue every 4 k-stages (16 MMAs:
   // a bias of at most 16 x 2^-24, below the rounding noise of an fp32 FFMA convolution; epilogue-bound, ~4x slower, parity only)
-  g.seg_len = x_lo ? 4 : 9 * g.k_chunks;
+  g.seg_len = x_lo ? 4 : g.n_terms * 9 * (g.k_chunks + g.k_chunks2);
   g.rows_per_tap = rows_per_tap;
   g.out = y_rows;
   g.ldo = ldo;
   g.n_valid = n_out;
   g.bias = bias;
   g.addend = addend;
+  g.mask = mask;
   g.relu = relu;
-  rc = conv_make_b_map(&maps.b[0], packed, 9ll * rows_per_tap, cin, 256 / cta_group);
+  rc = conv_make_b_map(&maps.b[0], packed, 9ll * rows_per_tap, cin + cin2, 256 / cta_group);
   if (rc) return rc;
+  maps.b[1] = maps.b[0];
   if (packed_lo) {
-    rc = conv_make_b_map(&maps.b[1], packed_lo, 9ll * rows_per_tap, cin, 256 / cta_group);
+    rc = conv_make_b_map(&maps.b[1], packed_lo, 9ll * rows_per_tap, cin + cin2, 256 / cta_group);
     if (rc) return rc;
-  } else {
-    maps.b[1] = maps.b[0];
   }
   return cta_group == 2 ? conv_launch<2, 256>(maps, g, (cudaStream_t)stream) : conv_launch<1, 256>(maps, g, (cudaStream_t)stream);
+}
+
+extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* packed,
+                                 const float* packed_lo, int n_out, const float* bias, const float* addend, int relu, float* y_rows, int ldo,
+                                 int cta_group, void* stream) {
+  return scan_conv3x3_rows2(levels, x_rows, x_lo, cin, nullptr, nullptr, 0, packed, packed_lo, n_out, bias, addend, nullptr, relu, y_rows,
+                            ldo, cta_group, stream);
 }
 
 // ---------------------------------------------------------------------------- weight gradient: host side

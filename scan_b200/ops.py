@@ -1342,3 +1342,174 @@ def postprocess(geo, probs, box_regression, centerness, image_sizes, num_classes
          float(pre_nms_thresh), int(pre_nms_top_n), float(nms_thresh), int(post_top_n), float(min_size), _ptr(boxes), _ptr(scores),
          _ptr(labels), _ptr(counts), _ptr(ws), ws_bytes, _stream())
     return boxes, scores, labels, counts
+
+
+# ----------------------------------------------------------------------------------------------------
+# f3: CKA discriminator building blocks (csrc/cka.cu + the tower convolution kernels)
+# ----------------------------------------------------------------------------------------------------
+def thin_pack(geo, maps, c0, k, ld):
+    """Channels [c0, c0 + k) of per-level NCHW maps -> rows [R, ld] (zero padded)."""
+    maps = [m.contiguous() for m in maps]
+    rows = torch.empty((geo.R, ld), device=maps[0].device, dtype=torch.float32)
+    call("scan_thin_pack", geo.ref(), _ptr_array(maps), maps[0].shape[1], c0, k, _ptr(rows), ld, _stream())
+    return rows
+
+
+def thin_unpack(geo, rows, k_total, c0, k, scale=1.0):
+    """rows [R, ld] columns [0, k) * scale -> per-level NCHW [N, k_total, H, W] tensors (other channels zero)."""
+    outs = [torch.zeros((geo.n_images, k_total, h, w), device=rows.device, dtype=torch.float32) for h, w in geo.shapes]
+    call("scan_thin_unpack", geo.ref(), _ptr(rows), rows.shape[1], k_total, c0, k, float(scale), _ptr_array(outs), _stream())
+    return outs
+
+
+def colsum(x, n_cols):
+    """Column sums of the first n_cols columns of a contiguous [R, ld] matrix."""
+    nbytes = _lib.lib().scan_colsum_workspace_bytes(x.shape[0], n_cols)
+    ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
+    out = torch.empty((n_cols,), device=x.device, dtype=torch.float32)
+    call("scan_colsum", _ptr(x), x.shape[0], n_cols, x.shape[1], _ptr(out), _ptr(ws), nbytes, _stream())
+    return out
+
+
+class _GradScale(torch.autograd.Function):
+    """layer.py:6-24 GradientReversalFunction: identity forward, dx = -lambda * grad (scan_scale)."""
+
+    @staticmethod
+    def forward(ctx, x, lambda_):
+        ctx.lambda_ = float(lambda_)
+        return x.view_as(x)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous() if g.is_contiguous() else nhwc_dense(g)
+        out = torch.empty_like(g)
+        if g.numel() % 4 == 0:
+            call("scan_scale", _ptr(g), g.numel(), -ctx.lambda_, _ptr(out), _stream())
+        else:     # odd-sized tails (tiny maps): pad through a flat copy
+            flat = torch.zeros(((g.numel() + 3) // 4 * 4,), device=g.device, dtype=torch.float32)
+            flat[:g.numel()] = g.reshape(-1)
+            res = torch.empty_like(flat)
+            call("scan_scale", _ptr(flat), flat.numel(), -ctx.lambda_, _ptr(res), _stream())
+            out = res[:g.numel()].view(g.shape)
+        return out, None
+
+
+def grad_reverse(x, lambda_):
+    return _GradScale.apply(x, lambda_)
+
+
+def _pad256(n):
+    return (n + 255) // 256 * 256
+
+
+class _CkaClassMaps(torch.autograd.Function):
+    """The per-class loop of FCOSDiscriminator_con.forward (fcos_head_discriminator_con.py:100-123) for ALL classes at once:
+         h      = relu(conv3x3([x | maps]; w1) + b1)       w1 [C*128, 256 + C, 3, 3] block structured (class c: its 128 rows see
+                                                            the 256 feature columns and map column c)
+         logits = conv3x3(h; w2) + b2                       w2 [C, C*128, 3, 3] block diagonal
+         loss   = class-weighted BCE-with-logits(logits, target; weights = maps)
+    x_rows [R, 256], maps32 [R, 32] (maps of classes 1..C in columns 0..C-1).  Returns the scalar loss."""
+
+    @staticmethod
+    def forward(ctx, geo, x_rows, maps32, w1, b1, w2, b2, target, n_cls):
+        precise = CONV["precise"]
+        dev = x_rows.device
+        hc = w1.shape[0]                       # C * 128
+        hp = _pad256(hc)
+        lo = (lambda t: tf32_residual(t)) if precise else (lambda t: None)
+        w1_hi, w1_lo = conv3x3_pack(w1, False, precise)
+        h = torch.zeros((geo.R, hp), device=dev, dtype=torch.float32) if hp != hc else torch.empty((geo.R, hp), device=dev, dtype=torch.float32)
+        x_lo, m_lo = lo(x_rows), lo(maps32)
+        call("scan_conv3x3_rows2", geo.ref(), _ptr(x_rows), _ptr(x_lo), x_rows.shape[1], _ptr(maps32), _ptr(m_lo), 32, _ptr(w1_hi),
+             _ptr(w1_lo), hc, _ptr(b1), None, None, 1, _ptr(h), hp, CONV["cta_group"], _stream())
+        # the second convolution reads h with its padded width: pad w2's input channels with zero columns
+        w2p = w2 if hp == hc else torch.cat([w2, w2.new_zeros((w2.shape[0], hp - hc, 3, 3))], dim=1)
+        w2_hi, w2_lo = conv3x3_pack(w2p, False, precise)
+        logits = torch.empty((geo.R, 32), device=dev, dtype=torch.float32)
+        h_lo = lo(h)
+        call("scan_conv3x3_rows2", geo.ref(), _ptr(h), _ptr(h_lo), hp, None, None, 0, _ptr(w2_hi), _ptr(w2_lo), n_cls, _ptr(b2), None, None,
+             0, _ptr(logits), 32, CONV["cta_group"], _stream())
+        nbytes = _lib.lib().scan_cka_bce_workspace_bytes()
+        ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+        loss = torch.empty((1,), device=dev, dtype=torch.float32)
+        inv = torch.empty((16,), device=dev, dtype=torch.float32)
+        call("scan_cka_bce_fwd", _ptr(logits), 32, _ptr(maps32), 32, geo.R, n_cls, float(target), _ptr(loss), _ptr(inv), _ptr(ws), nbytes,
+             _stream())
+        ctx.geo, ctx.precise, ctx.target, ctx.n_cls, ctx.hc, ctx.hp = geo, precise, float(target), n_cls, hc, hp
+        ctx.save_for_backward(x_rows, maps32, w1, w2p, h, logits, inv)
+        ctx.lo = (x_lo, m_lo, h_lo)
+        return loss.reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_loss):
+        geo, precise, n_cls, hc, hp = ctx.geo, ctx.precise, ctx.n_cls, ctx.hc, ctx.hp
+        x_rows, maps32, w1, w2p, h, logits, inv = ctx.saved_tensors
+        x_lo, m_lo, h_lo = ctx.lo
+        dev = x_rows.device
+        lo = (lambda t: tf32_residual(t)) if precise else (lambda t: None)
+        d_loss = d_loss.reshape(1).contiguous().float()
+        dl32 = torch.empty((geo.R, 32), device=dev, dtype=torch.float32)
+        dl256 = torch.zeros((geo.R, 256), device=dev, dtype=torch.float32)
+        call("scan_cka_bce_bwd", _ptr(logits), 32, _ptr(maps32), 32, geo.R, n_cls, ctx.target, _ptr(inv), _ptr(d_loss), _ptr(dl32),
+             _ptr(dl256), 256, _stream())
+        d_b2 = colsum(dl32, n_cls)
+        # second convolution: weight gradient (dY padded to 256 columns for the 256-wide MMA tile) and data gradient through h's ReLU
+        dl32_lo, dl256_lo = lo(dl32), lo(dl256)
+        d_w2_full = torch.empty((256, hp, 3, 3), device=dev, dtype=torch.float32)
+        conv3x3_wgrad_raw(geo, h, dl256, x_lo=h_lo, dy_lo=dl256_lo, out=d_w2_full)
+        d_w2p = d_w2_full[:n_cls]
+        w2t_hi, w2t_lo = conv3x3_pack(w2p, True, precise)      # rows = h channels (hp), cols = classes (padded to 32)
+        d_pre = torch.zeros((geo.R, hp), device=dev, dtype=torch.float32) if hp != hc else torch.empty((geo.R, hp), device=dev, dtype=torch.float32)
+        call("scan_conv3x3_rows2", geo.ref(), _ptr(dl32), _ptr(dl32_lo), 32, None, None, 0, _ptr(w2t_hi), _ptr(w2t_lo), hc, None, None,
+             _ptr(h), 0, _ptr(d_pre), hp, CONV["cta_group"], _stream())
+        d_b1 = colsum(d_pre, hc)
+        d_pre_lo = lo(d_pre)
+        # first convolution: gradients wrt the features, the class maps and the block-structured weight
+        w1p = w1 if hp == hc else torch.cat([w1, w1.new_zeros((hp - hc,) + tuple(w1.shape[1:]))], dim=0)
+        w1x_hi, w1x_lo = conv3x3_pack(w1p[:, :256], True, precise)
+        d_x = conv3x3_rows_raw(geo, d_pre, w1x_hi, 256, x_lo=d_pre_lo, packed_lo=w1x_lo)
+        w1m_hi, w1m_lo = conv3x3_pack(w1p[:, 256:], True, precise)
+        d_maps32 = torch.zeros((geo.R, 32), device=dev, dtype=torch.float32)
+        call("scan_conv3x3_rows2", geo.ref(), _ptr(d_pre), _ptr(d_pre_lo), hp, None, None, 0, _ptr(w1m_hi), _ptr(w1m_lo), n_cls, None, None,
+             None, 0, _ptr(d_maps32), 32, CONV["cta_group"], _stream())
+        d_w1 = torch.empty_like(w1.contiguous())
+        d_w1x_full = torch.empty((hp, 256, 3, 3), device=dev, dtype=torch.float32)
+        conv3x3_wgrad_raw(geo, x_rows, d_pre, x_lo=x_lo, dy_lo=d_pre_lo, out=d_w1x_full)
+        maps256 = torch.zeros((geo.R, 256), device=dev, dtype=torch.float32)
+        maps256[:, :32] = maps32
+        d_w1m_full = torch.empty((hp, 256, 3, 3), device=dev, dtype=torch.float32)
+        conv3x3_wgrad_raw(geo, maps256, d_pre, x_lo=lo(maps256), dy_lo=d_pre_lo, out=d_w1m_full)
+        d_w1[:, :256] = d_w1x_full[:hc]
+        d_w1[:, 256:] = d_w1m_full[:hc, :n_cls]
+        d_w2 = d_w2p[:, :hc].contiguous()
+        return None, d_x, d_maps32, d_w1, d_b1, d_w2, d_b2, None, None
+
+
+def cka_class_maps_loss(geo, x_rows, maps32, w1, b1, w2, b2, target, n_cls):
+    if x_rows.shape[1] != C or maps32.shape[1] != 32 or n_cls > 16:
+        raise RuntimeError("cka_class_maps_loss: [R,256] features, [R,32] class maps, at most 16 classes")
+    if not x_rows.is_cuda:
+        raise RuntimeError("cka_class_maps_loss needs CUDA tensors (no CPU fallback)")
+    return _CkaClassMaps.apply(geo, x_rows.contiguous(), maps32.contiguous(), w1.contiguous(), b1.contiguous(), w2.contiguous(),
+                               b2.contiguous(), target, n_cls)
+
+
+class _ThinPackMaps(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geo, maps, c0, k):
+        ctx.geo, ctx.c0, ctx.k, ctx.k_total = geo, c0, k, maps.shape[1]
+        return thin_pack(geo, [maps], c0, k, 32)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_rows):
+        return None, thin_unpack(ctx.geo, d_rows.contiguous(), ctx.k_total, ctx.c0, ctx.k)[0], None, None
+
+
+def thin_pack_maps(geo, maps, c0, k):
+    """Single-level [N,K,H,W] class maps -> rows [R,32] holding channels [c0, c0 + k) (differentiable)."""
+    if not maps.is_cuda or maps.dtype != torch.float32 or k > 32:
+        raise RuntimeError("thin_pack_maps expects CUDA fp32 maps with at most 32 selected channels (no CPU fallback)")
+    return _ThinPackMaps.apply(geo, maps, c0, k)

@@ -913,3 +913,39 @@ def test_conv3x3_wgrad_matches_fp64(shapes, n):
     out = torch.empty(256, 256, 3, 3, device=DEV).contiguous(memory_format=torch.channels_last)
     ops.conv3x3_wgrad_raw(geo, x, dy, out=out)
     assert torch.equal(out, g1)
+
+
+@pytest.mark.parametrize("name", ["c9_source", "c9_target", "k2_target_only"])
+def test_cka_discriminator_matches_reference_golden(name, golden_dir):
+    """f3: FCOSDiscriminator_con (dis_tower, all-classes conditional maps as two tcgen05 convolutions, weighted BCE, gradient
+    reversal into the features AND the activation maps) against vectors of the unmodified reference module: loss, d(feature),
+    d(act_maps), every parameter gradient.  3xTF32 convolutions (parity mode), bound 1e-3 of each tensor's max (measured ~1e-5)."""
+    import os
+    import cka_case
+    from scan_b200.discriminator import FCOSDiscriminator_con
+    gold = np.load(os.path.join(golden_dir, "cka.npz"))
+    d = cka_case.build(name)
+    m = FCOSDiscriminator_con(num_convs=d["num_convs"], num_classes=d["k"], grad_reverse_lambda=d["lam"], grl_applied_domain=d["grl_dom"])
+    m.load_state_dict(cka_case.state_dict_for(m, seed=5))
+    m.to(DEV)
+    saved = ops.CONV["precise"]
+    ops.CONV["precise"] = True
+    try:
+        feat = d["feat"].to(DEV).requires_grad_(True)
+        act = d["act"].to(DEV).requires_grad_(True)
+        loss = m(feat, d["target"], act_maps=act, domain=d["domain"])
+        loss.backward()
+    finally:
+        ops.CONV["precise"] = saved
+    want = float(gold[name + "/loss"])
+    assert abs(float(loss.detach()) - want) <= 2e-5 * max(1.0, abs(want)), (float(loss.detach()), want)
+    got = {"d_feature": feat.grad, "d_act": act.grad if act.grad is not None else torch.zeros_like(act)}
+    for k, p in m.named_parameters():
+        got["grad/" + k] = p.grad
+    worst = 0.0
+    for k, v in got.items():
+        worst = max(worst, cka_case.check(v.detach().cpu().numpy(), gold[name + "/" + k + "#s"], gold[name + "/" + k + "#n"], 1e-3))
+    print("cka %s worst relative-to-max error %.2e" % (name, worst))
+    # the benchmark arithmetic (single-pass TF32 convolutions): same loss within the TF32 bound
+    loss_fast = m(d["feat"].to(DEV), d["target"], act_maps=d["act"].to(DEV), domain=d["domain"])
+    assert abs(float(loss_fast) - want) <= 5e-3 * max(1.0, abs(want))
