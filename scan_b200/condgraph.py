@@ -331,6 +331,13 @@ class GRAPHModule(nn.Module):
             return features
         layers = list(self.head_out.middle_tower)
         conv = layers[0]
+        if (TOWERS["impl"] == "scan" and len(layers) == 2 and isinstance(layers[1], nn.ReLU) and conv.weight.shape[0] == ops.C
+                and conv.bias is not None):
+            # the shipped form, entirely on the tower kernels: one launch over [features | maps] with bias + ReLU in its epilogue
+            geo = ops.Geometry.of(features, self.fpn_strides)
+            if us is None:
+                return ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), features=list(features))
+            return ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), us=list(us))
         wa = conv.weight[:, ops.C:].contiguous(memory_format=torch.channels_last)
         if us is None:
             us = self.head_out_feature_half(features)
@@ -367,7 +374,8 @@ class GRAPHModule(nn.Module):
         grad_on = torch.is_grad_enabled()
 
         def early():
-            if self.with_concated_maps:
+            # single GPU: nothing to hide, head_out then runs as ONE fused launch after the conditional convolution
+            if self.with_concated_maps and self._dist_world() > 1:
                 with torch.set_grad_enabled(grad_on):      # update_prototype_ensemble itself runs under no_grad
                     held["us"] = self.head_out_feature_half(features)
 
@@ -554,6 +562,12 @@ class GRAPHModule(nn.Module):
         elif self.training and mode == "target" and forward_target:
             return self._forward_train_target(images, features, targets=None, return_maps=return_maps)
         return self._forward_inference(images, features, targets=None, return_maps=return_maps)
+
+    def _dist_world(self):
+        if self.dist_group is None:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.dist_group)
 
     def _pre_stream(self, dev):
         streams = self.__dict__.setdefault("_pre_streams", {})

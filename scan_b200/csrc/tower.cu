@@ -595,8 +595,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
   extern __shared__ signed char slot_of[];     // [9][n_pairs]
   const int kinds = 9 * m_blocks * n_blocks;
   const int mb = blockIdx.z / n_blocks, nb = blockIdx.z - mb * n_blocks;
-  for (int i = threadIdx.x; i < 9 * n_pairs; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 9 * n_pairs; i += blockDim.x) {     // (only row blockIdx.x of the table is used by this block)
     const int tap = i / n_pairs, p = i - tap * n_pairs;
+    if (tap != (int)blockIdx.x) continue;
     const int kind = (mb * n_blocks + nb) * 9 + tap;
     int s = -1;
     for (int j = 0; j < period; ++j) {
@@ -613,7 +614,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
   const int c4 = threadIdx.x & 63, row = blockIdx.y * 4 + (threadIdx.x >> 6);
   const long long off = (long long)row * 256 + c4 * 4;
   const int co = mb * 256 + row, ci = nb * 256 + c4 * 4;
-  for (int tap = 0; tap < 9; ++tap) {
+  {
+    const int tap = blockIdx.x;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = 0; p < n_pairs; ++p) {
       const int sl = slot_of[tap * n_pairs + p];
@@ -837,9 +839,10 @@ extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_ro
     maps.a2[0][l] = maps.a2[0][0];
     maps.a2[1][l] = maps.a2[1][0];
   }
-  const int rows_per_tap = (n_out + 255) / 256 * 256;
+  const int rows_per_tap = (n_out + 255) / 256 * 256;     // the packed weight pads every tap to a multiple of 256 rows
+  const int bn = n_out <= 32 ? 32 : 256;                  // thin outputs (class maps): N = 32 MMAs, 48 cycles instead of 128
   g.n_tiles = tiles;
-  g.n_blocks = rows_per_tap / 256;
+  g.n_blocks = (n_out + bn - 1) / bn;
   g.k_chunks = cin / 32;
   g.k_chunks2 = cin2 / 32;
   g.n_terms = x_lo ? 3 : 1;
@@ -855,13 +858,14 @@ extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_ro
   g.addend = addend;
   g.mask = mask;
   g.relu = relu;
-  rc = conv_make_b_map(&maps.b[0], packed, 9ll * rows_per_tap, cin + cin2, 256 / cta_group);
+  rc = conv_make_b_map(&maps.b[0], packed, 9ll * rows_per_tap, cin + cin2, bn / cta_group);
   if (rc) return rc;
   maps.b[1] = maps.b[0];
   if (packed_lo) {
-    rc = conv_make_b_map(&maps.b[1], packed_lo, 9ll * rows_per_tap, cin + cin2, 256 / cta_group);
+    rc = conv_make_b_map(&maps.b[1], packed_lo, 9ll * rows_per_tap, cin + cin2, bn / cta_group);
     if (rc) return rc;
   }
+  if (bn == 32) return cta_group == 2 ? conv_launch<2, 32>(maps, g, (cudaStream_t)stream) : conv_launch<1, 32>(maps, g, (cudaStream_t)stream);
   return cta_group == 2 ? conv_launch<2, 256>(maps, g, (cudaStream_t)stream) : conv_launch<1, 256>(maps, g, (cudaStream_t)stream);
 }
 
@@ -1026,7 +1030,7 @@ extern "C" int scan_conv3x3_wgrad(const scan_levels_t* levels, const float* x_ro
   cfg.attrs = at;
   cfg.numAttrs = 1;
   SCAN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, maps, g));
-  conv_wgrad_reduce_kernel<<<dim3(1, 64, (unsigned)(g.m_blocks * g.n_blocks)), 256, 9 * pairs, (cudaStream_t)stream>>>(
+  conv_wgrad_reduce_kernel<<<dim3(9, 64, (unsigned)(g.m_blocks * g.n_blocks)), 256, 9 * pairs, (cudaStream_t)stream>>>(
       g.partial, pairs, g.slots, g.period, g.n_items, g.m_blocks, g.n_blocks, s_co, s_ci, s_ky, s_kx, d_w);
   SCAN_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
   return SCAN_OK;

@@ -1513,3 +1513,95 @@ def thin_pack_maps(geo, maps, c0, k):
     if not maps.is_cuda or maps.dtype != torch.float32 or k > 32:
         raise RuntimeError("thin_pack_maps expects CUDA fp32 maps with at most 32 selected channels (no CPU fallback)")
     return _ThinPackMaps.apply(geo, maps, c0, k)
+
+
+# ----------------------------------------------------------------------------------------------------
+# head_out on the tower kernels: relu(conv3x3(cat([features, act_maps], 1)) + bias) without the concatenation (a12 / f1)
+# ----------------------------------------------------------------------------------------------------
+class _HeadOut(torch.autograd.Function):
+    """y = relu(conv3x3([F | maps]; W) + b) in ONE scan_conv3x3_rows2 launch (two input tensors, bias + ReLU epilogue), or -- when
+    the feature half u = conv3x3(F; W[:, :256]) has been enqueued earlier (multi-GPU: it hides the prototype all-reduce) --
+    y = relu(conv3x3(maps; W[:, 256:]) + u + b) with u as the epilogue's addend.
+    Backward: d_pre = dy * [y > 0] and d_b (scan_add_relu_bwd), d_maps by the N = 32 instantiation of the convolution kernel,
+    d_F / d_W[:, :256] (fused form only) and d_W[:, 256:] by the data- and weight-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, geo, weight, bias, fused, n_levels, *tensors):
+        precise = CONV["precise"]
+        first = tensors[:n_levels]                 # fused: the feature levels; else: the early feature half u
+        acts = [a.contiguous() for a in tensors[n_levels:]]
+        k = acts[0].shape[1]
+        dev = acts[0].device
+        lo = (lambda t: tf32_residual(t)) if precise else (lambda t: None)
+        maps32 = torch.empty((geo.R, 32), device=dev, dtype=torch.float32)
+        call("scan_thin_pack", geo.ref(), _ptr_array(acts), k, 0, k, _ptr(maps32), 32, _stream())
+        m_lo = lo(maps32)
+        y_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
+        bias = bias.contiguous()
+        first_rows = _rows_of_levels(geo, list(first))
+        f_lo = None
+        if fused:
+            hi, wlo = conv3x3_pack(weight, False, precise)
+            f_lo = lo(first_rows)
+            call("scan_conv3x3_rows2", geo.ref(), _ptr(first_rows), _ptr(f_lo), C, _ptr(maps32), _ptr(m_lo), 32, _ptr(hi), _ptr(wlo), C,
+                 _ptr(bias), None, None, 1, _ptr(y_rows), C, CONV["cta_group"], _stream())
+        else:
+            hi, wlo = conv3x3_pack(weight[:, C:], False, precise)
+            call("scan_conv3x3_rows2", geo.ref(), _ptr(maps32), _ptr(m_lo), 32, None, None, 0, _ptr(hi), _ptr(wlo), C, _ptr(bias),
+                 _ptr(first_rows), None, 1, _ptr(y_rows), C, CONV["cta_group"], _stream())
+        ctx.geo, ctx.precise, ctx.fused, ctx.n_levels, ctx.k = geo, precise, fused, n_levels, k
+        ctx.save_for_backward(weight, y_rows, first_rows if fused else y_rows, *acts)
+        ctx.f_lo = f_lo
+        return tuple(level_views(geo, y_rows))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *d_levels):
+        geo, precise, fused, n_levels, k = ctx.geo, ctx.precise, ctx.fused, ctx.n_levels, ctx.k
+        weight, y_rows, f_rows = ctx.saved_tensors[:3]
+        acts = list(ctx.saved_tensors[3:])
+        dev = y_rows.device
+        lo = (lambda t: tf32_residual(t)) if precise else (lambda t: None)
+        views = level_views(geo, y_rows)
+        dys = [nhwc_dense(g) if g is not None else torch.zeros_like(v) for g, v in zip(d_levels, views)]
+        d_pre = torch.empty_like(y_rows)
+        d_bias = torch.empty((C,), device=dev, dtype=torch.float32)
+        ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
+        call("scan_add_relu_bwd", geo.ref(), _ptr_array(dys), _ptr(y_rows), _ptr(d_pre), _ptr(d_bias), _ptr(ws), ws.numel(), _stream())
+        d_pre_lo = lo(d_pre)
+        # d(maps): thin data gradient (N = 32 tile), back to per-level NCHW
+        hi, wlo = conv3x3_pack(weight[:, C:], True, precise)
+        d_maps32 = torch.empty((geo.R, 32), device=dev, dtype=torch.float32)
+        call("scan_conv3x3_rows2", geo.ref(), _ptr(d_pre), _ptr(d_pre_lo), C, None, None, 0, _ptr(hi), _ptr(wlo), k, None, None, None, 0,
+             _ptr(d_maps32), 32, CONV["cta_group"], _stream())
+        d_acts = [torch.empty((geo.n_images, k, h, w), device=dev, dtype=torch.float32) for h, w in geo.shapes]
+        call("scan_thin_unpack", geo.ref(), _ptr(d_maps32), 32, k, 0, k, 1.0, _ptr_array(d_acts), _stream())
+        # weight gradient: the map columns through the 256-wide kernel on a zero-padded copy of the maps
+        d_w = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+        maps256 = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
+        call("scan_thin_pack", geo.ref(), _ptr_array(acts), k, 0, k, _ptr(maps256), C, _stream())
+        d_wm = torch.empty((C, C, 3, 3), device=dev, dtype=torch.float32)
+        conv3x3_wgrad_raw(geo, maps256, d_pre, x_lo=lo(maps256), dy_lo=d_pre_lo, out=d_wm)
+        d_w[:, C:] = d_wm[:, :k]
+        if fused:
+            conv3x3_wgrad_raw(geo, f_rows, d_pre, x_lo=ctx.f_lo if precise else None, dy_lo=d_pre_lo, out=d_w[:, :C])
+            hi, wlo = conv3x3_pack(weight[:, :C], True, precise)
+            d_f = conv3x3_rows_raw(geo, d_pre, hi, C, x_lo=d_pre_lo, packed_lo=wlo)
+            d_first = tuple(level_views(geo, d_f))
+        else:
+            d_first = tuple(level_views(geo, d_pre))        # the early feature half receives d_pre unchanged
+        return (None, d_w, d_bias, None, None) + d_first + tuple(d_acts)
+
+
+def head_out_levels(geo, weight, bias, acts, features=None, us=None):
+    """head_out's single convolution + ReLU on the tower kernels; exactly one of `features` (fused form) / `us` (early feature half)."""
+    if (features is None) == (us is None):
+        raise RuntimeError("head_out_levels takes either the feature levels or the early feature half")
+    k = acts[0].shape[1]
+    if weight.shape[0] != C or weight.shape[1] != C + k or k > 32:
+        raise RuntimeError("head_out_levels is built for a [256, 256 + K <= 32, 3, 3] weight")
+    first = list(features if features is not None else us)
+    for t in first + list(acts):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError("head_out_levels needs CUDA fp32 tensors (no CPU fallback)")
+    return list(_HeadOut.apply(geo, weight, bias, features is not None, len(first), *first, *acts))

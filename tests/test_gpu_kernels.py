@@ -949,3 +949,39 @@ def test_cka_discriminator_matches_reference_golden(name, golden_dir):
     # the benchmark arithmetic (single-pass TF32 convolutions): same loss within the TF32 bound
     loss_fast = m(d["feat"].to(DEV), d["target"], act_maps=d["act"].to(DEV), domain=d["domain"])
     assert abs(float(loss_fast) - want) <= 5e-3 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("k", [9, 2])
+def test_head_out_levels_matches_fp64(fused, k):
+    """head_out on the tower kernels (two-input convolution with bias + ReLU epilogue; N = 32 data gradient for the maps): output
+    and every gradient against torch's fp64 conv2d(cat([features, maps], 1)); 3xTF32 mode, 1e-4 of each tensor's max."""
+    torch.manual_seed(6)
+    shapes, n = [(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 2
+    geo = ops.Geometry(shapes, STRIDES, n)
+    feats = [torch.randn(n, 256, h, w, device=DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for h, w in shapes]
+    acts = [torch.softmax(torch.randn(n, k, h, w, device=DEV), 1).requires_grad_(True) for h, w in shapes]
+    weight = (torch.randn(256, 256 + k, 3, 3, device=DEV) * 0.03).requires_grad_(True)
+    bias = (torch.randn(256, device=DEV) * 0.1).requires_grad_(True)
+    cots = [torch.randn(n, 256, h, w, device=DEV) for h, w in shapes]
+    saved = ops.CONV["precise"]
+    ops.CONV["precise"] = True
+    try:
+        if fused:
+            ys = ops.head_out_levels(geo, weight, bias, acts, features=feats)
+        else:
+            us = ops.conv3x3_levels(geo, weight[:, :256], feats)
+            ys = ops.head_out_levels(geo, weight, bias, acts, us=us)
+        torch.autograd.backward(ys, cots)
+    finally:
+        ops.CONV["precise"] = saved
+    got = [y.detach() for y in ys] + [f.grad for f in feats] + [a.grad for a in acts] + [weight.grad, bias.grad]
+    f64 = [f.detach().double().requires_grad_(True) for f in feats]
+    a64 = [a.detach().double().requires_grad_(True) for a in acts]
+    w64, b64 = weight.detach().double().requires_grad_(True), bias.detach().double().requires_grad_(True)
+    y64 = [torch.relu(torch.nn.functional.conv2d(torch.cat([f, a], 1), w64, b64, padding=1)) for f, a in zip(f64, a64)]
+    torch.autograd.backward(y64, [c.double() for c in cots])
+    want = [y.detach() for y in y64] + [f.grad for f in f64] + [a.grad for a in a64] + [w64.grad, b64.grad]
+    for i, (g, w_) in enumerate(zip(got, want)):
+        scale = float(w_.abs().max())
+        assert float((g.double() - w_).abs().max()) <= 1e-4 * scale, (i, float((g.double() - w_).abs().max()), scale)
