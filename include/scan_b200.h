@@ -357,6 +357,13 @@ int scan_conv3x3_wgrad(const scan_levels_t* lv, const float* x_rows, const float
                        const float* dy_lo, int32_t cout, float* d_w, int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* the class-map columns of head_out's weight gradient: d_w[co][k][ky][kx] (element strides; co < 256, k < K, 9 K <= 128) =
+ * sum_p dy_rows[p, co] * maps32[p + off, k].  The maps are spread to [R, 128] (one column per (class, tap)) and reduced against
+ * dy_rows by ONE MN-major tcgen05 GEMM over the pixels.  dy_lo non-NULL: 3xTF32.  Deterministic. */
+int64_t scan_thin_wgrad_workspace_bytes(const scan_levels_t* lv, int32_t precise);
+int scan_thin_wgrad(const scan_levels_t* lv, const float* maps32, const float* dy_rows, const float* dy_lo, int32_t k, float* d_w,
+                    int64_t s_co, int64_t s_k, int64_t s_ky, int64_t s_kx, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- f3: thin kernels of the CKA discriminator FCOSDiscriminator_con (modeling/discriminator/fcos_head_discriminator_con.py:88-127,
  *      layer.py:6-24); its convolutions are scan_conv3x3_rows2 / scan_conv3x3_wgrad ---------------------------------------------
  * scan_thin_pack: channels [c0, c0 + k) of per-level NCHW maps [N, k_total, H_l, W_l] (HOST array of device pointers) -> rows

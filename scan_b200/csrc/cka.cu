@@ -15,21 +15,25 @@ struct ThinArgs {
 };
 
 // NCHW channels [c0, c0 + k) -> rows [R, ld] columns [0, k); columns [k, ld) are zero-filled.  ld % 4 == 0.
+// One thread per float4 of the output (consecutive threads = consecutive 16-byte pieces of a row: coalesced writes).
 __global__ void __launch_bounds__(256) thin_pack_kernel(Levels lv, ThinArgs a, int k_total, int c0, int k, float* __restrict__ rows, int ld) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = ld >> 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long g = t / q;
   if (g >= lv.row_off[lv.n_levels]) return;
-  const int l = level_of_row(lv, g);
-  const long long hw = (long long)lv.h[l] * lv.w[l];
-  const long long local = g - lv.row_off[l];
-  const long long n = local / hw, p = local - n * hw;
-  const float* src = a.nchw[l] + (n * k_total + c0) * hw + p;
-  float* dst = rows + g * ld;
-  for (int j4 = 0; j4 < ld; j4 += 4) {
-    float v[4];
+  const int j4 = (int)(t - g * q) * 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (j4 < k) {
+    const int l = level_of_row(lv, g);
+    const long long hw = (long long)lv.h[l] * lv.w[l];
+    const long long local = g - lv.row_off[l];
+    const long long n = local / hw, p = local - n * hw;
+    const float* src = a.nchw[l] + (n * k_total + c0) * hw + p;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = (j4 + e < k) ? __ldg(src + (long long)(j4 + e) * hw) : 0.f;
-    *reinterpret_cast<float4*>(dst + j4) = make_float4(v[0], v[1], v[2], v[3]);
+    for (int e = 0; e < 4; ++e)
+      if (j4 + e < k) v[e] = __ldg(src + (long long)(j4 + e) * hw);
   }
+  *reinterpret_cast<float4*>(rows + g * ld + j4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // rows [R, ld] columns [0, k) * scale -> NCHW channels [c0, c0 + k) (the other channels are the caller's: zero-initialised)
@@ -203,7 +207,7 @@ extern "C" int scan_thin_pack(const scan_levels_t* levels, const void* const* nc
   rc = thin_args(lv, nchw_host, &a);
   if (rc) return rc;
   const long long R = lv.row_off[lv.n_levels];
-  thin_pack_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(lv, a, k_total, c0, k, rows, ld);
+  thin_pack_kernel<<<(unsigned)ceil_div(R * (ld / 4), 256), 256, 0, (cudaStream_t)stream>>>(lv, a, k_total, c0, k, rows, ld);
   SCAN_LAUNCH_CHECK("thin_pack_kernel");
   return SCAN_OK;
 }

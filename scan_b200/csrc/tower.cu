@@ -429,7 +429,8 @@ struct WgArgs {
   WgLevel lv[SCAN_MAX_LEVELS];
   int n_chunks, seg_len, n_seg;
   int n_terms;
-  int m_blocks, n_blocks;   // 256-wide blocks of co / ci
+  int n_taps;               // 9: the convolution's taps (X read at shifted positions); 1: X is read in place
+  int m_blocks, n_blocks;   // 256-wide blocks of co / (64 NB)-wide blocks of ci
   int n_items;              // n_seg * 9 * m_blocks * n_blocks
   int period, slots;        // distinct (tap, block) kinds a pair meets; slots = min(period, items per pair)
   float* partial;           // [pairs][slots][256][256]
@@ -440,11 +441,16 @@ __device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
+// NB = 32-channel blocks of the X operand each CTA stages (4: the 256-wide convolution; 2: the 128-wide tap-spread class maps)
+template <int NB>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgArgs g) {
+  constexpr int WN = 64 * NB;                           // output columns of the pair's tile
+  constexpr int X_BYTES = NB * 4096;
+  constexpr int STAGE = WG_OP_BYTES + X_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = smem;
-  uint64_t* bars = (uint64_t*)(stages + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(stages + WG_STAGES * STAGE);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + WG_STAGES;
   uint64_t* acc_full = bars + 2 * WG_STAGES;
@@ -454,8 +460,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int kinds = 9 * g.m_blocks * g.n_blocks;
-  constexpr uint32_t IDESC = umma_idesc_tf32(256, 256) | (1u << 15) | (1u << 16);
+  const int kinds = g.n_taps * g.m_blocks * g.n_blocks;
+  constexpr uint32_t IDESC = umma_idesc_tf32(256, WN) | (1u << 15) | (1u << 16);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < WG_STAGES; ++i) {
@@ -484,10 +490,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_
       uint32_t phase = 0;
       for (int it = pair; it < g.n_items; it += n_pairs) {
         const int kind = it % kinds, seg = it / kinds;
-        const int tap = kind % 9, nb = (kind / 9) % g.n_blocks, mb = kind / (9 * g.n_blocks);
-        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+        const int tap = kind % g.n_taps, nb = (kind / g.n_taps) % g.n_blocks, mb = kind / (g.n_taps * g.n_blocks);
+        const int dy = g.n_taps == 9 ? tap / 3 - 1 : 0, dx = g.n_taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
         const int c0 = seg * g.seg_len, c1 = min(c0 + g.seg_len, g.n_chunks);
-        const int a_cb = mb * 8 + (int)rank * 4, b_cb = nb * 8 + (int)rank * 4;     // first 32-channel block of this CTA's half
+        const int a_cb = mb * 8 + (int)rank * 4, b_cb = nb * 2 * NB + (int)rank * NB;     // first 32-channel block of this CTA's half
         // position of the segment's first chunk; stepped incrementally afterwards (one thread feeds a 512-cycle stage)
         int l0 = 0;
 #pragma unroll
@@ -504,9 +510,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_
             const int x0 = cx * L.cw, y0 = cy * L.ch;
             mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
             uint32_t fb = smem_u32(full_bar + stage);
-            if (rank == 0) mbar_expect_tx(fb, 2 * WG_STAGE_BYTES);
+            if (rank == 0) mbar_expect_tx(fb, 2 * STAGE);
             fb = mapa_shared(fb, 0);
-            const uint32_t dst = smem_u32(stages + stage * WG_STAGE_BYTES);
+            const uint32_t dst = smem_u32(stages + stage * STAGE);
             cv_tma_5d_pair(dst, &maps.dy[pa][l], fb, 0, x0, y0, a_cb, n);
             cv_tma_5d_pair(dst + WG_OP_BYTES, &maps.x[pb][l], fb, 0, x0 + dx, y0 + dy, b_cb, n);
             if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
@@ -533,11 +539,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_
         const int buf = j & 1;
         mbar_wait(smem_u32(acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d = tmem_base + buf * 256;
+        const uint32_t d = tmem_base + buf * WN;
         for (int i = 0; i < k_iters; ++i) {
           mbar_wait(smem_u32(full_bar + stage), phase);
           tcgen05_fence_after();
-          const uint32_t a = smem_u32(stages + stage * WG_STAGE_BYTES), b = a + WG_OP_BYTES;
+          const uint32_t a = smem_u32(stages + stage * STAGE), b = a + WG_OP_BYTES;
 #pragma unroll
           for (int k = 0; k < WG_KB / 8; ++k) cv_mma<2>(d, umma_desc_mn32(a + k * 1024), umma_desc_mn32(b + k * 1024), IDESC, (i | k) != 0);
           cv_commit<2>(smem_u32(empty_bar + stage));
@@ -555,12 +561,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_
       const int buf = j & 1;
       const int slot = j % g.period;
       const bool first = j < g.period;
-      float* out = g.partial + ((long long)pair * g.slots + slot) * WG_TILE + (long long)((int)rank * 128 + q * 32 + lane) * 256;
+      float* out = g.partial + ((long long)pair * g.slots + slot) * (256 * WN) + (long long)((int)rank * 128 + q * 32 + lane) * WN;
       mbar_wait(smem_u32(acc_full + buf), (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
-      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + buf * WN;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < WN / 32; ++c) {
         float v[32];
         cv_ld32(tl + c * 32, v);
 #pragma unroll
@@ -629,6 +635,45 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
     o[2 * s_ci] = s.z;
     o[3 * s_ci] = s.w;
   }
+}
+
+// ---------------------------------------------------------------------------- thin weight gradient (the K class-map columns)
+//     dW[co][256 + k][tap] = sum_p dY[p, co] * maps[p + off(tap), k]                     K * 9 <= 128
+// The maps are first spread to S[p, k * 9 + tap] = maps[p + off(tap), k] (zero outside the image; [R, 128], 1/8 of dY's size),
+// which turns the nine shifted products into ONE MN-major GEMM dY^T . S over the pixels: conv_wgrad_kernel<2> with a single
+// "tap" -- dY is read once instead of nine times and the tensor core works on 128 useful columns instead of 9 of 256.
+__global__ void __launch_bounds__(256) thin_spread_kernel(Levels lv, const float* __restrict__ maps32, int k, float* __restrict__ s) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long g = t >> 5;
+  if (g >= lv.row_off[lv.n_levels]) return;
+  const int c0 = (int)(t & 31) * 4;
+  const int l = level_of_row(lv, g);
+  const int w = lv.w[l], h = lv.h[l];
+  const long long local = g - lv.row_off[l];
+  const int hw = h * w;
+  const int p = (int)(local % hw);
+  const int y = p / w, x = p - y * w;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = c0 + e, kk = c / 9, tap = c - kk * 9;
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    v[e] = (kk < k && yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(maps32 + (g + (long long)(yy - y) * w + (xx - x)) * 32 + kk) : 0.f;
+  }
+  *reinterpret_cast<float4*>(s + g * 128 + c0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// d_w[co][k][ky][kx] (element strides) = sum over the pairs' slot-0 tiles [256][128], pair order ascending
+__global__ void __launch_bounds__(256) thin_wgrad_reduce_kernel(const float* __restrict__ partial, int n_pairs, int slots, int k,
+                                                                long long s_co, long long s_k, long long s_ky, long long s_kx,
+                                                                float* __restrict__ d_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (co, col)
+  const int co = i >> 7, col = i & 127;
+  if (co >= 256 || col >= 9 * k) return;
+  float s = 0.f;
+  for (int p = 0; p < n_pairs; ++p) s += __ldg(partial + (long long)p * slots * (256 * 128) + co * 128 + col);
+  const int kk = col / 9, tap = col - kk * 9;
+  d_w[co * s_co + kk * s_k + (tap / 3) * s_ky + (tap % 3) * s_kx] = s;
 }
 
 // ---------------------------------------------------------------------------- operand preparation
@@ -898,8 +943,8 @@ static void wg_pick_chunk(int h, int w, int* ch_out, int* cw_out) {
 static int wg_gcd(int a, int b) { return b == 0 ? a : wg_gcd(b, a % b); }
 
 // the static schedule shared by the workspace query and the launch
-static int wg_plan(const Levels& lv, int cin, int cout, int precise, WgArgs* g, int* pairs_out) {
-  if (cin < 256 || (cin % 256) || cout < 256 || (cout % 256)) return SCAN_EINVAL;
+static int wg_plan(const Levels& lv, int cin, int cout, int precise, WgArgs* g, int* pairs_out, int n_taps = 9, int x_width = 256) {
+  if (cin < x_width || (cin % x_width) || cout < 256 || (cout % 256)) return SCAN_EINVAL;
   g->n_levels = lv.n_levels;
   g->n_images = lv.n_images;
   int chunks = 0;
@@ -918,9 +963,10 @@ static int wg_plan(const Levels& lv, int cin, int cout, int precise, WgArgs* g, 
   }
   g->n_chunks = chunks;
   g->n_terms = precise ? 3 : 1;
+  g->n_taps = n_taps;
   g->m_blocks = cout / 256;
-  g->n_blocks = cin / 256;
-  const int kinds = 9 * g->m_blocks * g->n_blocks;
+  g->n_blocks = cin / x_width;
+  const int kinds = n_taps * g->m_blocks * g->n_blocks;
   int pairs = sm_count() / 2;
   if (pairs < 1) pairs = 1;
   // segments: accumulation chains of at most 512 k-chunks (8 x 3 terms = 96 MMAs in the fp32-accurate mode: the tensor core
@@ -950,7 +996,7 @@ static int wg_plan(const Levels& lv, int cin, int cout, int precise, WgArgs* g, 
   return SCAN_OK;
 }
 
-static int wg_make_map(CUtensorMap* m, const float* base, int c, int w, int h, int n, int cw, int ch) {
+static int wg_make_map(CUtensorMap* m, const float* base, int c, int w, int h, int n, int cw, int ch, int box_blocks = 4) {
   EncodeTiledFn enc;
   int rc = get_tensormap_encoder(&enc);
   if (rc) return rc;
@@ -959,7 +1005,7 @@ static int wg_make_map(CUtensorMap* m, const float* base, int c, int w, int h, i
   // channels lands as [block][pixel][32], the MN-major operand layout
   cuuint64_t dims[5] = {32, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(c / 32), (cuuint64_t)n};
   cuuint64_t strides[4] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, 128, (cuuint64_t)h * w * c * 4};
-  cuuint32_t box[5] = {32, (cuuint32_t)cw, (cuuint32_t)ch, 4, 1};
+  cuuint32_t box[5] = {32, (cuuint32_t)cw, (cuuint32_t)ch, (cuuint32_t)box_blocks, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1016,7 +1062,7 @@ extern "C" int scan_conv3x3_wgrad(const scan_levels_t* levels, const float* x_ro
   }
   static unsigned long long attr = 0;
   if (first_use_on_device(&attr))
-    SCAN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(pairs * 2));
   cfg.blockDim = dim3(CV_THREADS);
@@ -1029,9 +1075,85 @@ extern "C" int scan_conv3x3_wgrad(const scan_levels_t* levels, const float* x_ro
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  SCAN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, maps, g));
+  SCAN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<4>, maps, g));
   conv_wgrad_reduce_kernel<<<dim3(9, 64, (unsigned)(g.m_blocks * g.n_blocks)), 256, 9 * pairs, (cudaStream_t)stream>>>(
       g.partial, pairs, g.slots, g.period, g.n_items, g.m_blocks, g.n_blocks, s_co, s_ci, s_ky, s_kx, d_w);
   SCAN_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
+  return SCAN_OK;
+}
+
+extern "C" int64_t scan_thin_wgrad_workspace_bytes(const scan_levels_t* levels, int32_t precise) {
+  Levels lv;
+  if (make_levels(levels, &lv)) return -1;
+  WgArgs g = {};
+  int pairs = 0;
+  if (wg_plan(lv, 128, 256, precise, &g, &pairs, 1, 128)) return -1;
+  const int64_t R = lv.row_off[lv.n_levels];
+  return (int64_t)pairs * g.slots * 256 * 128 * 4 + R * 128 * 4 * (precise ? 2 : 1) + 1024;
+}
+
+// d_w[co][k][ky][kx] (element strides s_*; the map columns of head_out's weight gradient) from dy_rows [R, 256] and the class maps
+// maps32 [R, 32] (columns [0, k), 9 k <= 128).  dy_lo non-NULL: 3xTF32.
+extern "C" int scan_thin_wgrad(const scan_levels_t* levels, const float* maps32, const float* dy_rows, const float* dy_lo, int32_t k,
+                               float* d_w, int64_t s_co, int64_t s_k, int64_t s_ky, int64_t s_kx, void* workspace, int64_t workspace_bytes,
+                               void* stream) {
+  Levels lv;
+  int rc = make_levels(levels, &lv);
+  if (rc) return rc;
+  if (!maps32 || !dy_rows || !d_w || !workspace || k < 1 || 9 * k > 128 || ((uintptr_t)workspace & 15)) return SCAN_EINVAL;
+  const int precise = dy_lo != nullptr;
+  if (workspace_bytes < scan_thin_wgrad_workspace_bytes(levels, precise)) return SCAN_EINVAL;
+  WgArgs g = {};
+  int pairs = 0;
+  rc = wg_plan(lv, 128, 256, precise, &g, &pairs, 1, 128);
+  if (rc) return rc;
+  const long long R = lv.row_off[lv.n_levels];
+  cudaStream_t st = (cudaStream_t)stream;
+  g.partial = (float*)workspace;
+  float* s = g.partial + (long long)pairs * g.slots * 256 * 128;
+  float* s_lo = precise ? s + R * 128 : nullptr;
+  thin_spread_kernel<<<(unsigned)ceil_div(R * 32, 256), 256, 0, st>>>(lv, maps32, k, s);
+  SCAN_LAUNCH_CHECK("thin_spread_kernel");
+  if (precise) {
+    long long blocks = ceil_div(R * 32, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tf32_residual_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(s), R * 32, reinterpret_cast<float4*>(s_lo));
+    SCAN_LAUNCH_CHECK("tf32_residual_kernel");
+  }
+  WgMaps maps;
+  for (int l = 0; l < SCAN_MAX_LEVELS; ++l) {
+    const int ll = l < lv.n_levels ? l : 0;
+    const WgLevel& L = g.lv[ll];
+    rc = wg_make_map(&maps.dy[0][l], dy_rows + lv.row_off[ll] * 256, 256, lv.w[ll], lv.h[ll], lv.n_images, L.cw, L.ch, 4);
+    if (rc) return rc;
+    rc = wg_make_map(&maps.x[0][l], s + lv.row_off[ll] * 128, 128, lv.w[ll], lv.h[ll], lv.n_images, L.cw, L.ch, 2);
+    if (rc) return rc;
+    maps.dy[1][l] = maps.dy[0][l];
+    maps.x[1][l] = maps.x[0][l];
+    if (precise) {
+      rc = wg_make_map(&maps.dy[1][l], dy_lo + lv.row_off[ll] * 256, 256, lv.w[ll], lv.h[ll], lv.n_images, L.cw, L.ch, 4);
+      if (rc) return rc;
+      rc = wg_make_map(&maps.x[1][l], s_lo + lv.row_off[ll] * 128, 128, lv.w[ll], lv.h[ll], lv.n_images, L.cw, L.ch, 2);
+      if (rc) return rc;
+    }
+  }
+  static unsigned long long attr = 0;
+  if (first_use_on_device(&attr))
+    SCAN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pairs * 2));
+  cfg.blockDim = dim3(CV_THREADS);
+  cfg.dynamicSmemBytes = WG_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SCAN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<2>, maps, g));
+  thin_wgrad_reduce_kernel<<<(256 * 128) / 256, 256, 0, st>>>(g.partial, pairs, g.slots, k, s_co, s_k, s_ky, s_kx, d_w);
+  SCAN_LAUNCH_CHECK("thin_wgrad_reduce_kernel");
   return SCAN_OK;
 }

@@ -1550,7 +1550,7 @@ class _HeadOut(torch.autograd.Function):
             call("scan_conv3x3_rows2", geo.ref(), _ptr(maps32), _ptr(m_lo), 32, None, None, 0, _ptr(hi), _ptr(wlo), C, _ptr(bias),
                  _ptr(first_rows), None, 1, _ptr(y_rows), C, CONV["cta_group"], _stream())
         ctx.geo, ctx.precise, ctx.fused, ctx.n_levels, ctx.k = geo, precise, fused, n_levels, k
-        ctx.save_for_backward(weight, y_rows, first_rows if fused else y_rows, *acts)
+        ctx.save_for_backward(weight, y_rows, first_rows if fused else y_rows, maps32, *acts)
         ctx.f_lo = f_lo
         return tuple(level_views(geo, y_rows))
 
@@ -1558,8 +1558,8 @@ class _HeadOut(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, *d_levels):
         geo, precise, fused, n_levels, k = ctx.geo, ctx.precise, ctx.fused, ctx.n_levels, ctx.k
-        weight, y_rows, f_rows = ctx.saved_tensors[:3]
-        acts = list(ctx.saved_tensors[3:])
+        weight, y_rows, f_rows, maps32 = ctx.saved_tensors[:4]
+        acts = list(ctx.saved_tensors[4:])
         dev = y_rows.device
         lo = (lambda t: tf32_residual(t)) if precise else (lambda t: None)
         views = level_views(geo, y_rows)
@@ -1576,13 +1576,22 @@ class _HeadOut(torch.autograd.Function):
              _ptr(d_maps32), 32, CONV["cta_group"], _stream())
         d_acts = [torch.empty((geo.n_images, k, h, w), device=dev, dtype=torch.float32) for h, w in geo.shapes]
         call("scan_thin_unpack", geo.ref(), _ptr(d_maps32), 32, k, 0, k, 1.0, _ptr_array(d_acts), _stream())
-        # weight gradient: the map columns through the 256-wide kernel on a zero-padded copy of the maps
+        # weight gradient of the map columns: tap-spread maps x d_pre as one MN-major GEMM (scan_thin_wgrad); more than 14 classes
+        # fall back to the 256-wide kernel on a zero-padded copy of the maps
         d_w = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-        maps256 = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
-        call("scan_thin_pack", geo.ref(), _ptr_array(acts), k, 0, k, _ptr(maps256), C, _stream())
-        d_wm = torch.empty((C, C, 3, 3), device=dev, dtype=torch.float32)
-        conv3x3_wgrad_raw(geo, maps256, d_pre, x_lo=lo(maps256), dy_lo=d_pre_lo, out=d_wm)
-        d_w[:, C:] = d_wm[:, :k]
+        if 9 * k <= 128:
+            nbytes = _lib.lib().scan_thin_wgrad_workspace_bytes(geo.ref(), int(precise))
+            ws2 = _workspace("thin_wgrad", nbytes, dev)
+            d_wm = d_w[:, C:]
+            s = d_wm.stride()
+            call("scan_thin_wgrad", geo.ref(), _ptr(maps32), _ptr(d_pre), _ptr(d_pre_lo), k, _ptr(d_wm), s[0], s[1], s[2], s[3], _ptr(ws2),
+                 nbytes, _stream())
+        else:
+            maps256 = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
+            call("scan_thin_pack", geo.ref(), _ptr_array(acts), k, 0, k, _ptr(maps256), C, _stream())
+            d_wm = torch.empty((C, C, 3, 3), device=dev, dtype=torch.float32)
+            conv3x3_wgrad_raw(geo, maps256, d_pre, x_lo=lo(maps256), dy_lo=d_pre_lo, out=d_wm)
+            d_w[:, C:] = d_wm[:, :k]
         if fused:
             conv3x3_wgrad_raw(geo, f_rows, d_pre, x_lo=ctx.f_lo if precise else None, dy_lo=d_pre_lo, out=d_w[:, :C])
             hi, wlo = conv3x3_pack(weight[:, :C], True, precise)
