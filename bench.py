@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--images", type=int, default=8, help="source images (= target images) per GPU per step")
     ap.add_argument("--settle", type=int, default=6, help="untimed source steps that fill the paradigm buffer before the fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cooldown", type=float, default=0.0, help="idle seconds before the end-to-end loop (diagnostics)")
+    ap.add_argument("--sustained", type=float, default=4.0, help="seconds of the back-to-back steady-state run (0: skip)")
     ap.add_argument("--dropout", type=float, default=0.1, help="attention dropout (reference train-mode value 0.1)")
     ap.add_argument("--config", default="c2f", choices=["c2f", "sim10k", "kitti-eval"])
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-torch-on-GPU run of the oracle port")
@@ -82,6 +84,24 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
 
     def run(self):
+        # NVML in-process (one init, ~20 us per query) instead of spawning `nvidia-smi` (an NVML initialisation per sample)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for nm, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -89,18 +109,23 @@ class ClockSampler(threading.Thread):
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
+                self.samples.append((time.perf_counter(), float(out[0])))
                 self.max_mhz = float(out[1])
                 for nm, v in zip(names, out[2:]):
                     if "Active" in v and "Not" not in v:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.5)
 
-    def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+    def median(self, windows=None):
+        s = sorted(v for t, v in self.samples if windows is None or any(a <= t <= b for a, b in windows))
+        return s[len(s) // 2] if s else None
+
+    def summary(self, windows=None):
+        """windows: [(t0, t1)] perf_counter spans of the timed regions; the median is taken over the samples inside them."""
+        m = self.median(windows)
+        return {"sm_mhz": m if m is not None else self.median(), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
 def bind_to_gpu_numa_node(index):
@@ -321,8 +346,12 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         "add_relu_bwd": ("hbm", 2 * R * 2 * row),
         # tower convolutions (csrc/tower.cu): 3 layers (2 head_in + the feature half of head_out) on R rows per pass; forward and
         # data gradient share scan_conv3x3_rows, the weight gradient is scan_conv3x3_wgrad
-        "conv3x3_rows": ("tensor", 2 * 3 * 2 * (2 * R * 256 * 256 * 9)),     # passes x layers x (fprop + dgrad) x flops
+        # per pass: head_in fprop x 2 + data gradients x 3 (head_in x 2, head_out's feature columns) through scan_conv3x3_rows;
+        # head_out's fused two-input forward (288 input channels) + the thin data gradient into the K maps through _rows2
+        "conv3x3_rows": ("tensor", 2 * 5 * (2 * R * 256 * 256 * 9)),
+        "conv3x3_rows2": ("tensor", 2 * (2 * R * 288 * 256 * 9 + 2 * R * 256 * k * 9)),
         "conv3x3_wgrad": ("tensor", 2 * 3 * (2 * R * 256 * 256 * 9)),
+        "thin_wgrad": ("tensor", 2 * (2 * R * 256 * k * 9)),
         "condconv_fwd": ("hbm", 2 * R * (row + 4 * k) + R * 8),        # rows + K maps (+ labels on the source pass)
         "condconv_bwd": ("hbm", 2 * R * (2 * row + 2 * 4 * k)),        # rows read, d_rows written, maps + map gradients
         "gather_rows": ("hbm", ms * 2 * row),
@@ -351,9 +380,15 @@ def traffic_of(kernel):
 
 
 # entry point -> the kernel that dominates it (the name the ncu capture and the roofline line report)
-DOMINANT_KERNEL = {"conv3x3_rows": "conv3x3_kernel", "conv3x3_wgrad": "conv_wgrad_kernel", "attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_levels_span": "db_adj_tc_kernel",
+DOMINANT_KERNEL = {"conv3x3_rows": "conv3x3_kernel", "conv3x3_rows2": "conv3x3_kernel", "conv3x3_wgrad": "conv_wgrad_kernel",
+                   "thin_wgrad": "conv_wgrad_kernel", "attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_levels_span": "db_adj_tc_kernel",
                    "condconv_fwd": "condconv_fwd_ts_kernel", "condconv_bwd": "condconv_bwd_rows_kernel", "gn_relu_bwd": "gn_bwd_apply_kernel",
                    "gn_relu_fwd": "gn_apply_kernel", "qkv_fwd": "gemm3x_kernel", "qkv_bwd": "gemm3x_kernel"}
+
+
+def condgraph_towers():
+    from scan_b200 import condgraph
+    return condgraph.TOWERS["impl"]
 
 
 def main():
@@ -419,6 +454,8 @@ def main():
         dist.broadcast(module.prototype, 0)
     state0 = {k_: v.detach().clone() for k_, v in module.state_dict().items()}
     counter0 = module.counter_rnn.counter if hasattr(module, "counter_rnn") else None
+    proto0 = module.prototype.detach().clone()
+    counters0 = {nm: getattr(module, nm).counter for nm in ("counter_rnn", "counter") if hasattr(getattr(module, nm, None), "counter")}
     g = torch.Generator().manual_seed(5)
     # the module returns channels-last feature tensors; the FCOS head that consumes them hands back gradients in the same
     # memory format (cuDNN's backward-data follows its input), so the stand-in cotangents are channels-last as well
@@ -438,6 +475,14 @@ def main():
                 torch.cuda.current_stream().wait_event(ready[0])
             _, probs = eval_step(module, feats_s, cls_logits, mode)
             return [torch.stack([p_.reshape(-1)[0] for p_ in probs])]
+        # Every step starts from the SAME paradigm state (a 27 KB device copy on the step's stream, inside the timed region): the
+        # benchmarked step is then exactly the parity-tested one (tests/test_gpu_module.py::test_benchmark_configuration_n8_every_
+        # element).  Without an optimizer in the loop the EMA drifts on the fixed synthetic inputs, the maps grow more confident
+        # every step and the DBSCAN point count -- O(n^2) work -- climbs from 39 k to 47 k+ within 40 steps (measured: 21 -> 47
+        # ms/step over 80 steps, plus a workspace regrow every ~20).
+        module.prototype.copy_(proto0, non_blocking=True)
+        for name_, c_ in counters0.items():
+            getattr(module, name_).counter = c_
         return one_step(module, feats_s, src_t, feats_t, cots, ready=ready)
 
     def barrier():
@@ -467,6 +512,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     host_t0 = time.perf_counter()
+    timed_windows = []
     host_prof = None
     if os.environ.get("SCAN_HOST_PROFILE") == "1":      # diagnostics: where the host spends a step (never set for a reported number)
         import cProfile
@@ -481,6 +527,7 @@ def main():
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host time to enqueue a step (incl. its sync points)
     e1.record()
     barrier()
+    timed_windows.append((host_t0, time.perf_counter()))
     if profiling:
         torch.cuda.profiler.stop()
     launches = _lib.CALLS["launches"]
@@ -534,7 +581,13 @@ def main():
     bufs = [[[torch.empty(f.shape, device=dev) for f in hs] for hs in host_sets] for _ in range(2)]
     consumed = [None, None]   # event: the step that read buffer set b has finished
 
+    no_stage = {"on": False}      # diagnostics only (SCAN_E2E_NOSTAGE=1): the timed e2e loop without its H2D copies
+
     def stage(b):
+        if no_stage["on"]:
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            return [ev] * len(host_sets)
         with torch.cuda.stream(copy_stream):
             if consumed[b] is not None:
                 copy_stream.wait_event(consumed[b])
@@ -567,6 +620,12 @@ def main():
         consumed[0].record(main_stream)
     barrier()
     consumed = [None, None]
+    if args.cooldown > 0:
+        time.sleep(args.cooldown)
+    if os.environ.get("SCAN_E2E_NOSTAGE") == "1":
+        stage(1)
+        torch.cuda.synchronize()
+        no_stage["on"] = True
     e2e_marks = [time.perf_counter()]
     # result read-back: every step's losses are copied to pinned host memory inside the timed region and READ one step later
     # (after the next step has been enqueued), the way a training loop logs its loss without draining the queue every step
@@ -602,8 +661,40 @@ def main():
     host = [float(h_.sum()) for h_ in pending[1]]
     f1.record()
     barrier()
+    timed_windows.append((e2e_marks[0], time.perf_counter()))
     ms_e2e = f0.elapsed_time(f1)
     e2e_dev_ms = [round(a_.elapsed_time(b2), 2) for a_, b2 in zip(step_evs[:-1], step_evs[1:])]
+    # ---------------- sustained: device-resident steps back to back for args.sustained seconds, the last second averaged ----------------
+    sustained = None
+    if args.sustained > 0 and not is_eval:
+        barrier()
+        marks = []
+        t_sus0 = time.perf_counter()
+        t_end = t_sus0 + args.sustained
+        while time.perf_counter() < t_end:
+            step_dev([f.detach() for f in src_d], [f.detach() for f in tgt_d])
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
+        torch.cuda.synchronize()
+        per = [a_.elapsed_time(b2) for a_, b2 in zip(marks[:-1], marks[1:])]
+        if os.environ.get("SCAN_SUSTAINED_DIAG") == "1":
+            print("sustained per-step ms:", [round(v, 1) for v in per], file=sys.stderr)
+            print("memory allocated / reserved MB:", torch.cuda.memory_allocated() >> 20, torch.cuda.memory_reserved() >> 20,
+                  "num_alloc_retries", torch.cuda.memory_stats().get("num_alloc_retries"), "cudaMalloc count",
+                  torch.cuda.memory_stats().get("num_device_alloc"), file=sys.stderr)
+        tail, acc = [], 0.0
+        for v in reversed(per):
+            tail.append(v)
+            acc += v
+            if acc >= 1000.0:
+                break
+        if tail:
+            sustained = {"value": 2 * n * world * len(tail) / (acc / 1e3), "unit": "images/s", "ms_per_step": acc / len(tail),
+                         "max_ms": max(per), "steps": len(per), "seconds": args.sustained,
+                         "sm_mhz": sampler.median([(t_sus0 + args.sustained - 1.0, time.perf_counter())]),
+                         "what": "device-resident steps back to back for %.0f s (steady state under the power cap), mean of the last "
+                                 "second; max_ms = the slowest single step of the run" % args.sustained}
     sampler.stop_flag = True
     h2d = sum(f.numel() * 4 for hs in host_sets for f in hs)
 
@@ -618,6 +709,16 @@ def main():
     if rank == 0:
         hbm_peak, peak_src = peaks()
         # ---- per-entry-point roofline table: algorithmic work of one step / CUDA-event time of the entry point in the step
+        # tensor-pipe denominator: half of the driver-measured bf16 burst rate (a tf32 MMA runs at half the bf16 rate) or, if larger,
+        # the cuBLAS tf32 8192^3 rate measured in this process -- the tower convolution kernel EXCEEDS the latter
+        half_bf16 = None
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp):
+            half_bf16 = 0.5 * float(json.load(open(mp)).get("bf16_tflops", 0.0)) or None
+        tensor_peak = max(x for x in (tf32_peak, half_bf16) if x)
+        tensor_src = ("0.5 x MEASURED_PEAKS.json bf16_tflops (burst) = %.1f; cuBLAS tf32 8192^3 measured in this process: %.1f"
+                      % (half_bf16, tf32_peak)) if half_bf16 and tensor_peak == half_bf16 else \
+            "cuBLAS tf32 8192^3 measured in this process (MEASURED_PEAKS recipe)"
         table = []
         if not is_eval:
             work = work_model(n, k_cls, m_src, m_tgt, db_points, module.transfer_cfg[0] is not None or module.with_self_training)
@@ -628,19 +729,20 @@ def main():
                 if bound == "hbm":
                     ach, peak, unit = amount / (t_ms * 1e-3) / 1e9, hbm_peak, "GB/s"
                 else:
-                    ach, peak, unit = amount / (t_ms * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
+                    ach, peak, unit = amount / (t_ms * 1e-3) / 1e12, tensor_peak, "TFLOP/s"
                 table.append({"entry": name, "bound": bound, "algorithmic": amount, "ms_per_step": t_ms, "achieved": ach, "peak": peak,
                               "unit": unit, "frac": ach / peak})
             table.sort(key=lambda r: -r["ms_per_step"])
         roofline = None
         if table:
-            top = table[0]
+            # the dominant entry: `*_span` rows are fork -> join spans of side streams (they include waiting for whatever the main
+            # stream runs meanwhile), not kernel time
+            top = ([r for r in table if not r["entry"].endswith("_span")] or table)[0]
             kern = DOMINANT_KERNEL.get(top["entry"], top["entry"])
             roofline = {"kernel": kern, "entry": top["entry"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
                         "unit": top["unit"], "frac": top["frac"], "traffic": traffic_of(kern), "traffic_unit": "bytes/launch",
                         "algorithmic_per_step": top["algorithmic"], "ms_per_step": top["ms_per_step"],
-                        "peak_source": ("cuBLAS tf32 8192^3 measured in this process (MEASURED_PEAKS recipe)" if top["bound"] == "tensor"
-                                        else peak_src),
+                        "peak_source": tensor_src if top["bound"] == "tensor" else peak_src,
                         "note": "achieved = algorithmic flops (1x, not the 3x of 3xTF32) of the entry point per step / its CUDA-event time; "
                                 "the entry includes its small pre-pass kernels",
                         "table": table}
@@ -657,15 +759,19 @@ def main():
                 eager = {"unavailable": repr(e)[:200]}
         line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core kernels, fp32 accumulate; tower convolutions cuDNN tf32)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core kernels: 3xTF32 with fp32 accumulate; 3x3 tower convolutions single-pass TF32 = torch's cuDNN default)",
                 "data": "synthetic",
                 "config": {"workload": workload, "name": args.config,
                            "parallelism": "dp%d (image shards, prototype all-reduce)" % world, "settle_steps": args.settle,
                            "attention_dropout": args.dropout,
-                           "towers": "3x3 convolutions = cuDNN NHWC tf32 implicit GEMM (torch's default allow_tf32 = the reference's own GPU "
-                                     "arithmetic), cudnn.benchmark %s; parity runs force fp32 towers, the error at THESE flags is "
-                                     "recorded by tests/test_gpu_module.py::test_benchmark_flags_cudnn_tf32_error_is_reported"
-                                     % ("on" if torch.backends.cudnn.benchmark else "off"),
+                           "stationary": "the paradigm buffer is restored before every step (27 KB device copy inside the timed region): "
+                                         "each step is the parity-tested step; without it the EMA drifts on the fixed inputs and the DBSCAN "
+                                         "point count grows step by step",
+                           "towers": ("3x3 convolutions = scan_b200 tcgen05 implicit GEMM (csrc/tower.cu), single-pass TF32 = what cuDNN runs "
+                                      "under torch's default allow_tf32, the reference's own GPU arithmetic; parity runs use its 3xTF32 "
+                                      "mode, the error at THESE flags is recorded by "
+                                      "tests/test_gpu_module.py::test_benchmark_flags_cudnn_tf32_error_is_reported")
+                                     if condgraph_towers() == "scan" else "3x3 convolutions = cuDNN NHWC tf32 (SCAN_B200_TOWERS=cudnn, A/B run)",
                            "e2e_input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i"
                                                  + ("; process bound to the GPU's NUMA node %s before pinning" % numa_node if numa_node is not None else ""),
                            "l2_note": "inputs %d MB per pass exceed the 126 MB L2" % (n * L_PER_IMAGE * 1024 // 2 ** 20)},
@@ -674,7 +780,7 @@ def main():
                         "device_ms_per_step": e2e_dev_ms,
                         "h2d_alone_ms_per_step": h2d_alone_ms,
                         "result_read": "pinned, non-blocking, consumed one step later (every step's result is read inside the timed region)"},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+                "sustained": sustained, "gpu_launches": launches, "clocks": sampler.summary(timed_windows), "roofline": roofline, "cpu_baseline": cpu,
                 "eager_gpu_baseline": eager, "tf32_peak_tflops_measured": tf32_peak, "hbm_peak_gbs": hbm_peak,
                 "kernel_ms_per_step": {k_: v["ms"] / kernel_steps for k_, v in kernel_ms.items()},
                 "source_nodes": m_src, "target_nodes": m_tgt, "dbscan_points_per_level": db_points,

@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
     }
   }
   tcgen05_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();                               // CTA-level: the allocator's write of tmem_slot, the barrier inits
+  if constexpr (CG == 2) cluster_sync_all();     // pair-level: the peer's barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_wgrad_kernel(const __grid_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
   tcgen05_fence_before();
+  __syncthreads();
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;

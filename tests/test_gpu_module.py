@@ -153,9 +153,10 @@ def test_benchmark_configuration_sim10k_n8():
 
 
 def test_benchmark_flags_cudnn_tf32_error_is_reported(bench_like):
-    """bench.py leaves torch's default cudnn.allow_tf32 = True for the tower convolutions (the reference's own GPU
-    behaviour); parity runs force true fp32.  This run uses the BENCH flags: integer results must still be bit-exact
-    up to the first tf32-induced label flip, and the float error is recorded (gpurun_out/parity_tf32_flags.json)."""
+    """bench.py runs the tower convolutions (csrc/tower.cu) in single-pass TF32 -- the arithmetic cuDNN uses for them under torch's
+    default cudnn.allow_tf32 = True, i.e. the reference's own GPU behaviour; parity runs use their 3xTF32 mode.  This run uses the
+    BENCH flags: integer results must still be bit-exact up to the first tf32-induced label flip, and the float error is
+    recorded (gpurun_out/parity_tf32_flags.json)."""
     from scan_b200.condgraph import build_condgraph
     prepared, loader, want = bench_like
     prep_src = (prepared[0], dict(prepared[1], steps=["source"]), prepared[2], prepared[3], prepared[4])
