@@ -347,9 +347,11 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         # tower convolutions (csrc/tower.cu): 3 layers (2 head_in + the feature half of head_out) on R rows per pass; forward and
         # data gradient share scan_conv3x3_rows, the weight gradient is scan_conv3x3_wgrad
         # per pass: head_in fprop x 2 + data gradients x 3 (head_in x 2, head_out's feature columns) through scan_conv3x3_rows;
-        # head_out's fused two-input forward (288 input channels) + the thin data gradient into the K maps through _rows2
+        # head_out's fused two-input forward (288 input channels) through _rows2; the thin data gradient into the K maps is one
+        # scan_gemm_nt (3xTF32) of d_pre against the [9 K, 256] weight slice + a tap gather
         "conv3x3_rows": ("tensor", 2 * 5 * (2 * R * 256 * 256 * 9)),
-        "conv3x3_rows2": ("tensor", 2 * (2 * R * 288 * 256 * 9 + 2 * R * 256 * k * 9)),
+        "conv3x3_rows2": ("tensor", 2 * (2 * R * 288 * 256 * 9)),
+        "gemm_nt": ("tensor", 2 * (2 * R * 256 * k * 9)),
         "conv3x3_wgrad": ("tensor", 2 * 3 * (2 * R * 256 * 256 * 9)),
         "thin_wgrad": ("tensor", 2 * (2 * R * 256 * k * 9)),
         "condconv_fwd": ("hbm", 2 * R * (row + 4 * k) + R * 8),        # rows + K maps (+ labels on the source pass)

@@ -374,6 +374,9 @@ int scan_thin_pack(const scan_levels_t* lv, const void* const* nchw_host, int32_
 int scan_thin_unpack(const scan_levels_t* lv, const float* rows, int32_t ld, int32_t k_total, int32_t c0, int32_t k, float scale,
                      void* const* nchw_host, void* stream);
 int scan_scale(const float* x, int64_t n, float scale, float* y, void* stream);
+/* thin data gradient of a 3x3 convolution with K <= 14 input channels: d [R, ldd] = dY . W[:, k, tap]^T (one scan_gemm_nt of the
+ * pixel rows against the [K * 9, C] weight slice, column k * 9 + tap); out32[p, k] = sum_tap d[p - off(tap), k * 9 + tap]. */
+int scan_thin_gather(const scan_levels_t* lv, const float* d, int32_t ldd, int32_t k, float* out32, void* stream);
 int64_t scan_colsum_workspace_bytes(int64_t n_rows, int32_t n_cols);
 int scan_colsum(const float* x, int64_t n_rows, int32_t n_cols, int32_t ld, float* out, void* workspace, int64_t workspace_bytes,
                 void* stream);

@@ -50,6 +50,30 @@ __global__ void __launch_bounds__(256) thin_unpack_kernel(Levels lv, ThinArgs a,
   for (int j = 0; j < k; ++j) dst[(long long)j * hw] = scale * __ldg(src + j);
 }
 
+// Inverse of the tap spread (tower.cu): out32[p, k] = sum_tap d[p - off(tap), k * 9 + tap] over the neighbours inside the image.
+// d [R, ldd] holds, per pixel q, the K * 9 products "what q sends to its neighbour through tap" (one GEMM of the pixel rows
+// against the [K * 9, C] weight slice); gathering them is the thin data gradient of a 3x3 convolution with K <= 14 inputs.
+__global__ void __launch_bounds__(256) thin_gather_kernel(Levels lv, const float* __restrict__ d, int ldd, int k, float* __restrict__ out32) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long g = t >> 5;
+  if (g >= lv.row_off[lv.n_levels]) return;
+  const int kk = (int)(t & 31);
+  float s = 0.f;
+  if (kk < k) {
+    const int l = level_of_row(lv, g);
+    const int w = lv.w[l], h = lv.h[l];
+    const long long local = g - lv.row_off[l];
+    const int p = (int)(local % ((long long)h * w));
+    const int y = p / w, x = p - y * w;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += __ldg(d + (g + (long long)(yy - y) * w + (xx - x)) * ldd + kk * 9 + tap);
+    }
+  }
+  out32[g * 32 + kk] = s;
+}
+
 __global__ void __launch_bounds__(256) scale_kernel(const float4* __restrict__ x, long long n4, float scale, float4* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = __ldg(x + i);
@@ -283,5 +307,17 @@ extern "C" int scan_cka_bce_bwd(const float* logits, int32_t ldl, const float* w
   bce_bwd_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(logits, ldl, weights, ldw, n_rows, n_cls, target, weighted,
                                                                                    inv, d_loss, dl32, dl_wide, ld_wide);
   SCAN_LAUNCH_CHECK("bce_bwd_kernel");
+  return SCAN_OK;
+}
+
+// out32 [R, 32] (columns >= k zero) = tap gather of d [R, ldd] (columns k * 9 + tap), see thin_gather_kernel
+extern "C" int scan_thin_gather(const scan_levels_t* levels, const float* d, int32_t ldd, int32_t k, float* out32, void* stream) {
+  Levels lv;
+  int rc = make_levels(levels, &lv);
+  if (rc) return rc;
+  if (!d || !out32 || k < 1 || k > 32 || ldd < 9 * k) return SCAN_EINVAL;
+  const long long R = lv.row_off[lv.n_levels];
+  thin_gather_kernel<<<(unsigned)ceil_div(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(lv, d, ldd, k, out32);
+  SCAN_LAUNCH_CHECK("thin_gather_kernel");
   return SCAN_OK;
 }

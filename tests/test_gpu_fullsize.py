@@ -127,3 +127,47 @@ def test_attention_full_size_dropout_fwd_bwd_consistent(m):
         scale = float(b.abs().max())
         err = float((a - b).abs().max())
         assert err <= 5e-5 * scale + 2e-5, "%s: max|d|=%.3e scale=%.3e" % (name, err, scale)
+
+
+def test_tower_convolution_at_benchmark_geometry():
+    """The tower convolution kernels at the size bench.py launches them (five levels of the 800x1344 pyramid, 8 images, 179 200
+    pixels per launch; 2 928 / 2 CTA-pair tiles over 74 pairs, 5 863 32-pixel chunks in the weight gradient): forward, data
+    gradient and weight gradient in the benchmark's single-pass TF32 arithmetic against torch's fp32 convolution (the TF32 bound:
+    11-bit inputs, 2 304 products per output) and in 3xTF32 against the same at fp32 accuracy."""
+    from scan_b200 import ops
+    torch.manual_seed(11)
+    shapes, n = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)], 8
+    geo = ops.Geometry(shapes, [8, 16, 32, 64, 128], n)
+    x = torch.randn(geo.R, 256, device="cuda")
+    dy = torch.randn(geo.R, 256, device="cuda")
+    w = (torch.randn(256, 256, 3, 3, device="cuda") * 0.02)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xs = [t.detach().requires_grad_(True) for t in ops.level_views(geo, x)]
+        wr = w.detach().requires_grad_(True)
+        ys = [torch.nn.functional.conv2d(t, wr, None, padding=1) for t in xs]
+        gs = ops.level_views(geo, dy)
+        grads = torch.autograd.grad(ys, xs + [wr], gs)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    y_ref = torch.cat([y.detach().permute(0, 2, 3, 1).reshape(-1, 256) for y in ys])
+    dx_ref = torch.cat([g.permute(0, 2, 3, 1).reshape(-1, 256) for g in grads[:5]])
+    # the weight gradient sums 179 200 products per entry: the fp32 reference is itself off by ~6e-5 of the maximum, take fp64
+    xs64 = [t.detach().double() for t in ops.level_views(geo, x)]
+    w64 = w.detach().double().requires_grad_(True)
+    ys64 = [torch.nn.functional.conv2d(t, w64, None, padding=1) for t in xs64]
+    (dw_ref,) = torch.autograd.grad(ys64, [w64], [g.double() for g in gs])
+    for precise, tol in ((False, 2e-3), (True, 2e-5)):
+        hi, lo = ops.conv3x3_pack(w, False, precise)
+        hit, lot = ops.conv3x3_pack(w, True, precise)
+        x_lo = ops.tf32_residual(x) if precise else None
+        dy_lo = ops.tf32_residual(dy) if precise else None
+        y = ops.conv3x3_rows_raw(geo, x, hi, 256, x_lo=x_lo, packed_lo=lo)
+        dx = ops.conv3x3_rows_raw(geo, dy, hit, 256, x_lo=dy_lo, packed_lo=lot)
+        dw = ops.conv3x3_wgrad_raw(geo, x, dy, x_lo=x_lo, dy_lo=dy_lo)
+        for name, got, ref in (("y", y, y_ref), ("dx", dx, dx_ref), ("dw", dw, dw_ref)):
+            err = float((got.double() - ref.double()).abs().max()) / float(ref.abs().max())
+            assert err <= tol, "%s precise=%s: %.3e" % (name, precise, err)
+    assert torch.equal(dw, ops.conv3x3_wgrad_raw(geo, x, dy, x_lo=x_lo, dy_lo=dy_lo))      # fixed reduction order

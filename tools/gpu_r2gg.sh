@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout -k 10 "$TMO" "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?"; tail -n "${TAILN:-6}" gpurun_out/$name.log | cut -c1-300; }
+TMO=600 TAILN=4 run gg_kern python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -q -m gpu --tb=short -k "head_out_levels or tower_convolution or conv3x3 or cka"
+TMO=1200 TAILN=4 run gg_module python -m pytest tests/test_gpu_module.py -q -m gpu --tb=short
+TMO=900 TAILN=1 run gg_bench_n1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-baseline
+python - <<'PY'
+import json
+d=json.loads([x for x in open("gpurun_out/gg_bench_n1.log") if x.startswith("{")][-1])
+print(round(d["value"],1), round(d["ms_per_step"],2), round(d["e2e"]["value"],1), d["clocks"], d.get("sustained") and round(d["sustained"]["value"],1))
+print({k:v for k,v in d["roofline"].items() if k not in ("table","note","peak_source")})
+for r in d["roofline"]["table"][:14]: print("  ", r["entry"], round(r["ms_per_step"],3), round(r["achieved"],1), r["unit"], round(r["frac"],3))
+PY
