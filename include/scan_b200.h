@@ -197,6 +197,12 @@ int scan_condconv_bwd(const scan_levels_t* lv, const float* rows, const float* w
                       const void* const* d_act_nchw_host, const int64_t* labels, float loss_scale,
                       const float* d_loss, float* d_rows, float* d_weight, float* d_bias, void* workspace,
                       int64_t workspace_bytes, void* stream);
+/* the same with accumulate_rows != 0: d_rows already holds the gradient of a LATER consumer of the same rows (head_out's data
+ * gradient) and this call adds its own in place — the sum autograd would otherwise form with a separate full-size add. */
+int scan_condconv_bwd2(const scan_levels_t* lv, const float* rows, const float* weight, int32_t num_classes, int32_t act_mode,
+                       const void* const* act_nchw_host, const void* const* d_act_nchw_host, const int64_t* labels, float loss_scale,
+                       const float* d_loss, float* d_rows, int32_t accumulate_rows, float* d_weight, float* d_bias, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 
 /* ---- K4a: paradigm manifestation, RNN variant (condgraph.py:313-336 get_conded_weight with USE_RNN:
  *      nn.RNN(I->H, 2 layers, tanh) over the P paradigm slots of the K classes, then the (P x 1)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "scan_condconv_fwd": (c_int32, [_LV, _P, _P, _P, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
     "scan_condconv_bwd_workspace_bytes": (c_int64, [_LV, c_int32]),
     "scan_condconv_bwd": (c_int32, [_LV, _P, _P, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
+    "scan_condconv_bwd2": (c_int32, [_LV, _P, _P, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, c_int32, _P, _P, _P, c_int64, _P]),
     "scan_manifest_rnn_saved_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "scan_manifest_rnn_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "scan_manifest_rnn_fwd": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, c_int32] + [_P] * 13),
@@ -127,7 +128,7 @@ SIGNATURES = {
 _lib = None
 # kernels each entry point launches (memsets excluded): bench.py's gpu_launches is counted from this table
 LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_upload_small": 1, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_unpack_levels": 1, "scan_fcos_assign": 1, "scan_fcos_assign_reg": 1, "scan_fcos_loss_fwd": 2, "scan_fcos_loss_bwd": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
-            "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_attn_fwd": 5, "scan_attn_bwd": 4,
+            "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_condconv_bwd2": 3, "scan_attn_fwd": 5, "scan_attn_bwd": 4,
             "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
             "scan_qkv_fwd": 1, "scan_qkv_bwd": 9, "scan_attn_out_ln_fwd": 1, "scan_attn_out_ln_bwd": 9, "scan_node_cls_fwd": 3,
             "scan_node_cls_bwd": 9, "scan_class_mean_bwd": 1,

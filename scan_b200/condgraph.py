@@ -323,21 +323,37 @@ class GRAPHModule(nn.Module):
         geo = ops.Geometry.of(features, self.fpn_strides)
         return _tower_conv(geo, wf, None, features)
 
-    def features_post_processing(self, features, act_maps, us=None):
-        """head_out(cat([features, act_maps], 1)) without materialising the concatenation (SURVEY 8f rank 1): the first
-        convolution is split into its 256 feature columns (channels-last, NHWC kernels) and its K map columns.
-        us: the feature half when the caller has already enqueued it (head_out_feature_half)."""
+    def _head_out_on_tower_kernels(self):
         if not self.with_concated_maps:
-            return features
+            return False
         layers = list(self.head_out.middle_tower)
         conv = layers[0]
-        if (TOWERS["impl"] == "scan" and len(layers) == 2 and isinstance(layers[1], nn.ReLU) and conv.weight.shape[0] == ops.C
-                and conv.bias is not None):
+        return (TOWERS["impl"] == "scan" and len(layers) == 2 and isinstance(layers[1], nn.ReLU) and conv.weight.shape[0] == ops.C
+                and conv.bias is not None)
+
+    def features_post_processing(self, features, act_maps, us=None, rows=None, through=False):
+        """head_out(cat([features, act_maps], 1)) without materialising the concatenation (SURVEY 8f rank 1): the first
+        convolution is split into its 256 feature columns (channels-last, NHWC kernels) and its K map columns.
+        us: the feature half when the caller has already enqueued it (head_out_feature_half).
+        rows: the [R,256] rows matrix of `features` as the autograd input of the fused form (the alias chain gather -> conditional
+        conv -> head_out, whose gradients meet inside kernel epilogues instead of autograd's add kernels); through=True returns
+        (levels, rows alias) for a consumer that comes after head_out."""
+        if not self.with_concated_maps:
+            return (features, rows) if through else features
+        layers = list(self.head_out.middle_tower)
+        conv = layers[0]
+        if self._head_out_on_tower_kernels():
             # the shipped form, entirely on the tower kernels: one launch over [features | maps] with bias + ReLU in its epilogue
             geo = ops.Geometry.of(features, self.fpn_strides)
+            if us is None and rows is not None:
+                return ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), rows=rows, through=through)
             if us is None:
-                return ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), features=list(features))
-            return ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), us=list(us))
+                out = ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), features=list(features))
+            else:
+                out = ops.head_out_levels(geo, conv.weight, conv.bias, list(act_maps), us=list(us))
+            return (out, rows) if through else out
+        if through:
+            return self.features_post_processing(features, act_maps, us=us), rows
         wa = conv.weight[:, ops.C:].contiguous(memory_format=torch.channels_last)
         if us is None:
             us = self.head_out_feature_half(features)
@@ -384,11 +400,15 @@ class GRAPHModule(nn.Module):
         if self.record:
             self.last["prototype_batch"], self.last["conded_weight"] = proto_batch, weight
         with_loss = self.act_loss_cfg in ("softmaxFL", "sigmoidFL")
-        acts, act_loss, flags = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode(),
-                                             labels if with_loss else None, self.lamda2)
+        # gather -> conditional conv -> head_out read the rows through a chain of aliases: each backward adds its gradient into the
+        # buffer the later consumer wrote (scatter-add / accumulate_rows / the convolution's addend), no full-size autograd sums
+        chain = self._head_out_on_tower_kernels() and "us" not in held and torch.is_grad_enabled()
+        res = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode(), labels if with_loss else None, self.lamda2,
+                           through=chain)
+        acts, act_loss, flags = res[:3]
         if self.record:
             self.last["act_loss_flags"] = flags
-        out = self.features_post_processing(features, acts, us=held.get("us"))
+        out = self.features_post_processing(features, acts, us=held.get("us"), rows=res[3] if chain else None)
         return out, (node_loss, 0), act_loss, acts
 
     def get_transfer_loss(self, tg_prototype, tg_nodes, tg_labels):
@@ -497,18 +517,26 @@ class GRAPHModule(nn.Module):
         geo = ops.Geometry.of(features, self.fpn_strides)
         rows = ops.join_rows(geo, features)
         weight, bias = self._split_kernel(self.get_conded_weight())   # identical at every level (condgraph.py:507)
-        acts, _, _ = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode())
+        # alias chain conditional conv -> head_out -> node gather (see _forward_train_source)
+        chain = self._head_out_on_tower_kernels() and torch.is_grad_enabled()
+        res = ops.condconv(geo, rows, weight, bias, self.used_num_classes, self._act_mode(), through=chain)
+        acts = res[0]
         # head_out needs the maps only: enqueue it between the fork and the join of the DBSCAN streams, ahead of the host read
         held = {}
+        grad_on = torch.is_grad_enabled()
 
         def head_out():
-            held["out"] = self.features_post_processing(features, acts)
+            with torch.set_grad_enabled(grad_on):
+                if chain:
+                    held["out"], held["rows"] = self.features_post_processing(features, acts, rows=res[3], through=True)
+                else:
+                    held["out"] = self.features_post_processing(features, acts)
 
         smp = self._sample_target(geo, rows, acts, between=head_out)
         self._record_nodes(geo, smp)
         out = held["out"]
         if smp.n_nodes > 0 and (self.transfer_cfg[0] is not None or self.with_self_training):
-            pos_points = ops.gather_rows(rows, smp.node_rows)
+            pos_points = ops.gather_rows(held.get("rows", rows), smp.node_rows)
             # the class means feed the transfer losses WITH gradient in the reference (condgraph.py:398, 526)
             node_loss, packed, nodes, tg_proto = self._forward_gcns(pos_points, smp.node_labels)
             node_loss = self.lamda4 * node_loss

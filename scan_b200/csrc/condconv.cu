@@ -260,10 +260,11 @@ __global__ void __launch_bounds__(256) condconv_dlogit_kernel(Levels lv, ConstAc
   }
 }
 
-template <int KP>
+// ACC: d_rows already holds the gradient of a later consumer of the same rows (head_out's data gradient): add to it in place
+template <int KP, bool ACC>
 __global__ void __launch_bounds__(CB_THREADS, 4) condconv_bwd_rows_kernel(const float* __restrict__ rows, const float* __restrict__ weight,
                                                                          const float* __restrict__ dzw, long long R, int num_tiles,
-                                                                         float* __restrict__ d_rows, float* __restrict__ partial_w) {
+                                                                         float* d_rows, float* __restrict__ partial_w) {
   constexpr int KS = (KP + 3) / 4 * 4;   // shared-memory row stride: whole float4s
   __shared__ __align__(16) float dzs[CB_ROWS * KS];
   const int c = threadIdx.x;
@@ -303,7 +304,10 @@ __global__ void __launch_bounds__(CB_THREADS, 4) condconv_bwd_rows_kernel(const 
           dx = fmaf(dz[k], w[k], dx);
           acc[k] = fmaf(dz[k], x[j], acc[k]);
         }
-        if (r0 + j < nrows) dr[(long long)(r0 + j) * CC_C] = dx;
+        if (r0 + j < nrows) {
+          if (ACC) dx += dr[(long long)(r0 + j) * CC_C];
+          dr[(long long)(r0 + j) * CC_C] = dx;
+        }
       }
     }
   }
@@ -431,10 +435,10 @@ extern "C" int64_t scan_condconv_bwd_workspace_bytes(const scan_levels_t* lvh, i
   return parts * 16 * scan::CC_C * 4 + parts * 16 * 4 + lv.row_off[SCAN_MAX_LEVELS] * num_classes * 4 + 512;
 }
 
-extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, const float* weight, int32_t num_classes,
-                                 int32_t act_mode, const void* const* act_nchw_host, const void* const* d_act_nchw_host,
-                                 const int64_t* labels, float loss_scale, const float* d_loss, float* d_rows, float* d_weight,
-                                 float* d_bias, void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int scan_condconv_bwd2(const scan_levels_t* lvh, const float* rows, const float* weight, int32_t num_classes,
+                                  int32_t act_mode, const void* const* act_nchw_host, const void* const* d_act_nchw_host,
+                                  const int64_t* labels, float loss_scale, const float* d_loss, float* d_rows, int32_t accumulate_rows,
+                                  float* d_weight, float* d_bias, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace scan;
   Levels lv;
   int rc = make_levels(lvh, &lv);
@@ -461,7 +465,10 @@ extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, co
   switch (num_classes) {
 #define SCAN_BWD_CASE(KP)                                                                                                \
   case KP:                                                                                                               \
-    condconv_bwd_rows_kernel<KP><<<parts, CB_THREADS, 0, st>>>(rows, weight, dzw, R, num_tiles, d_rows, pw);           \
+    if (accumulate_rows)                                                                                                 \
+      condconv_bwd_rows_kernel<KP, true><<<parts, CB_THREADS, 0, st>>>(rows, weight, dzw, R, num_tiles, d_rows, pw);    \
+    else                                                                                                                 \
+      condconv_bwd_rows_kernel<KP, false><<<parts, CB_THREADS, 0, st>>>(rows, weight, dzw, R, num_tiles, d_rows, pw);   \
     break;
     SCAN_BWD_CASE(1) SCAN_BWD_CASE(2) SCAN_BWD_CASE(3) SCAN_BWD_CASE(4) SCAN_BWD_CASE(5) SCAN_BWD_CASE(6) SCAN_BWD_CASE(7) SCAN_BWD_CASE(8)
     SCAN_BWD_CASE(9) SCAN_BWD_CASE(10) SCAN_BWD_CASE(11) SCAN_BWD_CASE(12) SCAN_BWD_CASE(13) SCAN_BWD_CASE(14) SCAN_BWD_CASE(15)
@@ -472,4 +479,12 @@ extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, co
   condconv_bwd_reduce_kernel<<<dim3(num_classes, CC_C / 32), 256, 0, st>>>(pw, pb, parts, parts_b, num_classes, d_weight, d_bias);
   SCAN_LAUNCH_CHECK("condconv_bwd_reduce_kernel");
   return SCAN_OK;
+}
+
+extern "C" int scan_condconv_bwd(const scan_levels_t* lvh, const float* rows, const float* weight, int32_t num_classes,
+                                 int32_t act_mode, const void* const* act_nchw_host, const void* const* d_act_nchw_host,
+                                 const int64_t* labels, float loss_scale, const float* d_loss, float* d_rows, float* d_weight,
+                                 float* d_bias, void* workspace, int64_t workspace_bytes, void* stream) {
+  return scan_condconv_bwd2(lvh, rows, weight, num_classes, act_mode, act_nchw_host, d_act_nchw_host, labels, loss_scale, d_loss, d_rows, 0,
+                            d_weight, d_bias, workspace, workspace_bytes, stream);
 }

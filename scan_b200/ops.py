@@ -649,8 +649,12 @@ CONDCONV_IMPL = {"impl": int(__import__("os").environ.get("SCAN_B200_CONDCONV_IM
 
 
 class _CondConv(torch.autograd.Function):
+    """through = True: `rows` is also handed on as an alias (last output).  A consumer that runs AFTER the conditional convolution
+    (head_out) reads the alias, so its dense d_rows arrives here and this backward adds its own gradient into that buffer inside
+    the kernel (scan_condconv_bwd2, accumulate_rows) -- instead of autograd summing two [R,256] gradients with an add kernel."""
+
     @staticmethod
-    def forward(ctx, geo, num_classes, act_mode, loss_weight, rows, weight, bias, labels):
+    def forward(ctx, geo, num_classes, act_mode, loss_weight, rows, weight, bias, labels, through=False):
         rows = rows.contiguous()
         weight = weight.contiguous()
         dev = rows.device
@@ -670,6 +674,10 @@ class _CondConv(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.save_for_backward(rows, weight, labels, *acts)
         ctx.mark_non_differentiable(flags)
+        ctx.through = bool(through)
+        if through:
+            ctx.set_materialize_grads(False)
+            return (loss, flags) + tuple(acts) + (rows,)
         return (loss, flags) + tuple(acts)
 
     @staticmethod
@@ -679,27 +687,38 @@ class _CondConv(torch.autograd.Function):
         acts = ctx.saved_tensors[3:]
         geo, k = ctx.geo, ctx.k
         dev = rows.device
+        d_alias = None
+        if ctx.through:
+            d_alias, d_acts = d_acts[-1], d_acts[:-1]
+            if d_loss is None and all(g is None for g in d_acts):      # nothing reached the maps or the loss: hand the alias' gradient on
+                return None, None, None, None, d_alias, None, None, None, None
         d_acts = [None if g is None else g.contiguous() for g in d_acts]
         # d(total)/d(act_loss) stays on the device (read by the kernel): no host sync in backward
         d_loss_dev = None
         if ctx.loss_scale != 0.0 and d_loss is not None:
             d_loss_dev = d_loss.to(torch.float32).reshape(1).contiguous()
-        d_rows = torch.empty_like(rows)
+        # d_alias is the fresh buffer the later consumer's backward just wrote (sole consumer of the alias): accumulate in place
+        acc = d_alias is not None
+        d_rows = (d_alias if d_alias.is_contiguous() else d_alias.contiguous()) if acc else torch.empty_like(rows)
         d_weight = torch.empty_like(weight)
         d_bias = torch.empty((k,), device=dev, dtype=torch.float32) if ctx.has_bias else None
         ws_bytes = _lib.lib().scan_condconv_bwd_workspace_bytes(geo.ref(), k)
         ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
-        call("scan_condconv_bwd", geo.ref(), _ptr(rows), _ptr(weight), k, ctx.act_mode, _ptr_array(acts),
-             _ptr_array(d_acts), _ptr(labels), ctx.loss_scale, _ptr(d_loss_dev), _ptr(d_rows), _ptr(d_weight),
+        call("scan_condconv_bwd2", geo.ref(), _ptr(rows), _ptr(weight), k, ctx.act_mode, _ptr_array(acts),
+             _ptr_array(d_acts), _ptr(labels), ctx.loss_scale, _ptr(d_loss_dev), _ptr(d_rows), int(acc), _ptr(d_weight),
              _ptr(d_bias), _ptr(ws), ws_bytes, _stream())
-        return None, None, None, None, d_rows, d_weight, d_bias, None
+        return None, None, None, None, d_rows, d_weight, d_bias, None, None
 
 
-def condconv(geo, rows, weight, bias, num_classes, act_mode, labels=None, loss_weight=1.0):
-    """Returns (act_maps: list of [N,K,H_l,W_l], loss or None, flags)."""
+def condconv(geo, rows, weight, bias, num_classes, act_mode, labels=None, loss_weight=1.0, through=False):
+    """Returns (act_maps: list of [N,K,H_l,W_l], loss or None, flags) and, with through=True, an alias of `rows` that every LATER
+    consumer of the rows must read (see _CondConv)."""
     if num_classes > _lib.SCAN_MAX_CLASSES:
         raise RuntimeError("used_num_classes > %d is not supported" % _lib.SCAN_MAX_CLASSES)
-    out = _CondConv.apply(geo, num_classes, act_mode, float(loss_weight), rows, weight, bias, labels)
+    out = _CondConv.apply(geo, num_classes, act_mode, float(loss_weight), rows, weight, bias, labels, bool(through))
+    if through:
+        loss, flags, acts, alias = out[0], out[1], list(out[2:-1]), out[-1]
+        return acts, (loss if labels is not None else None), flags, alias
     loss, flags, acts = out[0], out[1], list(out[2:])
     return acts, (loss if labels is not None else None), flags
 
@@ -1527,9 +1546,15 @@ class _HeadOut(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, geo, weight, bias, fused, n_levels, *tensors):
+        # n_levels > 0: `first` = that many per-level tensors (fused: the feature levels; else: the early feature half u);
+        # n_levels = 0 / -1: `first` = ONE [R,256] rows matrix (fused form); -1 additionally hands the rows on as an alias (last
+        # output) whose gradient -- from consumers that run after head_out -- enters the data-gradient kernel as its addend
         precise = CONV["precise"]
-        first = tensors[:n_levels]                 # fused: the feature levels; else: the early feature half u
-        acts = [a.contiguous() for a in tensors[n_levels:]]
+        rows_in = n_levels <= 0
+        ctx.rows_in, ctx.through = rows_in, n_levels < 0
+        n_first = 1 if rows_in else n_levels
+        first = tensors[:n_first]
+        acts = [a.contiguous() for a in tensors[n_first:]]
         k = acts[0].shape[1]
         dev = acts[0].device
         lo = (lambda t: tf32_residual(t)) if precise else (lambda t: None)
@@ -1538,7 +1563,7 @@ class _HeadOut(torch.autograd.Function):
         m_lo = lo(maps32)
         y_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
         bias = bias.contiguous()
-        first_rows = _rows_of_levels(geo, list(first))
+        first_rows = first[0].contiguous() if rows_in else _rows_of_levels(geo, list(first))
         f_lo = None
         if fused:
             hi, wlo = conv3x3_pack(weight, False, precise)
@@ -1552,12 +1577,20 @@ class _HeadOut(torch.autograd.Function):
         ctx.geo, ctx.precise, ctx.fused, ctx.n_levels, ctx.k = geo, precise, fused, n_levels, k
         ctx.save_for_backward(weight, y_rows, first_rows if fused else y_rows, maps32, *acts)
         ctx.f_lo = f_lo
+        if ctx.through:
+            ctx.set_materialize_grads(False)
+            return tuple(level_views(geo, y_rows)) + (first[0],)
         return tuple(level_views(geo, y_rows))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *d_levels):
         geo, precise, fused, n_levels, k = ctx.geo, ctx.precise, ctx.fused, ctx.n_levels, ctx.k
+        d_alias = None
+        if ctx.through:
+            d_alias, d_levels = d_levels[-1], d_levels[:-1]
+            if all(g is None for g in d_levels):
+                return (None,) * 5 + (d_alias,) + (None,) * len(ctx.saved_tensors[4:])
         weight, y_rows, f_rows, maps32 = ctx.saved_tensors[:4]
         acts = list(ctx.saved_tensors[4:])
         dev = y_rows.device
@@ -1602,17 +1635,29 @@ class _HeadOut(torch.autograd.Function):
         if fused:
             conv3x3_wgrad_raw(geo, f_rows, d_pre, x_lo=ctx.f_lo if precise else None, dy_lo=d_pre_lo, out=d_w[:, :C])
             hi, wlo = conv3x3_pack(weight[:, :C], True, precise)
-            d_f = conv3x3_rows_raw(geo, d_pre, hi, C, x_lo=d_pre_lo, packed_lo=wlo)
-            d_first = tuple(level_views(geo, d_f))
+            if d_alias is not None and not d_alias.is_contiguous():
+                d_alias = d_alias.contiguous()
+            d_f = conv3x3_rows_raw(geo, d_pre, hi, C, addend=d_alias, x_lo=d_pre_lo, packed_lo=wlo)
+            d_first = (d_f,) if ctx.rows_in else tuple(level_views(geo, d_f))
         else:
             d_first = tuple(level_views(geo, d_pre))        # the early feature half receives d_pre unchanged
         return (None, d_w, d_bias, None, None) + d_first + tuple(d_acts)
 
 
-def head_out_levels(geo, weight, bias, acts, features=None, us=None):
-    """head_out's single convolution + ReLU on the tower kernels; exactly one of `features` (fused form) / `us` (early feature half)."""
-    if (features is None) == (us is None):
-        raise RuntimeError("head_out_levels takes either the feature levels or the early feature half")
+def head_out_levels(geo, weight, bias, acts, features=None, us=None, rows=None, through=False):
+    """head_out's single convolution + ReLU on the tower kernels; exactly one of `features` (fused form, per-level tensors), `rows`
+    (fused form, the [R,256] rows matrix; through=True also returns an alias of it as last element for later consumers) and `us`
+    (early feature half)."""
+    if (features is None) + (us is None) + (rows is None) != 2:
+        raise RuntimeError("head_out_levels takes the feature levels, the rows matrix or the early feature half")
+    if rows is not None:
+        k = acts[0].shape[1]
+        if weight.shape[0] != C or weight.shape[1] != C + k or k > 32 or rows.shape[1] != C:
+            raise RuntimeError("head_out_levels is built for a [256, 256 + K <= 32, 3, 3] weight")
+        if not rows.is_cuda:
+            raise RuntimeError("head_out_levels needs CUDA fp32 tensors (no CPU fallback)")
+        out = list(_HeadOut.apply(geo, weight, bias, True, -1 if through else 0, rows, *acts))
+        return (out[:-1], out[-1]) if through else out
     k = acts[0].shape[1]
     if weight.shape[0] != C or weight.shape[1] != C + k or k > 32:
         raise RuntimeError("head_out_levels is built for a [256, 256 + K <= 32, 3, 3] weight")

@@ -985,3 +985,42 @@ def test_head_out_levels_matches_fp64(fused, k):
     for i, (g, w_) in enumerate(zip(got, want)):
         scale = float(w_.abs().max())
         assert float((g.double() - w_).abs().max()) <= 1e-4 * scale, (i, float((g.double() - w_).abs().max()), scale)
+
+
+def test_alias_chain_condconv_head_out_gather_matches_plain_autograd():
+    """The alias chain of the training branches (conditional conv hands the rows on, head_out reads them as one matrix and hands
+    them on again, the node gather comes last): every gradient must equal the plain formulation in which autograd sums the three
+    d_rows contributions itself (same kernels otherwise, so the comparison is tight: 1e-5 of each tensor's max)."""
+    torch.manual_seed(8)
+    shapes, n, k = [(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 2, 9
+    geo = ops.Geometry(shapes, STRIDES, n)
+    base = torch.randn(geo.R, 256, device=DEV)
+    w_cc = torch.randn(k, 256, device=DEV) * 0.05
+    w_ho = torch.randn(256, 256 + k, 3, 3, device=DEV) * 0.03
+    b_ho = torch.randn(256, device=DEV) * 0.1
+    idx = torch.randperm(geo.R, device=DEV)[:300].sort().values.to(torch.int32)
+    cot_y = [torch.randn(n, 256, h, w, device=DEV) for h, w in shapes]
+    cot_a = [torch.randn(n, k, h, w, device=DEV) * 0.1 for h, w in shapes]
+    cot_n = torch.randn(300, 256, device=DEV)
+    saved = ops.CONV["precise"]
+    ops.CONV["precise"] = True
+    results = []
+    try:
+        for chain in (True, False):
+            rows = base.clone().requires_grad_(True)
+            wc, wh, bh = (t.clone().requires_grad_(True) for t in (w_cc, w_ho, b_ho))
+            if chain:
+                acts, _, _, r1 = ops.condconv(geo, rows, wc, None, k, 0, through=True)
+                ys, r2 = ops.head_out_levels(geo, wh, bh, acts, rows=r1, through=True)
+                nodes = ops.gather_rows(r2, idx)
+            else:
+                acts, _, _ = ops.condconv(geo, rows, wc, None, k, 0)
+                ys = ops.head_out_levels(geo, wh, bh, acts, features=ops.level_views(geo, rows))
+                nodes = ops.gather_rows(rows, idx)
+            torch.autograd.backward(list(ys) + list(acts) + [nodes], cot_y + cot_a + [cot_n])
+            results.append([y.detach() for y in ys] + [rows.grad, wc.grad, wh.grad, bh.grad])
+    finally:
+        ops.CONV["precise"] = saved
+    for i, (a, b) in enumerate(zip(*results)):
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 1e-5 * scale, (i, float((a - b).abs().max()), scale)
