@@ -171,3 +171,38 @@ def test_tower_convolution_at_benchmark_geometry():
             err = float((got.double() - ref.double()).abs().max()) / float(ref.abs().max())
             assert err <= tol, "%s precise=%s: %.3e" % (name, precise, err)
     assert torch.equal(dw, ops.conv3x3_wgrad_raw(geo, x, dy, x_lo=x_lo, dy_lo=dy_lo))      # fixed reduction order
+
+
+def test_cka_discriminator_full_level_against_torch():
+    """f3 at the size the trainer calls it (P3 of the 800x1344 pyramid, 8 images, 8 conditional classes: the [R, 1024] hidden
+    maps are 550 MB): loss and d(feature) / d(act maps) against the same formulas in torch (cuDNN fp32) -- 3xTF32 mode: relative L2
+    2e-3 with at most 0.1 % ReLU-flip outliers; fast single-pass TF32 mode: relative L2 5e-2 (gross indexing errors would be O(1))."""
+    from scan_b200.discriminator import FCOSDiscriminator_con
+    torch.manual_seed(2)
+    n, h, w, k = 8, 100, 168, 9
+    m = FCOSDiscriminator_con(num_convs=2, num_classes=k, grad_reverse_lambda=0.5).cuda()
+    feat = torch.randn(n, 256, h, w, device="cuda").requires_grad_(True)
+    act = torch.softmax(torch.randn(n, k, h, w, device="cuda") * 2, 1).requires_grad_(True)
+    saved = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = orc.cka_discriminator_loss(dict(m.named_parameters()), feat, act, 0.1, k - 1, 2)
+        r_feat, r_act = torch.autograd.grad(ref, [feat, act])
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    keep = ops.CONV["precise"]
+    try:
+        # a flipped ReLU (pre-activation within rounding of zero) moves single gradient entries by a few % of the maximum even at
+        # fp32 accuracy: bound the fraction of such entries and the relative L2 error, not the max norm
+        for precise, tol_frac, tol_l2 in ((True, 1e-3, 2e-3), (False, 1.0, 5e-2)):
+            ops.CONV["precise"] = precise
+            loss = m(feat, 0.1, act_maps=act, domain="target")
+            g_feat, g_act = torch.autograd.grad(loss, [feat, act])
+            assert abs(float(loss.detach()) - float(ref.detach())) <= 2e-3 * abs(float(ref.detach()))
+            for got, want in ((g_feat, r_feat), (g_act, r_act)):
+                want = -0.5 * want                                   # gradient reversal, layer.py:19-24
+                frac = float(((got - want).abs() > 1e-2 * want.abs().max()).float().mean())
+                rel = float((got - want).norm() / want.norm())
+                assert frac <= tol_frac and rel <= tol_l2, (precise, frac, rel)
+    finally:
+        ops.CONV["precise"] = keep
