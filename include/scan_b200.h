@@ -355,6 +355,10 @@ int scan_conv3x3_rows2(const scan_levels_t* lv, const float* x_rows, const float
                        const float* x2_lo, int32_t cin2, const float* packed, const float* packed_lo, int32_t n_out, const float* bias,
                        const float* addend, const float* mask, int32_t relu, float* y_rows, int32_t ldo, int32_t cta_group, void* stream);
 
+/* y_rows [R, ldo] (first n_out columns) = act(x_rows [R, cin] . w^T + bias) on the same kernel with one tap (no shifted reads):
+ * w [256-padded rows, cin] row-major with zero rows beyond n_out; w_lo non-NULL (with x_lo): 3xTF32. */
+int scan_conv1x1_rows(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* w, const float* w_lo,
+                      int32_t n_out, const float* bias, int32_t relu, float* y_rows, int32_t ldo, int32_t cta_group, void* stream);
 /* weight gradient of the same convolution: d_w[co][ci][ky][kx] (element strides s_*) = sum_p dy_rows[p, co] * x_rows[p + off, ci];
  * cin and cout multiples of 256; both operands are read in place (MN-major tcgen05 operands, no transposed copy); x_lo / dy_lo
  * both non-NULL: 3xTF32.  Deterministic (per-CTA-pair partial tiles summed in a fixed order); workspace from the _bytes query. */

@@ -95,6 +95,7 @@ SIGNATURES = {
     "scan_tf32_residual": (c_int32, [_P, c_int64, _P, _P]),
     "scan_conv3x3_rows": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "scan_conv3x3_rows2": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
+    "scan_conv1x1_rows": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, c_int32, _P, c_int32, c_int32, _P]),
     "scan_conv3x3_wgrad_workspace_bytes": (c_int64, [_LV, c_int32, c_int32, c_int32]),
     "scan_conv3x3_wgrad": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P]),
     "scan_thin_wgrad_workspace_bytes": (c_int64, [_LV, c_int32]),
@@ -135,7 +136,7 @@ LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_rel
             "scan_gemm_nt": 2, "scan_transpose": 1, "scan_linear_wgrad": 5, "scan_rows_softmax": 1, "scan_rows_l2normalize": 1,
             "scan_gcn_act_fwd": 1, "scan_gcn_act_bwd": 1,
             "scan_rows_linear_fwd": 1, "scan_rows_linear_bwd": 2, "scan_rows_gn_relu_fwd": 1, "scan_rows_gn_relu_bwd": 2,
-            "scan_postprocess": 4, "scan_conv3x3_pack_weights": 1, "scan_tf32_residual": 1, "scan_conv3x3_rows": 1, "scan_conv3x3_rows2": 1, "scan_thin_pack": 1, "scan_thin_unpack": 1, "scan_scale": 1, "scan_thin_gather": 1,
+            "scan_postprocess": 4, "scan_conv3x3_pack_weights": 1, "scan_tf32_residual": 1, "scan_conv3x3_rows": 1, "scan_conv3x3_rows2": 1, "scan_conv1x1_rows": 1, "scan_thin_pack": 1, "scan_thin_unpack": 1, "scan_scale": 1, "scan_thin_gather": 1,
             "scan_colsum": 2, "scan_thin_wgrad": 3, "scan_cka_bce_fwd": 2, "scan_cka_bce_bwd": 1, "scan_conv3x3_wgrad": 2,
             "scan_transfer_nodes_fwd": 2, "scan_transfer_nodes_bwd": 1, "scan_transfer_proto": 1,
             "scan_sigmoid_focal_fwd": 1, "scan_sigmoid_focal_bwd": 1, "scan_ensemble_levels": 1}

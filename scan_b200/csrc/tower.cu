@@ -61,6 +61,7 @@ struct ConvArgs {
   int k_chunks;          // Cin / 32
   int k_chunks2;         // 32-channel chunks of the second input (0: none)
   int n_terms;           // 1: single-pass tf32, 3: 3xTF32
+  int n_taps;            // 9: 3x3 convolution; 1: plain rows GEMM (the "1x1" case: no shifted reads)
   int seg_len;           // k-stages accumulated in tensor memory before the epilogue takes the partial sum (>= k_iters: one segment)
   int rows_per_tap;      // rows of one tap in the packed weight matrix (>= n_blocks * BN)
   float* out;            // [R, ldo]
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
   const int n_tile_groups = (g.n_tiles + CG - 1) / CG;
   const int n_work = n_tile_groups * g.n_blocks;
   const int kc_all = g.k_chunks + g.k_chunks2;
-  const int k_iters = g.n_terms * 9 * kc_all;
+  const int k_iters = g.n_terms * g.n_taps * kc_all;
   constexpr uint32_t IDESC = umma_idesc_tf32(CV_BM * CG, BN);
 
   if (threadIdx.x == 0) {
@@ -261,8 +262,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
           const CUtensorMap* ma = &maps.a[term == 2 ? 1 : 0][t.l];
           const CUtensorMap* ma2 = &maps.a2[term == 2 ? 1 : 0][t.l];
           const CUtensorMap* mb = &maps.b[term == 1 ? 1 : 0];
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          for (int tap = 0; tap < g.n_taps; ++tap) {
+            const int dy = g.n_taps == 9 ? tap / 3 - 1 : 0, dx = g.n_taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
             for (int kc = 0; kc < kc_all; ++kc) {
               mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
               uint32_t fb = smem_u32(full_bar + stage);
@@ -831,9 +832,10 @@ extern "C" int scan_tf32_residual(const float* x, int64_t n, float* lo, void* st
 // y_rows[R, ldo] = act(conv3x3([x_rows[R, cin] | x2_rows[R, cin2]]; packed weights) + bias + addend), optionally masked.
 // `packed` is scan_conv3x3_pack_weights' output for n_out output channels (rows padded to 256) and cin + cin2 input channels
 // (cin, cin2 multiples of 32; x2_rows may be NULL).  x_lo / packed_lo (and x2_lo) non-null selects 3xTF32.  cta_group = 1 or 2.
-extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* x2_rows,
-                                  const float* x2_lo, int cin2, const float* packed, const float* packed_lo, int n_out, const float* bias,
-                                  const float* addend, const float* mask, int relu, float* y_rows, int ldo, int cta_group, void* stream) {
+static int conv_rows_impl(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* x2_rows,
+                          const float* x2_lo, int cin2, const float* packed, const float* packed_lo, int n_out, const float* bias,
+                          const float* addend, const float* mask, int relu, float* y_rows, int ldo, int cta_group, int n_taps,
+                          void* stream) {
   Levels lv;
   int rc = make_levels(levels, &lv);
   if (rc) return rc;
@@ -893,10 +895,11 @@ extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_ro
   g.k_chunks = cin / 32;
   g.k_chunks2 = cin2 / 32;
   g.n_terms = x_lo ? 3 : 1;
+  g.n_taps = n_taps;
   // single-pass TF32: one accumulation per tile (what cuDNN does).  3xTF32: the tensor core TRUNCATES when it adds into its
   // accumulator, so the fp32-accurate mode hands the partial sum to the epilogue every 4 k-stages (16 MMAs:
   // a bias of at most 16 x 2^-24, below the rounding noise of an fp32 FFMA convolution; epilogue-bound, ~4x slower, parity only)
-  g.seg_len = x_lo ? 4 : g.n_terms * 9 * (g.k_chunks + g.k_chunks2);
+  g.seg_len = x_lo ? 4 : g.n_terms * n_taps * (g.k_chunks + g.k_chunks2);
   g.rows_per_tap = rows_per_tap;
   g.out = y_rows;
   g.ldo = ldo;
@@ -905,15 +908,31 @@ extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_ro
   g.addend = addend;
   g.mask = mask;
   g.relu = relu;
-  rc = conv_make_b_map(&maps.b[0], packed, 9ll * rows_per_tap, cin + cin2, bn / cta_group);
+  rc = conv_make_b_map(&maps.b[0], packed, (long long)n_taps * rows_per_tap, cin + cin2, bn / cta_group);
   if (rc) return rc;
   maps.b[1] = maps.b[0];
   if (packed_lo) {
-    rc = conv_make_b_map(&maps.b[1], packed_lo, 9ll * rows_per_tap, cin + cin2, bn / cta_group);
+    rc = conv_make_b_map(&maps.b[1], packed_lo, (long long)n_taps * rows_per_tap, cin + cin2, bn / cta_group);
     if (rc) return rc;
   }
   if (bn == 32) return cta_group == 2 ? conv_launch<2, 32>(maps, g, (cudaStream_t)stream) : conv_launch<1, 32>(maps, g, (cudaStream_t)stream);
   return cta_group == 2 ? conv_launch<2, 256>(maps, g, (cudaStream_t)stream) : conv_launch<1, 256>(maps, g, (cudaStream_t)stream);
+}
+
+extern "C" int scan_conv3x3_rows2(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* x2_rows,
+                                  const float* x2_lo, int cin2, const float* packed, const float* packed_lo, int n_out, const float* bias,
+                                  const float* addend, const float* mask, int relu, float* y_rows, int ldo, int cta_group, void* stream) {
+  return conv_rows_impl(levels, x_rows, x_lo, cin, x2_rows, x2_lo, cin2, packed, packed_lo, n_out, bias, addend, mask, relu, y_rows, ldo,
+                        cta_group, 9, stream);
+}
+
+// y_rows [R, ldo] (first n_out columns) = act(x_rows [R, cin] . w^T + bias): the same persistent CTA-pair kernel with ONE tap and no
+// shifted reads (a 1x1 convolution / rows GEMM).  w [rows padded to 256, cin] row-major, zero rows beyond n_out; w_lo: 3xTF32.
+extern "C" int scan_conv1x1_rows(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int32_t cin, const float* w,
+                                 const float* w_lo, int32_t n_out, const float* bias, int32_t relu, float* y_rows, int32_t ldo,
+                                 int32_t cta_group, void* stream) {
+  return conv_rows_impl(levels, x_rows, x_lo, cin, nullptr, nullptr, 0, w, w_lo, n_out, bias, nullptr, nullptr, relu, y_rows, ldo,
+                        cta_group, 1, stream);
 }
 
 extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* packed,

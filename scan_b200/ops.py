@@ -1602,14 +1602,17 @@ class _HeadOut(torch.autograd.Function):
         ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
         call("scan_add_relu_bwd", geo.ref(), _ptr_array(dys), _ptr(y_rows), _ptr(d_pre), _ptr(d_bias), _ptr(ws), ws.numel(), _stream())
         d_pre_lo = lo(d_pre)
-        # d(maps): thin data gradient, back to per-level NCHW.  d_pre is read ONCE by a plain GEMM against the [K * 9, 256] weight
-        # slice (what each pixel sends to its nine neighbours), then gathered over the taps; more than 14 classes take the
+        # d(maps): thin data gradient, back to per-level NCHW.  d_pre is read ONCE by a one-tap launch of the convolution kernel
+        # against the [K * 9, 256] weight slice (what each pixel sends to its nine neighbours), then gathered over the taps; more than 14 classes take the
         # N = 32 instantiation of the convolution kernel (nine shifted reads of d_pre)
         d_maps32 = torch.empty((geo.R, 32), device=dev, dtype=torch.float32)
         if 9 * k <= 128:
-            w_taps = weight[:, C:].permute(1, 2, 3, 0).reshape(9 * k, C).contiguous()
-            sent = gemm_nt(d_pre, w_taps, geo.R, 9 * k, C, C, C)
-            call("scan_thin_gather", geo.ref(), _ptr(sent), sent.shape[1], k, _ptr(d_maps32), _stream())
+            w_taps = torch.zeros((256, C), device=dev, dtype=torch.float32)
+            w_taps[:9 * k] = weight[:, C:].permute(1, 2, 3, 0).reshape(9 * k, C)
+            sent = torch.empty((geo.R, 128), device=dev, dtype=torch.float32)
+            call("scan_conv1x1_rows", geo.ref(), _ptr(d_pre), _ptr(d_pre_lo), C, _ptr(w_taps), _ptr(lo(w_taps)), 9 * k, None, 0, _ptr(sent),
+                 128, CONV["cta_group"], _stream())
+            call("scan_thin_gather", geo.ref(), _ptr(sent), 128, k, _ptr(d_maps32), _stream())
         else:
             hi, wlo = conv3x3_pack(weight[:, C:], True, precise)
             call("scan_conv3x3_rows2", geo.ref(), _ptr(d_pre), _ptr(d_pre_lo), C, None, None, 0, _ptr(hi), _ptr(wlo), k, None, None, None, 0,
