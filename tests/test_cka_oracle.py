@@ -51,3 +51,23 @@ def test_state_dict_layout_matches_reference_names():
     assert m.state_dict()["classifier_cls_0.0.weight"].shape == (128, 257, 3, 3)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 256, 4, 4), 1, act_maps=torch.zeros(1, 9, 4, 4))      # CPU tensors: no fallback
+
+
+def test_block_structured_weights_reproduce_the_per_class_loop():
+    """Host logic of the all-classes formulation (scan_b200/discriminator.py:_dense_weights), checked with plain torch on the CPU:
+    ONE convolution of [features | all class maps] with the block-structured weight, then ONE with the block-diagonal weight,
+    equals the reference's per-class Conv(cat(x, map_c)) -> ReLU -> Conv (fcos_head_discriminator_con.py:100-112)."""
+    import torch.nn.functional as F
+    from scan_b200.discriminator import FCOSDiscriminator_con
+    torch.manual_seed(0)
+    m = FCOSDiscriminator_con(num_convs=1, num_classes=4)
+    m.load_state_dict(cka_case.state_dict_for(m, seed=9))
+    x = torch.randn(2, 256, 6, 7)
+    maps = torch.rand(2, 3, 6, 7)
+    w1, b1, w2, b2 = m._dense_weights()
+    assert w1.shape == (3 * 128, 256 + 3, 3, 3) and w2.shape == (3, 3 * 128, 3, 3)
+    h = F.relu(F.conv2d(torch.cat([x, maps], 1), w1, b1, padding=1))
+    logits = F.conv2d(h, w2, b2, padding=1)
+    for c, block in enumerate(m.class_cond_map):
+        want = block(torch.cat([x, maps[:, c:c + 1]], 1))
+        assert torch.allclose(logits[:, c:c + 1], want, rtol=1e-4, atol=1e-5), c
