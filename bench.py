@@ -343,7 +343,7 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         "gn_relu_fwd": ("hbm", 2 * 2 * R * 3 * row),                   # 2 passes x 2 layers: 2 reads + 1 write
         "gn_relu_bwd": ("hbm", 2 * 2 * R * 7 * row),                   # 6 reads + 1 write
         "add_relu_fwd": ("hbm", 2 * R * 3 * row),
-        "add_relu_bwd": ("hbm", 2 * R * 2 * row),
+        "add_relu_bwd": ("hbm", 2 * R * 3 * row),                      # dy and y read, d_pre written
         # tower convolutions (csrc/tower.cu): 3 layers (2 head_in + the feature half of head_out) on R rows per pass; forward and
         # data gradient share scan_conv3x3_rows, the weight gradient is scan_conv3x3_wgrad
         # per pass: head_in fprop x 2 + data gradients x 3 (head_in x 2, head_out's feature columns) through scan_conv3x3_rows;
@@ -356,6 +356,8 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         "thin_wgrad": ("tensor", 2 * (2 * R * 256 * k * 9)),
         "condconv_fwd": ("hbm", 2 * R * (row + 4 * k) + R * 8),        # rows + K maps (+ labels on the source pass)
         "condconv_bwd": ("hbm", 2 * R * (2 * row + 2 * 4 * k)),        # rows read, d_rows written, maps + map gradients
+        # alias chain: d_rows already holds head_out's data gradient and is read-modify-written
+        "condconv_bwd2": ("hbm", 2 * R * (3 * row + 2 * 4 * k)),
         "gather_rows": ("hbm", ms * 2 * row),
         "scatter_add_rows": ("hbm", ms * 2 * row + 0 * R),
         "attn_fwd": ("tensor", 1024 * mm),                            # 4 chunks x (QK^T + PV) x 2 M^2 64
@@ -384,7 +386,7 @@ def traffic_of(kernel):
 # entry point -> the kernel that dominates it (the name the ncu capture and the roofline line report)
 DOMINANT_KERNEL = {"conv3x3_rows": "conv3x3_kernel", "conv3x3_rows2": "conv3x3_kernel", "conv1x1_rows": "conv3x3_kernel", "conv3x3_wgrad": "conv_wgrad_kernel",
                    "thin_wgrad": "conv_wgrad_kernel", "attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_levels_span": "db_adj_tc_kernel",
-                   "condconv_fwd": "condconv_fwd_ts_kernel", "condconv_bwd": "condconv_bwd_rows_kernel", "gn_relu_bwd": "gn_bwd_apply_kernel",
+                   "condconv_fwd": "condconv_fwd_ts_kernel", "condconv_bwd": "condconv_bwd_rows_kernel", "condconv_bwd2": "condconv_bwd_rows_kernel", "gn_relu_bwd": "gn_bwd_apply_kernel",
                    "gn_relu_fwd": "gn_apply_kernel", "qkv_fwd": "gemm3x_kernel", "qkv_bwd": "gemm3x_kernel"}
 
 
