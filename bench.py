@@ -330,6 +330,8 @@ def measure_tf32_peak(dev):
 def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
     """Algorithmic work per STEP of every entry point (SURVEY 8d per-unit figures x the units one step processes):
     {entry: (bound, amount)}; bytes for HBM-bound entries, flops for tensor-bound ones.  R = rows of one pass."""
+    from scan_b200 import ops as _ops
+    gn_stats = bool(_ops.CONV["gn_stats"]) and condgraph_towers() == "scan"
     R = n_img * L_PER_IMAGE
     row = 1024                                   # one fp32 row of 256 channels
     if not tgt_graph:                            # no transfer loss / self-training: the target pass skips graph aggregation
@@ -340,8 +342,9 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         "pack_rows": ("hbm", 2 * R * 2 * row),                         # 2 passes: NCHW read + rows write
         "unpack_rows": ("hbm", 2 * R * 2 * row),
         "unpack_levels": ("hbm", 2 * R * 2 * row),
-        "gn_relu_fwd": ("hbm", 2 * 2 * R * 3 * row),                   # 2 passes x 2 layers: 2 reads + 1 write
-        "gn_relu_bwd": ("hbm", 2 * 2 * R * 7 * row),                   # 6 reads + 1 write
+        "gn_relu_fwd": ("hbm", 2 * 2 * R * 3 * row),                   # 2 passes x 2 layers: 2 reads + 1 write (SCAN_B200_GN_STATS=0)
+        "gn_relu_apply": ("hbm", 2 * 2 * R * 2 * row),                 # statistics from the convolution's epilogue: 1 read + 1 write
+        "gn_relu_bwd": ("hbm", 2 * 2 * R * 5 * row),                   # x and dy read twice, dx written (the ReLU mask is recomputed)
         "add_relu_fwd": ("hbm", 2 * R * 3 * row),
         "add_relu_bwd": ("hbm", 2 * R * 3 * row),                      # dy and y read, d_pre written
         # tower convolutions (csrc/tower.cu): 3 layers (2 head_in + the feature half of head_out) on R rows per pass; forward and
@@ -349,7 +352,9 @@ def work_model(n_img, k, m_src, m_tgt, db_points, tgt_graph=True):
         # per pass: head_in fprop x 2 + data gradients x 3 (head_in x 2, head_out's feature columns) through scan_conv3x3_rows;
         # head_out's fused two-input forward (288 input channels) through _rows2; the thin data gradient into the K maps is a one-tap
         # launch of the same kernel (d_pre against the [9 K, 256] weight slice) + a tap gather
-        "conv3x3_rows": ("tensor", 2 * 5 * (2 * R * 256 * 256 * 9)),
+        # (with the GroupNorm statistics in the epilogue the two head_in forward launches are the scan_conv3x3_rows_gn entry point)
+        "conv3x3_rows": ("tensor", 2 * (3 if gn_stats else 5) * (2 * R * 256 * 256 * 9)),
+        "conv3x3_rows_gn": ("tensor", 2 * 2 * (2 * R * 256 * 256 * 9)),
         "conv3x3_rows2": ("tensor", 2 * (2 * R * 288 * 256 * 9)),
         "conv1x1_rows": ("tensor", 2 * (2 * R * 256 * k * 9)),
         "conv3x3_wgrad": ("tensor", 2 * 3 * (2 * R * 256 * 256 * 9)),
@@ -384,10 +389,10 @@ def traffic_of(kernel):
 
 
 # entry point -> the kernel that dominates it (the name the ncu capture and the roofline line report)
-DOMINANT_KERNEL = {"conv3x3_rows": "conv3x3_kernel", "conv3x3_rows2": "conv3x3_kernel", "conv1x1_rows": "conv3x3_kernel", "conv3x3_wgrad": "conv_wgrad_kernel",
+DOMINANT_KERNEL = {"conv3x3_rows": "conv3x3_kernel", "conv3x3_rows_gn": "conv3x3_kernel", "conv3x3_rows2": "conv3x3_kernel", "conv1x1_rows": "conv3x3_kernel", "conv3x3_wgrad": "conv_wgrad_kernel",
                    "thin_wgrad": "conv_wgrad_kernel", "attn_bwd": "attn_bwd_dkv_t5_kernel", "attn_fwd": "attn_fwd_t5_kernel", "dbscan_levels_span": "db_adj_tc_kernel",
                    "condconv_fwd": "condconv_fwd_ts_kernel", "condconv_bwd": "condconv_bwd_rows_kernel", "condconv_bwd2": "condconv_bwd_rows_kernel", "gn_relu_bwd": "gn_bwd_apply_kernel",
-                   "gn_relu_fwd": "gn_apply_kernel", "qkv_fwd": "gemm3x_kernel", "qkv_bwd": "gemm3x_kernel"}
+                   "gn_relu_fwd": "gn_apply_kernel", "gn_relu_apply": "gn_apply_kernel", "qkv_fwd": "gemm3x_kernel", "qkv_bwd": "gemm3x_kernel"}
 
 
 def condgraph_towers():

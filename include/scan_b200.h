@@ -85,13 +85,18 @@ int scan_unpack_levels(const scan_levels_t* lv, const void* const* rows_levels_h
 int64_t scan_gn_workspace_bytes(const scan_levels_t* lv);
 /* conv_bias (nullable, [256]): the bias of the preceding convolution, added on the fly so that the convolution
  * itself runs bias-free; the backward then also returns d_conv_bias (column sums of dx) instead of a
- * separate full-tensor reduction.  conv_bias and d_conv_bias must both be given or both be NULL. */
+ * separate full-tensor reduction.  conv_bias and d_conv_bias must both be given or both be NULL.
+ * The backward does not read y: it recomputes the ReLU mask [x * a + c > 0] from x with the forward's own
+ * operations (a = rstd * gamma, c = beta - mean * a, one fused multiply-add), which is why it takes beta. */
 int scan_gn_relu_fwd(const scan_levels_t* lv, const void* const* x_levels_host, const float* conv_bias,
                      const float* gamma, const float* beta, float eps, float* y_rows, float* stats,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* the apply pass alone (y = relu(gn(x + conv_bias))) with statistics from scan_conv3x3_rows_gn */
+int scan_gn_relu_apply(const scan_levels_t* lv, const void* const* x_levels_host, const float* conv_bias,
+                       const float* gamma, const float* beta, const float* stats, float* y_rows, void* stream);
 int scan_gn_relu_bwd(const scan_levels_t* lv, const void* const* x_levels_host,
-                     const void* const* dy_levels_host, const float* conv_bias, const float* y_rows,
-                     const float* gamma, const float* stats, float* dx_rows, float* dgamma, float* dbeta,
+                     const void* const* dy_levels_host, const float* conv_bias, const float* gamma,
+                     const float* beta, const float* stats, float* dx_rows, float* dgamma, float* dbeta,
                      float* d_conv_bias, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- f1: head_out epilogue y = relu(u + v + bias) (condgraph.py:379-384 with the concat removed:
@@ -347,6 +352,14 @@ int scan_tf32_residual(const float* x, int64_t n, float* lo, void* stream);
 int scan_conv3x3_rows(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* packed,
                       const float* packed_lo, int32_t n_out, const float* bias, const float* addend, int32_t relu, float* y_rows,
                       int32_t ldo, int32_t cta_group, void* stream);
+/* the tower convolution in front of a GroupNorm(32) (condgraph.py:100-107): y_rows [R, 256] = conv3x3(x_rows), bias-free, plus the
+ * GroupNorm statistics of (y + gn_bias) from the kernel's epilogue (per-warp partial sums, combined per (level, image, group) in
+ * fp64 in a fixed order): stats [L * N * 32][mean, 1 / sqrt(var + eps)] -- the array scan_gn_relu_fwd's statistics pass would
+ * produce, without re-reading the tensor.  scan_gn_relu_apply then normalises with them. */
+int64_t scan_conv3x3_gn_workspace_bytes(const scan_levels_t* lv);
+int scan_conv3x3_rows_gn(const scan_levels_t* lv, const float* x_rows, const float* x_lo, int32_t cin, const float* packed,
+                         const float* packed_lo, const float* gn_bias, float eps, float* y_rows, float* stats, int32_t cta_group,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 /* the same with an optional SECOND input tensor x2_rows [R, cin2] whose channels follow x_rows' in the weight columns (the
  * concatenation [features | activation maps] of head_out, condgraph.py:379-384, and of the CKA discriminator's class-conditional
  * maps, fcos_head_discriminator_con.py:104-105, without materialising it), and an optional mask [R, ldo]: out = mask > 0 ? out : 0

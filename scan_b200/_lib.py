@@ -43,6 +43,7 @@ SIGNATURES = {
     "scan_unpack_levels": (c_int32, [_LV, _P, c_int32, _P, _P]),
     "scan_gn_workspace_bytes": (c_int64, [_LV]),
     "scan_gn_relu_fwd": (c_int32, [_LV, _P, _P, _P, _P, c_float, _P, _P, _P, c_int64, _P]),
+    "scan_gn_relu_apply": (c_int32, [_LV, _P, _P, _P, _P, _P, _P, _P]),
     "scan_gn_relu_bwd": (c_int32, [_LV, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "scan_add_relu_fwd": (c_int32, [_LV, _P, _P, _P, _P, _P]),
     "scan_add_relu_bwd": (c_int32, [_LV, _P, _P, _P, _P, _P, c_int64, _P]),
@@ -93,6 +94,8 @@ SIGNATURES = {
     "scan_conv3x3_packed_floats": (c_int64, [c_int32, c_int32]),
     "scan_conv3x3_pack_weights": (c_int32, [_P, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
     "scan_tf32_residual": (c_int32, [_P, c_int64, _P, _P]),
+    "scan_conv3x3_gn_workspace_bytes": (c_int64, [_LV]),
+    "scan_conv3x3_rows_gn": (c_int32, [_LV, _P, _P, c_int32, _P, _P, _P, c_float, _P, _P, c_int32, _P, c_int64, _P]),
     "scan_conv3x3_rows": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "scan_conv3x3_rows2": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "scan_conv1x1_rows": (c_int32, [_LV, _P, _P, c_int32, _P, _P, c_int32, _P, c_int32, _P, c_int32, c_int32, _P]),
@@ -128,7 +131,7 @@ SIGNATURES = {
 
 _lib = None
 # kernels each entry point launches (memsets excluded): bench.py's gpu_launches is counted from this table
-LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_upload_small": 1, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_unpack_levels": 1, "scan_fcos_assign": 1, "scan_fcos_assign_reg": 1, "scan_fcos_loss_fwd": 2, "scan_fcos_loss_bwd": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
+LAUNCHES = {"scan_manifest_rnn_fwd": 6, "scan_manifest_rnn_bwd": 7, "scan_gn_relu_fwd": 3, "scan_gn_relu_apply": 1, "scan_conv3x3_rows_gn": 2, "scan_gn_relu_bwd": 4, "scan_add_relu_fwd": 1, "scan_add_relu_bwd": 2, "scan_upload_small": 1, "scan_pack_rows": 1, "scan_unpack_rows": 1, "scan_unpack_levels": 1, "scan_fcos_assign": 1, "scan_fcos_assign_reg": 1, "scan_fcos_loss_fwd": 2, "scan_fcos_loss_bwd": 1, "scan_sample_nodes": 4, "scan_gather_rows": 1,
             "scan_scatter_add_rows": 1, "scan_condconv_fwd": 1, "scan_condconv_bwd": 3, "scan_condconv_bwd2": 3, "scan_attn_fwd": 5, "scan_attn_bwd": 4,
             "scan_class_sums": 1, "scan_proto_update": 1, "scan_dbscan_level": 20, "scan_dbscan_points": 15,
             "scan_qkv_fwd": 1, "scan_qkv_bwd": 9, "scan_attn_out_ln_fwd": 1, "scan_attn_out_ln_bwd": 9, "scan_node_cls_fwd": 3,

@@ -96,8 +96,9 @@ class GRAPHHead(nn.Module):
                 gn = layers[i]
                 i += 2
                 # bias-free convolution: the GroupNorm kernel adds the bias and returns its gradient as a by-product
-                outs = _tower_conv(geo, conv.weight, w, h)
-                h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs, conv_bias=conv.bias)
+                # (and takes its statistics from the convolution's epilogue when that is the tcgen05 kernel)
+                outs, stats = _tower_conv(geo, conv.weight, w, h, gn=(conv.bias, gn.eps))
+                h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs, conv_bias=conv.bias, stats=stats)
             else:   # IN / BN variants and the norm-free head_out: torch modules (not used by the shipped configs' head_in)
                 outs = [F.conv2d(ops.nhwc_dense(x), w, conv.bias, padding=1) for x in h]
                 while i < len(layers) and not isinstance(layers[i], nn.Conv2d):
@@ -110,15 +111,22 @@ class GRAPHHead(nn.Module):
 TOWERS = {"impl": os.environ.get("SCAN_B200_TOWERS", "scan")}     # "scan" (csrc/tower.cu) | "cudnn"
 
 
-def _tower_conv(geo, weight, weight_cl, levels):
+def _tower_conv(geo, weight, weight_cl, levels, gn=None):
     """Bias-free 3x3 tower convolution of all levels: the tcgen05 implicit GEMM of csrc/tower.cu (f1) for the 256 -> 256 layers of
     every shipped config; other widths, and SCAN_B200_TOWERS=cudnn (the A/B switch of tools/ and bench.py), go to cuDNN's
-    channels-last kernels."""
-    if TOWERS["impl"] == "scan" and weight.shape[0] % 256 == 0 and weight.shape[1] % 256 == 0:
-        return ops.conv3x3_levels(geo, weight, list(levels))
-    if weight_cl is None:
-        weight_cl = weight.contiguous(memory_format=torch.channels_last)
-    return [F.conv2d(ops.nhwc_dense(x), weight_cl, None, padding=1) for x in levels]
+    channels-last kernels.
+    gn = (conv_bias, eps) of a following GroupNorm(32): returns (levels, stats | None), the statistics being a by-product of the
+    tcgen05 kernel's epilogue (ops.CONV["gn_stats"]); without gn: the levels."""
+    own = TOWERS["impl"] == "scan" and weight.shape[0] % 256 == 0 and weight.shape[1] % 256 == 0
+    if own and gn is not None and ops.CONV["gn_stats"] and weight.shape[0] == 256:
+        return ops.conv3x3_levels(geo, weight, list(levels), gn=gn)
+    if own:
+        outs = ops.conv3x3_levels(geo, weight, list(levels))
+    else:
+        if weight_cl is None:
+            weight_cl = weight.contiguous(memory_format=torch.channels_last)
+        outs = [F.conv2d(ops.nhwc_dense(x), weight_cl, None, padding=1) for x in levels]
+    return outs if gn is None else (outs, None)
 
 
 class MultiHeadAttention(nn.Module):

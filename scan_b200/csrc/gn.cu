@@ -3,7 +3,8 @@
 // FPN levels of a call in ONE launch each and write the result straight into the contiguous [R, 256] rows matrix the rest
 // of the path works on (no NCHW<->NHWC conversion, no separate ReLU pass, no pack).  HBM-bound streaming kernels:
 //   forward   stats pass (read x) -> finalize (fp64) -> apply pass (read x, write y)
-//   backward  reduce pass (read x, y, dy) -> finalize (fp64) -> apply pass (read x, y, dy, write dx)
+//   backward  reduce pass (read x, dy) -> finalize (fp64) -> apply pass (read x, dy, write dx); the ReLU mask is recomputed
+//             from x with the forward's own operations, so y is never read back
 // A block owns 128 consecutive pixels of one (level, image); a thread owns 4 channels (half a group of 8) of every 4th
 // pixel, so each pixel row is one 1 KB coalesced access.  Partials are per block, combined in fp64: deterministic.
 #include "common.cuh"
@@ -54,6 +55,17 @@ __device__ __forceinline__ float4 gn_bias4(const float* cbias, int c4) {
 __device__ __forceinline__ float4 gn_ldx(const float4* p, const float4& cb) {
   const float4 v = __ldg(p);
   return make_float4(v.x + cb.x, v.y + cb.y, v.z + cb.z, v.w + cb.w);
+}
+
+// y = relu(x * a + c) with a = rstd * gamma, c = beta - mean * a (the form torch's kernel uses; c and x * a + c one fused
+// multiply-add each).  One definition with explicit roundings: the backward kernels recompute the ReLU mask [x * a + c > 0] from x instead of reading y back (two of seven
+// HBM streams), which is only exact if forward and backward evaluate the very same operations.
+__device__ __forceinline__ void gn_affine(float mean, float rstd, const float4& ga, const float4& be, float4& a, float4& c) {
+  a = make_float4(__fmul_rn(rstd, ga.x), __fmul_rn(rstd, ga.y), __fmul_rn(rstd, ga.z), __fmul_rn(rstd, ga.w));
+  c = make_float4(__fmaf_rn(-mean, a.x, be.x), __fmaf_rn(-mean, a.y, be.y), __fmaf_rn(-mean, a.z, be.z), __fmaf_rn(-mean, a.w, be.w));
+}
+__device__ __forceinline__ float4 gn_pre(const float4& v, const float4& a, const float4& c) {
+  return make_float4(__fmaf_rn(v.x, a.x, c.x), __fmaf_rn(v.y, a.y, c.y), __fmaf_rn(v.z, a.z, c.z), __fmaf_rn(v.w, a.w, c.w));
 }
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
@@ -115,22 +127,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Levels lv, GnLevels g, co
   const float mean = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)));
   const float rstd = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)) + 1);
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-  // y = x * a + c with a = rstd * gamma, c = beta - mean * a  (the form torch's kernel uses)
-  const float4 a = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
-  const float4 c = make_float4(be.x - mean * a.x, be.y - mean * a.y, be.z - mean * a.z, be.w - mean * a.w);
+  float4 a, c;
+  gn_affine(mean, rstd, ga, be, a, c);
   const float4* x = reinterpret_cast<const float4*>(g.x[b.l] + ((long long)b.n * b.hw + b.p0) * GN_C) + c4;
   float4* y = reinterpret_cast<float4*>(y_rows + b.row0 * GN_C) + c4;
   for (int p = rsub; p < b.np; p += 4) {
-    const float4 v = gn_ldx(x + (long long)p * (GN_C / 4), cb);
-    y[(long long)p * (GN_C / 4)] = make_float4(fmaxf(fmaf(v.x, a.x, c.x), 0.f), fmaxf(fmaf(v.y, a.y, c.y), 0.f),
-                                               fmaxf(fmaf(v.z, a.z, c.z), 0.f), fmaxf(fmaf(v.w, a.w, c.w), 0.f));
+    const float4 r = gn_pre(gn_ldx(x + (long long)p * (GN_C / 4), cb), a, c);
+    y[(long long)p * (GN_C / 4)] = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
   }
 }
 
 // ---------------------------------------------------------------------------- backward
-// per block and channel: A_c = sum dyr, B_c = sum dyr * xhat, with dyr = dy * [y > 0], xhat = (x - mean) * rstd
+// per block and channel: A_c = sum dyr, B_c = sum dyr * xhat, with dyr = dy * [y > 0], xhat = (x - mean) * rstd; the mask
+// [y > 0] is recomputed from x (gn_affine / gn_pre: the forward's own operations), y is not read
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
-                                                            const float* __restrict__ stats, const float* __restrict__ y_rows,
+                                                            const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
                                                             float* __restrict__ partial /* [blocks][256][2] */) {
   __shared__ float red[4][GN_C][2];
   const GnBlock b = gn_decode(lv, g, blockIdx.x);
@@ -138,14 +150,17 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Levels lv, GnLevels 
   const float4 cb = gn_bias4(cbias, c4);
   const float mean = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)));
   const float rstd = __ldg(stats + 2 * (b.stat * GN_G + (c4 >> 1)) + 1);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+  float4 fa, fc;
+  gn_affine(mean, rstd, ga, be, fa, fc);
   const long long base = ((long long)b.n * b.hw + b.p0) * GN_C;
   const float4* x = reinterpret_cast<const float4*>(g.x[b.l] + base) + c4;
   const float4* dy = reinterpret_cast<const float4*>(g.dy[b.l] + base) + c4;
-  const float4* y = reinterpret_cast<const float4*>(y_rows + b.row0 * GN_C) + c4;
   float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int p = rsub; p < b.np; p += 4) {
     const long long o = (long long)p * (GN_C / 4);
-    const float4 xv = gn_ldx(x + o, cb), dv = __ldg(dy + o), yv = __ldg(y + o);
+    const float4 xv = gn_ldx(x + o, cb), dv = __ldg(dy + o);
+    const float4 yv = gn_pre(xv, fa, fc);
     const float d0 = yv.x > 0.f ? dv.x : 0.f, d1 = yv.y > 0.f ? dv.y : 0.f, d2 = yv.z > 0.f ? dv.z : 0.f, d3 = yv.w > 0.f ? dv.w : 0.f;
     a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
     bb[0] += d0 * ((xv.x - mean) * rstd);
@@ -213,7 +228,7 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(Levels lv, GnLevel
 // dx, plus (when the convolution bias is folded in) per-block column sums of dx = the convolution's bias gradient partials
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Levels lv, GnLevels g, const float* __restrict__ cbias,
                                                            const float* __restrict__ stats, const float* __restrict__ gsum,
-                                                           const float* __restrict__ gamma, const float* __restrict__ y_rows,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            float* __restrict__ dx_rows, float* __restrict__ colsum /* [blocks][256] or null */) {
   __shared__ float red[4][GN_C];
   const GnBlock b = gn_decode(lv, g, blockIdx.x);
@@ -223,16 +238,18 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Levels lv, GnLevels g
   const float mean = __ldg(stats + 2 * si), rstd = __ldg(stats + 2 * si + 1);
   const float inv_m = 1.f / ((float)b.hw * 8.f);
   const float k1 = __ldg(gsum + 2 * si) * inv_m, k2 = __ldg(gsum + 2 * si + 1) * inv_m;
-  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+  float4 fa, fc;
+  gn_affine(mean, rstd, ga, be, fa, fc);
   const long long base = ((long long)b.n * b.hw + b.p0) * GN_C;
   const float4* x = reinterpret_cast<const float4*>(g.x[b.l] + base) + c4;
   const float4* dy = reinterpret_cast<const float4*>(g.dy[b.l] + base) + c4;
-  const float4* y = reinterpret_cast<const float4*>(y_rows + b.row0 * GN_C) + c4;
   float4* dx = reinterpret_cast<float4*>(dx_rows + b.row0 * GN_C) + c4;
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = rsub; p < b.np; p += 4) {
     const long long o = (long long)p * (GN_C / 4);
-    const float4 xv = gn_ldx(x + o, cb), dv = __ldg(dy + o), yv = __ldg(y + o);
+    const float4 xv = gn_ldx(x + o, cb), dv = __ldg(dy + o);
+    const float4 yv = gn_pre(xv, fa, fc);
     float4 r;
     // dx = rstd * (dyr * gamma - (s1 + xhat * s2) / m)
     r.x = rstd * ((yv.x > 0.f ? dv.x : 0.f) * ga.x - (k1 + (xv.x - mean) * rstd * k2));
@@ -368,8 +385,22 @@ extern "C" int scan_gn_relu_fwd(const scan_levels_t* lv_in, const void* const* x
   return SCAN_OK;
 }
 
+// the apply pass alone, with statistics that came out of the convolution's epilogue (scan_conv3x3_rows_gn)
+extern "C" int scan_gn_relu_apply(const scan_levels_t* lv_in, const void* const* x_levels_host, const float* conv_bias, const float* gamma,
+                                  const float* beta, const float* stats, float* y_rows, void* stream) {
+  using namespace scan;
+  Levels lv;
+  GnLevels g;
+  int rc = gn_build(lv_in, x_levels_host, nullptr, &lv, &g);
+  if (rc) return rc;
+  if (!gamma || !beta || !y_rows || !stats) return SCAN_EINVAL;
+  gn_apply_kernel<<<g.blk_off[lv.n_levels], 256, 0, (cudaStream_t)stream>>>(lv, g, conv_bias, stats, gamma, beta, y_rows);
+  SCAN_LAUNCH_CHECK("gn_apply_kernel");
+  return SCAN_OK;
+}
+
 extern "C" int scan_gn_relu_bwd(const scan_levels_t* lv_in, const void* const* x_levels_host, const void* const* dy_levels_host,
-                                const float* conv_bias, const float* y_rows, const float* gamma, const float* stats, float* dx_rows,
+                                const float* conv_bias, const float* gamma, const float* beta, const float* stats, float* dx_rows,
                                 float* dgamma, float* dbeta, float* d_conv_bias, void* workspace, int64_t workspace_bytes,
                                 void* stream) {
   using namespace scan;
@@ -377,7 +408,7 @@ extern "C" int scan_gn_relu_bwd(const scan_levels_t* lv_in, const void* const* x
   GnLevels g;
   int rc = gn_build(lv_in, x_levels_host, dy_levels_host, &lv, &g);
   if (rc) return rc;
-  if (!dy_levels_host || !y_rows || !gamma || !stats || !dx_rows || !dgamma || !dbeta || !workspace) return SCAN_EINVAL;
+  if (!dy_levels_host || !gamma || !beta || !stats || !dx_rows || !dgamma || !dbeta || !workspace) return SCAN_EINVAL;
   if ((conv_bias != nullptr) != (d_conv_bias != nullptr)) return SCAN_EINVAL;
   if (workspace_bytes < scan_gn_workspace_bytes(lv_in)) return SCAN_ECAPACITY;
   cudaStream_t st = (cudaStream_t)stream;
@@ -385,12 +416,12 @@ extern "C" int scan_gn_relu_bwd(const scan_levels_t* lv_in, const void* const* x
   float* partial = (float*)workspace;
   float* gsum = partial + (long long)blocks * GN_C * 2;
   float* colsum = gsum + (long long)lv.n_levels * lv.n_images * GN_G * 2 + 64;
-  gn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, y_rows, partial);
+  gn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, gamma, beta, partial);
   SCAN_LAUNCH_CHECK("gn_bwd_reduce_kernel");
   const int n_fin = lv.n_levels * lv.n_images * GN_G + GN_C;
   gn_bwd_finalize_kernel<<<(n_fin + 7) / 8, 256, 0, st>>>(lv, g, partial, gamma, gsum, dgamma, dbeta);
   SCAN_LAUNCH_CHECK("gn_bwd_finalize_kernel");
-  gn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, gsum, gamma, y_rows, dx_rows, d_conv_bias ? colsum : nullptr);
+  gn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(lv, g, conv_bias, stats, gsum, gamma, beta, dx_rows, d_conv_bias ? colsum : nullptr);
   SCAN_LAUNCH_CHECK("gn_bwd_apply_kernel");
   if (d_conv_bias) {
     gn_colsum_kernel<<<GN_C / 8, 256, 0, st>>>(colsum, blocks, d_conv_bias);

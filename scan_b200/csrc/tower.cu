@@ -71,6 +71,12 @@ struct ConvArgs {
   const float* addend;   // [R, ldo] or null: out = act(acc + bias + addend)
   const float* mask;     // [R, ldo] or null: out = mask > 0 ? out : 0 (the ReLU of a saved forward output, for data gradients)
   int relu;
+  // GroupNorm statistics of the output as a by-product (BN = 256 only; null: off): every epilogue warp writes the sums and sums
+  // of squares of (out + gn_bias) over its 32 pixels for each of the 32 groups of 8 channels -> gn_partial [tile][warp][32][2];
+  // conv_gn_finalize_kernel combines them per (level, image) in fp64 in a fixed order.  Saves the statistics pass of
+  // scan_gn_relu_fwd (one full read of the tensor); the epilogue has the time (it overlaps the next tile's main loop).
+  float* gn_partial;
+  const float* gn_bias;  // [256] or null: the convolution bias that scan_gn_relu adds on the fly
 };
 
 struct ConvTile {
@@ -338,45 +344,91 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const __grid_con
           float v[32];
           cv_ld32(tl + c * 32, v);
           const int col = nb * BN + c * 32;
-          if (!valid || col >= g.n_valid) continue;
-          if (col + 32 <= g.n_valid) {
+          const bool act = valid && col < g.n_valid;
+          if (act) {
+            if (col + 32 <= g.n_valid) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-              float4* dst = reinterpret_cast<float4*>(out + c * 32 + e);
-              if (!first) {
-                const float4 p = *dst;
-                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-              }
-              if (last) {
-                if (g.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + e));
-                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                if (add) {
-                  const float4 p = __ldg(reinterpret_cast<const float4*>(add + c * 32 + e));
+              for (int e = 0; e < 32; e += 4) {
+                float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                float4* dst = reinterpret_cast<float4*>(out + c * 32 + e);
+                if (!first) {
+                  const float4 p = *dst;
                   o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
                 }
-                if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                if (msk) {
-                  const float4 q4 = __ldg(reinterpret_cast<const float4*>(msk + c * 32 + e));
-                  o.x = q4.x > 0.f ? o.x : 0.f; o.y = q4.y > 0.f ? o.y : 0.f; o.z = q4.z > 0.f ? o.z : 0.f; o.w = q4.w > 0.f ? o.w : 0.f;
-                }
-              }
-              *dst = o;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (col + e < g.n_valid) {
-                float o = v[e] + (first ? 0.f : out[c * 32 + e]);
                 if (last) {
-                  o += (g.bias ? __ldg(g.bias + col + e) : 0.f) + (add ? __ldg(add + c * 32 + e) : 0.f);
-                  o = g.relu ? fmaxf(o, 0.f) : o;
-                  if (msk) o = __ldg(msk + c * 32 + e) > 0.f ? o : 0.f;
+                  if (g.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + e));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                  }
+                  if (add) {
+                    const float4 p = __ldg(reinterpret_cast<const float4*>(add + c * 32 + e));
+                    o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                  }
+                  if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                  if (msk) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(msk + c * 32 + e));
+                    o.x = q4.x > 0.f ? o.x : 0.f; o.y = q4.y > 0.f ? o.y : 0.f; o.z = q4.z > 0.f ? o.z : 0.f; o.w = q4.w > 0.f ? o.w : 0.f;
+                  }
                 }
-                out[c * 32 + e] = o;
+                *dst = o;
+                v[e] = o.x; v[e + 1] = o.y; v[e + 2] = o.z; v[e + 3] = o.w;
               }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (col + e < g.n_valid) {
+                  float o = v[e] + (first ? 0.f : out[c * 32 + e]);
+                  if (last) {
+                    o += (g.bias ? __ldg(g.bias + col + e) : 0.f) + (add ? __ldg(add + c * 32 + e) : 0.f);
+                    o = g.relu ? fmaxf(o, 0.f) : o;
+                    if (msk) o = __ldg(msk + c * 32 + e) > 0.f ? o : 0.f;
+                  }
+                  out[c * 32 + e] = o;
+                }
+            }
+          }
+          if constexpr (BN == 256) {
+            if (g.gn_partial != nullptr && last) {   // warp-uniform: all 32 lanes take part in the shuffles
+              // this chunk = 4 groups of 8 channels: {sum, sum of squares} per group over this thread's pixel ...
+              float st[8];
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                float sm = 0.f, sq = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (g.gn_bias) b = __ldg(reinterpret_cast<const float4*>(g.gn_bias + col + gq * 8 + e));
+                  const float x0 = v[gq * 8 + e] + b.x, x1 = v[gq * 8 + e + 1] + b.y, x2 = v[gq * 8 + e + 2] + b.z,
+                              x3 = v[gq * 8 + e + 3] + b.w;
+                  sm += (x0 + x1) + (x2 + x3);
+                  sq += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+                }
+                st[2 * gq] = act ? sm : 0.f;          // a select, not a product: rows outside the image may hold anything
+                st[2 * gq + 1] = act ? sq : 0.f;
+              }
+              // ... summed over the warp's 32 pixels by a halving butterfly (8 -> 4 -> 2 -> 1 values per lane, 9 shuffles):
+              // lane bits 4, 3, 2 select which of the 8 values the lane ends up holding; fixed order, deterministic
+              float r4[4], r2[2], r1;
+              const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float keep = u16 ? st[i + 4] : st[i], send = u16 ? st[i] : st[i + 4];
+                r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float keep = u8 ? r4[i + 2] : r4[i], send = u8 ? r4[i] : r4[i + 2];
+                r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              {
+                const float keep = u4 ? r2[1] : r2[0], send = u4 ? r2[0] : r2[1];
+                r1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+              r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+              const int idx = (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);
+              if ((lane & 3) == 0 && ti < g.n_tiles) g.gn_partial[((long long)ti * 4 + q) * 64 + c * 8 + idx] = r1;
+            }
           }
         }
         tcgen05_fence_before();
@@ -714,6 +766,38 @@ __global__ void __launch_bounds__(256) tf32_residual_kernel(const float4* __rest
   }
 }
 
+// GroupNorm statistics from the convolution's epilogue partials: one warp per (level, image, group) sums the 4 * tiles-per-image
+// {sum, sum of squares} pairs in fp64 (fixed order) -> stats [(l * N + n) * 32 + group][mean, 1 / sqrt(var + eps)], the array
+// scan_gn_relu_fwd produces (biased variance like torch's native_group_norm)
+struct ConvGnGeo {
+  int n_levels, n_images;
+  int tile_off[SCAN_MAX_LEVELS], per[SCAN_MAX_LEVELS], hw[SCAN_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) conv_gn_finalize_kernel(ConvGnGeo geo, const float* __restrict__ partial, float eps,
+                                                               float* __restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= geo.n_levels * geo.n_images * 32) return;
+  const int gi = i % 32, ln = i / 32, l = ln / geo.n_images, n = ln % geo.n_images;
+  const long long first = ((long long)geo.tile_off[l] + (long long)n * geo.per[l]) * 4;
+  const int count = geo.per[l] * 4;
+  double s = 0.0, ss = 0.0;
+  for (int j = lane; j < count; j += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (first + j) * 32 + gi);
+    s += (double)v.x;
+    ss += (double)v.y;
+  }
+  s = warp_sum_d(s);
+  ss = warp_sum_d(ss);
+  if (lane == 0) {
+    const double m = (double)geo.hw[l] * 8.0;
+    const double mean = s / m;
+    const double var = fmax(ss / m - mean * mean, 0.0);
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 // tile rectangle of a level: th * tw <= 128 minimising the tile count (ties: the wider one, longer contiguous runs)
 static void conv_pick_tile(int h, int w, int* th_out, int* tw_out) {
@@ -835,7 +919,7 @@ extern "C" int scan_tf32_residual(const float* x, int64_t n, float* lo, void* st
 static int conv_rows_impl(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int cin, const float* x2_rows,
                           const float* x2_lo, int cin2, const float* packed, const float* packed_lo, int n_out, const float* bias,
                           const float* addend, const float* mask, int relu, float* y_rows, int ldo, int cta_group, int n_taps,
-                          void* stream) {
+                          void* stream, float* gn_partial = nullptr, const float* gn_bias = nullptr, ConvGnGeo* gn_geo = nullptr) {
   Levels lv;
   int rc = make_levels(levels, &lv);
   if (rc) return rc;
@@ -861,6 +945,11 @@ static int conv_rows_impl(const scan_levels_t* levels, const float* x_rows, cons
     L.tile_off = tiles;
     L.row_off = lv.row_off[l];
     tiles += lv.n_images * L.tiles_x * L.tiles_y;
+    if (gn_geo) {
+      gn_geo->tile_off[l] = L.tile_off;
+      gn_geo->per[l] = L.tiles_x * L.tiles_y;
+      gn_geo->hw[l] = L.h * L.w;
+    }
     rc = conv_make_a_map(&maps.a[0][l], x_rows + lv.row_off[l] * cin, cin, L.w, L.h, lv.n_images, L.tw, L.th);
     if (rc) return rc;
     maps.a[1][l] = maps.a[0][l];
@@ -908,6 +997,13 @@ static int conv_rows_impl(const scan_levels_t* levels, const float* x_rows, cons
   g.addend = addend;
   g.mask = mask;
   g.relu = relu;
+  if (gn_partial && (n_out != 256 || ((uintptr_t)gn_partial & 7) || (gn_bias && ((uintptr_t)gn_bias & 15)))) return SCAN_EINVAL;
+  g.gn_partial = gn_partial;
+  g.gn_bias = gn_bias;
+  if (gn_geo) {
+    gn_geo->n_levels = lv.n_levels;
+    gn_geo->n_images = lv.n_images;
+  }
   rc = conv_make_b_map(&maps.b[0], packed, (long long)n_taps * rows_per_tap, cin + cin2, bn / cta_group);
   if (rc) return rc;
   maps.b[1] = maps.b[0];
@@ -940,6 +1036,36 @@ extern "C" int scan_conv3x3_rows(const scan_levels_t* levels, const float* x_row
                                  int cta_group, void* stream) {
   return scan_conv3x3_rows2(levels, x_rows, x_lo, cin, nullptr, nullptr, 0, packed, packed_lo, n_out, bias, addend, nullptr, relu, y_rows,
                             ldo, cta_group, stream);
+}
+
+// The tower convolution in front of a GroupNorm(32): y_rows [R, 256] = conv3x3(x_rows) WITHOUT bias, plus the GroupNorm statistics
+// of (y + gn_bias) as a by-product of the epilogue -> stats [L * N * 32][2] = what scan_gn_relu_fwd would compute in its
+// statistics pass (scan_gn_relu_apply then normalises with them).  workspace: scan_conv3x3_gn_workspace_bytes(levels).
+extern "C" int64_t scan_conv3x3_gn_workspace_bytes(const scan_levels_t* levels) {
+  Levels lv;
+  if (make_levels(levels, &lv)) return -1;
+  long long tiles = 0;
+  for (int l = 0; l < lv.n_levels; ++l) {
+    int th, tw;
+    conv_pick_tile(lv.h[l], lv.w[l], &th, &tw);
+    tiles += (long long)lv.n_images * ceil_div(lv.w[l], tw) * ceil_div(lv.h[l], th);
+  }
+  return tiles * 4 * 64 * 4 + 256;
+}
+
+extern "C" int scan_conv3x3_rows_gn(const scan_levels_t* levels, const float* x_rows, const float* x_lo, int32_t cin, const float* packed,
+                                    const float* packed_lo, const float* gn_bias, float eps, float* y_rows, float* stats, int32_t cta_group,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!stats || !workspace || workspace_bytes < scan_conv3x3_gn_workspace_bytes(levels)) return SCAN_EINVAL;
+  float* partial = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  ConvGnGeo geo = {};
+  int rc = conv_rows_impl(levels, x_rows, x_lo, cin, nullptr, nullptr, 0, packed, packed_lo, 256, nullptr, nullptr, nullptr, 0, y_rows, 256,
+                          cta_group, 9, stream, partial, gn_bias, &geo);
+  if (rc) return rc;
+  const int n_stats = geo.n_levels * geo.n_images * 32;
+  conv_gn_finalize_kernel<<<(n_stats + 7) / 8, 256, 0, (cudaStream_t)stream>>>(geo, partial, eps, stats);
+  SCAN_LAUNCH_CHECK("conv_gn_finalize_kernel");
+  return SCAN_OK;
 }
 
 // ---------------------------------------------------------------------------- weight gradient: host side

@@ -96,8 +96,8 @@ class FCOSDiscriminator_con(nn.Module):
         layers = list(self.dis_tower)
         for i in range(0, len(layers), 3):
             conv, gn = layers[i], layers[i + 1]
-            x = _tower_conv(geo, conv.weight, None, x)
-            x = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, x, conv_bias=conv.bias)
+            x, stats = _tower_conv(geo, conv.weight, None, x, gn=(conv.bias, gn.eps))
+            x = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, x, conv_bias=conv.bias, stats=stats)
         x_rows = ops.join_rows(geo, x)
         maps32 = ops.thin_pack_maps(geo, act_maps, 0 if self.use_bg else 1, self.num_classes)
         w1, b1, w2, b2 = self._dense_weights()

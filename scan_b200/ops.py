@@ -4,6 +4,7 @@ torch is plumbing here (device memory, streams, autograd bookkeeping); the arith
 libscan_b200.so.  Every op raises if its input is not a CUDA tensor: there is no CPU fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -215,53 +216,61 @@ class _GnReluLevels(torch.autograd.Function):
     produced x: folded in here so that the convolution runs bias-free and its bias gradient is a by-product."""
 
     @staticmethod
-    def forward(ctx, geo, gamma, beta, conv_bias, eps, *xs):
+    def forward(ctx, geo, gamma, beta, conv_bias, eps, stats, *xs):
         xs = [nhwc_dense(x) for x in xs]
         dev = xs[0].device
         gamma, beta = gamma.contiguous(), beta.contiguous()
         conv_bias = None if conv_bias is None else conv_bias.contiguous()
         y_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)
-        stats = torch.empty((len(xs) * geo.n_images * 32 * 2,), device=dev, dtype=torch.float32)
-        ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
-        call("scan_gn_relu_fwd", geo.ref(), _ptr_array(xs), _ptr(conv_bias), _ptr(gamma), _ptr(beta), float(eps), _ptr(y_rows),
-             _ptr(stats), _ptr(ws), ws.numel(), _stream())
+        if stats is not None:     # statistics from the convolution's epilogue (conv3x3_levels(..., gn=...)): apply pass only
+            call("scan_gn_relu_apply", geo.ref(), _ptr_array(xs), _ptr(conv_bias), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(y_rows),
+                 _stream())
+        else:
+            stats = torch.empty((len(xs) * geo.n_images * 32 * 2,), device=dev, dtype=torch.float32)
+            ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
+            call("scan_gn_relu_fwd", geo.ref(), _ptr_array(xs), _ptr(conv_bias), _ptr(gamma), _ptr(beta), float(eps), _ptr(y_rows),
+                 _ptr(stats), _ptr(ws), ws.numel(), _stream())
         ctx.geo = geo
         ctx.has_cbias = conv_bias is not None
-        ctx.save_for_backward(gamma, stats, y_rows, gamma if conv_bias is None else conv_bias, *xs)
+        ctx.save_for_backward(gamma, stats, beta, gamma if conv_bias is None else conv_bias, *xs)
         return tuple(level_views(geo, y_rows))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *d_levels):
         geo = ctx.geo
-        gamma, stats, y_rows, cbias = ctx.saved_tensors[:4]
+        gamma, stats, beta, cbias = ctx.saved_tensors[:4]
         xs = ctx.saved_tensors[4:]
-        dev = y_rows.device
+        dev = gamma.device
         if not ctx.has_cbias:
             cbias = None
         dys = [nhwc_dense(g) if g is not None else torch.zeros_like(x) for g, x in zip(d_levels, xs)]
-        dx_rows = torch.empty_like(y_rows)
+        dx_rows = torch.empty((geo.R, C), device=dev, dtype=torch.float32)     # y is not read: the kernels recompute the ReLU mask
         dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
         dcb = torch.empty_like(gamma) if cbias is not None else None
         ws = torch.empty((_lib.lib().scan_gn_workspace_bytes(geo.ref()),), device=dev, dtype=torch.uint8)
-        call("scan_gn_relu_bwd", geo.ref(), _ptr_array(xs), _ptr_array(dys), _ptr(cbias), _ptr(y_rows), _ptr(gamma), _ptr(stats),
+        call("scan_gn_relu_bwd", geo.ref(), _ptr_array(xs), _ptr_array(dys), _ptr(cbias), _ptr(gamma), _ptr(beta), _ptr(stats),
              _ptr(dx_rows), _ptr(dgamma), _ptr(dbeta), _ptr(dcb), _ptr(ws), ws.numel(), _stream())
-        return (None, dgamma, dbeta, dcb, None) + tuple(level_views(geo, dx_rows))
+        return (None, dgamma, dbeta, dcb, None, None) + tuple(level_views(geo, dx_rows))
 
 
-def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None):
+def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None, stats=None):
+    """stats: the [L*N*32, 2] (mean, rstd) array conv3x3_levels(..., gn=(conv_bias, eps)) returned for these xs, or None (the
+    kernels then take a statistics pass of their own)."""
     if gamma.numel() != C:
         raise RuntimeError("the GroupNorm kernel is built for %d channels in 32 groups" % C)
     for x in xs:
         if not x.is_cuda or x.dtype != torch.float32 or x.shape[1] != C:
             raise RuntimeError("gn_relu_levels expects CUDA fp32 [N,%d,H,W] tensors (no CPU fallback)" % C)
-    return list(_GnReluLevels.apply(geo, gamma, beta, conv_bias, eps, *xs))
+    return list(_GnReluLevels.apply(geo, gamma, beta, conv_bias, eps, stats, *xs))
 
 
 # ----------------------------------------------------------------------------------------------------
 # f1: tower convolutions as a tcgen05 implicit GEMM on the rows layout (csrc/tower.cu)
 # ----------------------------------------------------------------------------------------------------
-CONV = {"cta_group": 2, "precise": False}     # precise = 3xTF32 (fp32-accurate; the parity runs), else single-pass TF32
+CONV = {"cta_group": 2, "precise": False,     # precise = 3xTF32 (fp32-accurate; the parity runs), else single-pass TF32
+        # GroupNorm statistics as a by-product of the tower convolution's epilogue (SCAN_B200_GN_STATS=0: separate statistics pass)
+        "gn_stats": os.environ.get("SCAN_B200_GN_STATS", "1") != "0"}
 
 
 _WORKSPACES = {}
@@ -345,21 +354,36 @@ class _Conv3x3Levels(torch.autograd.Function):
     Inputs / outputs are per-level channels_last views of rows buffers."""
 
     @staticmethod
-    def forward(ctx, geo, weight, *levels):
+    def forward(ctx, geo, weight, gn, *levels):
+        """gn = None | (conv_bias | None, eps): also return the GroupNorm(32) statistics of (y + conv_bias) as a last,
+        non-differentiable output (the dependence of the statistics on y is part of _GnReluLevels' backward formula)."""
         precise = CONV["precise"]
         x_rows = _rows_of_levels(geo, levels)
         hi, lo = conv3x3_pack(weight, False, precise)
         x_lo = tf32_residual(x_rows) if precise else None
-        y_rows = conv3x3_rows_raw(geo, x_rows, hi, weight.shape[0], x_lo=x_lo, packed_lo=lo)
-        ctx.geo, ctx.precise = geo, precise
+        ctx.geo, ctx.precise, ctx.with_stats = geo, precise, gn is not None
         ctx.save_for_backward(x_rows, weight)
         ctx.x_lo = x_lo
-        return tuple(_level_views_c(geo, y_rows))
+        if gn is None:
+            y_rows = conv3x3_rows_raw(geo, x_rows, hi, weight.shape[0], x_lo=x_lo, packed_lo=lo)
+            return tuple(_level_views_c(geo, y_rows))
+        gn_bias, eps = gn
+        gn_bias = None if gn_bias is None else gn_bias.detach().contiguous()
+        y_rows = torch.empty((geo.R, C), device=x_rows.device, dtype=torch.float32)
+        stats = torch.empty((len(levels) * geo.n_images * 32 * 2,), device=x_rows.device, dtype=torch.float32)
+        nbytes = _lib.lib().scan_conv3x3_gn_workspace_bytes(geo.ref())
+        ws = _workspace("conv_gn", nbytes, x_rows.device)
+        call("scan_conv3x3_rows_gn", geo.ref(), _ptr(x_rows), _ptr(x_lo), x_rows.shape[1], _ptr(hi), _ptr(lo), _ptr(gn_bias), float(eps),
+             _ptr(y_rows), _ptr(stats), CONV["cta_group"], _ptr(ws), nbytes, _stream())
+        ctx.mark_non_differentiable(stats)
+        return tuple(_level_views_c(geo, y_rows)) + (stats,)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, *d_levels):
         geo, precise = ctx.geo, ctx.precise
+        if ctx.with_stats:
+            d_levels = d_levels[:-1]
         x_rows, weight = ctx.saved_tensors
         d_levels = [g if g is not None else torch.zeros((geo.n_images, weight.shape[0], h, w), device=x_rows.device).contiguous(
             memory_format=torch.channels_last) for g, (h, w) in zip(d_levels, geo.shapes)]
@@ -375,17 +399,24 @@ class _Conv3x3Levels(torch.autograd.Function):
             hi, lo = conv3x3_pack(weight, True, precise)
             dx_rows = conv3x3_rows_raw(geo, dy_rows, hi, weight.shape[1], x_lo=dy_lo, packed_lo=lo)
             d_x = tuple(_level_views_c(geo, dx_rows))
-        return (None, d_w) + d_x
+        return (None, d_w, None) + d_x
 
 
-def conv3x3_levels(geo, weight, levels):
-    """Tower convolution (no bias) of per-level [N,Cin,H,W] CUDA tensors -> per-level channels_last views of one rows buffer."""
+def conv3x3_levels(geo, weight, levels, gn=None):
+    """Tower convolution (no bias) of per-level [N,Cin,H,W] CUDA tensors -> per-level channels_last views of one rows buffer.
+    gn = (conv_bias | None, eps) and 256 output channels: returns (levels, stats) with the GroupNorm(32) statistics of
+    (y + conv_bias) for gn_relu_levels(..., stats=stats)."""
     if weight.shape[2:] != (3, 3) or weight.shape[0] % 256 or weight.shape[1] % 256:
         raise RuntimeError("conv3x3_levels is built for 3x3 kernels with channel counts in multiples of 256")
     for x in levels:
         if not x.is_cuda or x.dtype != torch.float32 or x.shape[1] != weight.shape[1]:
             raise RuntimeError("conv3x3_levels expects CUDA fp32 [N,%d,H,W] tensors (no CPU fallback)" % weight.shape[1])
-    return list(_Conv3x3Levels.apply(geo, weight, *levels))
+    if gn is not None:
+        if weight.shape[0] != C:
+            raise RuntimeError("GroupNorm statistics from the convolution epilogue need %d output channels" % C)
+        out = _Conv3x3Levels.apply(geo, weight, gn, *levels)
+        return list(out[:-1]), out[-1]
+    return list(_Conv3x3Levels.apply(geo, weight, None, *levels))
 
 
 class _AddReluLevels(torch.autograd.Function):

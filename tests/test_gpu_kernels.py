@@ -889,6 +889,52 @@ def test_conv3x3_rows_matches_fp64_conv(shapes, n, cta_group):
     assert float((y.double() - torch.relu(ref + add.double())).abs().max()) <= 5e-6 * scale
 
 
+@pytest.mark.parametrize("precise", [False, True])
+@pytest.mark.parametrize("shapes,n", [([(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 3), ([(100, 168), (50, 84)], 2), ([(9, 5)], 1), ([(1, 1)], 1)])
+def test_conv3x3_epilogue_group_norm_statistics(shapes, n, precise):
+    """f1: the GroupNorm(32) statistics that come out of the tower convolution's epilogue (scan_conv3x3_rows_gn: per-warp partial
+    sums over real pixels only, fp64 combination) against float64 statistics of the SAME output tensor + bias, and the
+    normalised result against the kernels' own statistics pass; forward + backward through both operators."""
+    torch.manual_seed(21)
+    geo = ops.Geometry(shapes, STRIDES[:len(shapes)], n)
+    xs = [torch.randn(n, 256, h, w, device=DEV).contiguous(memory_format=torch.channels_last) for h, w in shapes]
+    w = (torch.randn(256, 256, 3, 3, device=DEV) * 0.02).requires_grad_(True)
+    cb = (torch.randn(256, device=DEV) * 0.3).requires_grad_(True)
+    gamma, beta = torch.randn(256, device=DEV).requires_grad_(True), (torch.randn(256, device=DEV) * 0.1).requires_grad_(True)
+    saved = ops.CONV["precise"]
+    ops.CONV["precise"] = precise
+    try:
+        res = {}
+        for fused in (True, False):
+            xi = [x.clone().requires_grad_(True) for x in xs]
+            if fused:
+                ys, stats = ops.conv3x3_levels(geo, w, xi, gn=(cb, 1e-5))
+                assert stats.shape == (len(shapes) * n * 32 * 2,) and not stats.requires_grad
+                for l, y in enumerate(ys):      # float64 statistics of the very tensor the kernel wrote
+                    v = (y.detach().double() + cb.detach().double().view(1, -1, 1, 1)).reshape(n, 32, -1)
+                    mean, var = v.mean(-1), v.var(-1, unbiased=False)
+                    got = stats.view(len(shapes), n, 32, 2)[l].double()
+                    scale = float(v.abs().max())
+                    assert float((got[..., 0] - mean).abs().max()) <= 2e-6 * scale, "mean l%d" % l
+                    rstd = 1.0 / torch.sqrt(var + 1e-5)
+                    assert float(((got[..., 1] - rstd) / rstd).abs().max()) <= 2e-5, "rstd l%d" % l
+            else:
+                ys, stats = ops.conv3x3_levels(geo, w, xi), None
+            hs = ops.gn_relu_levels(geo, gamma, beta, 1e-5, ys, conv_bias=cb, stats=stats)
+            # d(loss)/dh vanishes at h = 0: a ReLU mask that flips on a last-bit difference of the statistics changes nothing
+            loss = sum((h * h * torch.cos(h.detach() * 3.0)).sum() for h in hs)
+            grads = torch.autograd.grad(loss, [w, cb, gamma, beta] + xi)
+            res[fused] = ([h.detach() for h in hs], grads)
+        for a, b in zip(res[True][0], res[False][0]):
+            _close(a, b, 2e-5, "normalised output")
+        # single-pass TF32: a last-bit difference of an input moves it across a truncation boundary of the tensor core's operand
+        # read (2^-10 relative), so the two runs agree to the TF32 bound only; 3xTF32 runs agree to fp32 rounding
+        for i, (a, b) in enumerate(zip(res[True][1], res[False][1])):
+            _close(a, b, 1e-4 if precise else 2e-3, "gradient %d" % i)
+    finally:
+        ops.CONV["precise"] = saved
+
+
 @pytest.mark.parametrize("shapes,n", [([(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)], 3), ([(100, 168), (50, 84)], 2), ([(9, 5)], 1)])
 def test_conv3x3_wgrad_matches_fp64(shapes, n):
     """f1 weight-gradient kernel (MN-major operands, CTA pairs, deterministic split over pixel segments) against the fp64
