@@ -90,16 +90,16 @@ class GRAPHHead(nn.Module):
         while i < len(layers):
             conv = layers[i]
             i += 1
-            w = conv.weight.contiguous(memory_format=torch.channels_last)
             if i + 1 < len(layers) and isinstance(layers[i], nn.GroupNorm) and isinstance(layers[i + 1], nn.ReLU) \
                     and layers[i].num_groups == 32:
                 gn = layers[i]
                 i += 2
                 # bias-free convolution: the GroupNorm kernel adds the bias and returns its gradient as a by-product
                 # (and takes its statistics from the convolution's epilogue when that is the tcgen05 kernel)
-                outs, stats = _tower_conv(geo, conv.weight, w, h, gn=(conv.bias, gn.eps))
+                outs, stats = _tower_conv(geo, conv.weight, None, h, gn=(conv.bias, gn.eps))
                 h = ops.gn_relu_levels(geo, gn.weight, gn.bias, gn.eps, outs, conv_bias=conv.bias, stats=stats)
             else:   # IN / BN variants and the norm-free head_out: torch modules (not used by the shipped configs' head_in)
+                w = conv.weight.contiguous(memory_format=torch.channels_last)
                 outs = [F.conv2d(ops.nhwc_dense(x), w, conv.bias, padding=1) for x in h]
                 while i < len(layers) and not isinstance(layers[i], nn.Conv2d):
                     outs = [layers[i](o) for o in outs]
