@@ -30,3 +30,24 @@ def test_product_arm_metric_matches_baseline_json():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert "images/s" in src and "images/s" in json.dumps(base)
+
+
+def test_roofline_work_model_names_real_entry_points():
+    """Every row of bench.py's work model is a C-ABI entry point (scan_<name> in the ctypes table) or a `*_span` pseudo entry, and
+    maps to a kernel name for the grouped roofline line where one is declared: a renamed entry point cannot silently drop out of
+    the roofline table.  The GroupNorm rows count the streams the kernels actually move (2 forward, 5 backward per pixel row)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from scan_b200 import _lib
+    work = bench.work_model(8, 9, 8888, 7464, [34000, 8500, 2100, 520, 120])
+    for name, (bound, amount) in work.items():
+        assert bound in ("hbm", "tensor") and amount > 0, name
+        assert name.endswith("_span") or ("scan_" + name) in _lib.SIGNATURES, name
+    for name in bench.DOMINANT_KERNEL:
+        assert name in work, name
+    rows_bytes = 8 * bench.L_PER_IMAGE * 1024
+    assert work["gn_relu_apply"][1] == 2 * 2 * 2 * rows_bytes        # 2 passes x 2 layers x (1 read + 1 write)
+    assert work["gn_relu_bwd"][1] == 2 * 2 * 5 * rows_bytes          # x and dy read twice, dx written
+    # the head_in forward launches move to the statistics-carrying entry point; the flops of the group stay the same
+    total = work["conv3x3_rows"][1] + work["conv3x3_rows_gn"][1]
+    assert total == 2 * 5 * (2 * 8 * bench.L_PER_IMAGE * 256 * 256 * 9)
